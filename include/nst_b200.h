@@ -1,0 +1,164 @@
+/*
+ * nst_b200.h - C ABI of the B200-native neural-style-transfer hot path.
+ *
+ * The reference (msmink01/text-based-image-style-transfer) has no FFI of its own: its boundary is the
+ * Python import `from multi_style_transfer.run_style_transfer import run_multi_style_transfer`
+ * (app.py:36).  This header is what our Python mirror of that package binds through ctypes; every
+ * entry point names the reference code it replaces.  Plain C: device pointers are `void*`/`float*`
+ * into CUDA memory owned by the caller (torch tensors), `stream` is a `cudaStream_t` passed as
+ * `void*` (NULL = default stream).  All functions return 0 on success and a negative code on failure;
+ * `nst_last_error()` returns the message of the calling thread's last failure.
+ *
+ * There is no CPU path: every compute entry fails with NST_ERR_DEVICE unless the current device is
+ * compute capability 10.x.
+ */
+#ifndef NST_B200_H
+#define NST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NST_ABI_VERSION 1
+
+#define NST_MAX_CONV 16  /* conv1_1 .. conv5_4 of torchvision VGG-19 `features` */
+#define NST_OK 0
+#define NST_ERR_ARG -1
+#define NST_ERR_CUDA -2
+#define NST_ERR_DEVICE -3
+#define NST_ERR_STATE -4
+#define NST_ERR_UNSUPPORTED -5
+
+typedef struct nst_net nst_net;   /* VGG-19 trunk: repacked weights (fp16 forward, bf16 data-gradient) */
+typedef struct nst_plan nst_plan; /* per-resolution activations, tensor maps, targets, optimizer state */
+
+/* loss vector written by nst_plan_eval / read back by nst_lbfgs_status (floats) */
+enum {
+  NST_LOSS_TOTAL = 0, /* run_style_transfer.py:139 */
+  NST_LOSS_CONTENT_W = 1,
+  NST_LOSS_STYLE_W = 2,
+  NST_LOSS_TV_W = 3,
+  NST_LOSS_EDGE_W = 4,
+  NST_LOSS_GRAM0 = 5, /* 5..9: un-weighted per-layer Gram MSE (style_transfer_losses.py:138-144) */
+  NST_LOSS_CONTENT = 10,
+  NST_LOSS_STYLE = 11,
+  NST_LOSS_TV = 12,
+  NST_LOSS_EDGE = 13,
+  NST_LOSS_COUNT = 16
+};
+
+typedef struct nst_status {
+  int n_iter;        /* torch LBFGS state['n_iter'] */
+  int func_evals;    /* state['func_evals'] */
+  int closure_calls; /* iter[0] of run_style_transfer.py:99 */
+  int stop;          /* 0 = the step ran to max_iter; else the reason it ended early (lbfgs_ctl.h) */
+  int hist_len;
+  int reserved;
+  double loss, prev_loss, t, H_diag, gtd, gmax, max_td;
+  float losses[NST_LOSS_COUNT];
+} nst_status;
+
+int nst_abi_version(void);
+const char* nst_last_error(void);
+/* 0 when the current CUDA device can run this library (sm_100), NST_ERR_DEVICE otherwise */
+int nst_device_check(void);
+
+/* ---- VGG-19 trunk ------------------------------------------------------------------------------
+ * Replaces Vgg19.__init__ (helper_functions.py:44-92): `weights[i]` / `biases[i]` are device pointers
+ * to conv i's torch-layout fp32 parameters ([Cout,Cin,3,3], [Cout]) for the first `n_conv` convs of
+ * torchvision's vgg19().features.  Parameters are copied and repacked; the caller may free them. */
+int nst_net_create(nst_net** out, const float* const* weights, const float* const* biases, int n_conv, void* stream);
+void nst_net_destroy(nst_net* net);
+
+/* ---- plan --------------------------------------------------------------------------------------
+ * tap_mask: bit i set = conv i's pre-ReLU output is kept (Vgg19.forward's dict, helper_functions.py:94-101)
+ * style_mask / content_mask: subsets of tap_mask that carry a Gram / content target.
+ * with_grad != 0 also allocates the backward buffers and the L-BFGS state (history pairs). */
+int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
+                    uint32_t content_mask, int with_grad);
+void nst_plan_destroy(nst_plan* plan);
+/* bytes of device memory the plan holds */
+size_t nst_plan_bytes(const nst_plan* plan);
+
+/* normalize() constants (style_transfer_losses.py:9-28) and loss weights (run_style_transfer.py:115-139) */
+int nst_plan_set_norm(nst_plan* plan, const float mean[3], const float std[3]);
+int nst_plan_set_weights(nst_plan* plan, float w_style, float w_content, float w_tv, float w_edge);
+
+/* Vgg19.forward(normalize(x)): x = [3,H,W] fp32 device; taps stay resident as NHWC fp16 */
+int nst_plan_features(nst_plan* plan, const float* x, void* stream);
+int nst_plan_tap_shape(const nst_plan* plan, int conv, int* C, int* H, int* W);
+/* pre-ReLU feature of conv `conv` as [C,H,W] fp32 (torch layout) */
+int nst_plan_get_tap(nst_plan* plan, int conv, float* out_chw, void* stream);
+/* gram_matrix (style_transfer_losses.py:70-95) of a resident tap -> [C,C] fp32 */
+int nst_plan_tap_gram(nst_plan* plan, int conv, float* out, void* stream);
+/* gram_matrix of an arbitrary [C,H,W] fp32 device tensor (b = 1) -> [C,C] fp32 */
+int nst_gram_chw(const float* x, int C, int H, int W, float* out, void* stream);
+/* StyleMixer(...).mix() (StyleMixer.py:25-38) of the same tap of two plans, then gram_matrix -> [C,C] fp32 */
+int nst_style_mix_gram(nst_plan* a, nst_plan* b, int conv, float weight_b, float* out, void* stream);
+/* StyleMixer(...).mix() alone -> [C,Ho,Wo] fp32; Ho = Ha + Hb/2, Wo = Wa + Wb/2 */
+int nst_style_mix_chw(nst_plan* a, nst_plan* b, int conv, float weight_b, float* out_chw, void* stream);
+
+/* targets of the optimisation */
+int nst_plan_set_style_target(nst_plan* plan, int conv, const float* gram /* [C,C] device */, void* stream);
+/* content target = resident tap of `src` (same resolution) times an optional per-channel gate
+ * (channel_att_per_chosen_layers, run_style_transfer.py:13-25) */
+int nst_plan_set_content_target(nst_plan* plan, int conv, nst_plan* src, const float* gate /* [C] or NULL */,
+                                void* stream);
+/* ChannelAttention.forward's gate (ChannelAttention.py:30-37) from the resident tap: w1 [C/r,C], w2 [C,C/r] */
+int nst_plan_channel_gate(nst_plan* plan, int conv, const float* w1, const float* w2, int reduction,
+                          float* gate_out /* [C] device */, void* stream);
+/* get_gradient_imgs(to_grayscale(normalize(content))) (run_style_transfer.py:73-74) */
+int nst_plan_set_edge_target(nst_plan* plan, const float* content /* [3,H,W] device */, void* stream);
+
+/* the closure (run_style_transfer.py:102-148) at x: losses -> NST_LOSS_COUNT floats, gradient -> [3,H,W]
+ * (either may be NULL; both device pointers) */
+int nst_plan_eval(nst_plan* plan, const float* x, float* losses, float* grad, void* stream);
+
+/* individual loss terms on device tensors (function-level mirror of style_transfer_losses.py) */
+int nst_tv_edge(const float* x, const float* edge_target /* [2,H,W] or NULL */, int H, int W, const float mean[3],
+                const float std[3], float* out2 /* device: tv, edge */, void* stream);
+int nst_edge_images(const float* gray_or_rgb, int channels, int H, int W, float* out /* [2,H,W] */, void* stream);
+
+/* normalize (style_transfer_losses.py:9-28) of `planes` = b*3 planes of H*W */
+int nst_normalize(const float* x, float* y, int planes, int C, int H, int W, const float mean[3], const float std[3],
+                  void* stream);
+/* to_grayscale (helper_functions.py:104-113): [C,H,W] -> [H,W] */
+int nst_grayscale(const float* x, float* y, int C, int H, int W, void* stream);
+/* nn.MSELoss(reduction='mean') of two equally shaped tensors -> device scalar */
+int nst_mse(const float* a, const float* b, size_t n, float* out, void* stream);
+/* total_variation_loss (style_transfer_losses.py:149-174) of `planes` = b*c planes -> device scalar */
+int nst_total_variation(const float* y, int planes, int H, int W, float* out, void* stream);
+/* ChannelAttention.forward (ChannelAttention.py:23-40) on a [C,H,W] tensor */
+int nst_channel_attention_chw(const float* x, int C, int H, int W, const float* w1, const float* w2, int reduction,
+                              float* y, void* stream);
+/* StyleMixer.mix (StyleMixer.py:25-38) on two [C,H,W] tensors -> [C, Ha + Hb/2, Wa + Wb/2] */
+int nst_style_mix_tensors(const float* a, int Ha, int Wa, const float* b, int Hb, int Wb, int C, float weight_b,
+                          float* out, void* stream);
+
+/* ---- L-BFGS (torch.optim.LBFGS defaults; run_style_transfer.py:90,99-151) ------------------------ */
+int nst_lbfgs_init(nst_plan* plan, const float* x0 /* [3,H,W] device */, int trace_capacity, void* stream);
+/* one optimizer.step(closure): up to 20 evaluations enqueued without host synchronisation */
+int nst_lbfgs_step(nst_plan* plan, void* stream);
+/* synchronises the stream and copies the control block */
+int nst_lbfgs_status(nst_plan* plan, nst_status* out, void* stream);
+/* current iterate, clamped to [0,1] (run_style_transfer.py:153-155) -> [3,H,W] fp32 device */
+int nst_lbfgs_get_x(nst_plan* plan, float* out, void* stream);
+/* per-evaluation loss rows {total, content, style, tv, edge} (weighted); returns rows copied */
+int nst_lbfgs_trace(nst_plan* plan, float* host_out, int max_rows, void* stream);
+/* number of kernels one nst_lbfgs_step enqueues (for launch accounting) */
+int nst_lbfgs_launches_per_step(const nst_plan* plan);
+
+/* ---- host-buffer convenience (the e2e path: copies inside) ---------------------------------------
+ * content_u8: [H,W,3] uint8 host; out_u8: [H,W,3] uint8 host (truncating, like ToPILImage).
+ * Requires style / content / edge targets to be refreshed from the content image, which this call
+ * does (content target at the plan's content taps, edge target), then runs the whole loop. */
+int nst_run_frame_host(nst_plan* plan, const uint8_t* content_u8, uint8_t* out_u8, int num_steps, int channel_attention,
+                       const float* ca_w1, const float* ca_w2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NST_B200_H */

@@ -1,0 +1,1061 @@
+// C ABI of the library (include/nst_b200.h): VGG-19 trunk, per-resolution plan, the fused closure
+// evaluation and the device-resident L-BFGS loop.  Host-side orchestration only; every kernel lives in
+// conv_tc.cu / gram.cu / pixel.cu / lbfgs.cu.
+//
+// Reference call stack this file re-hosts (paths under /root/reference/multi_style_transfer/):
+//   run_multi_style_transfer   run_style_transfer.py:27-159
+//   closure                    run_style_transfer.py:102-148
+//   Vgg19.forward              helper_functions.py:94-101
+#include "../../include/nst_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "gram.cuh"
+#include "lbfgs.cuh"
+#include "pixel.cuh"
+
+using namespace nst;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) return fail(NST_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                        __FILE__, __LINE__);                                             \
+  } while (0)
+#define CKI(expr)                  \
+  do {                             \
+    int r__ = (expr);              \
+    if (r__ != NST_OK) return r__; \
+  } while (0)
+
+extern "C" int nst_abi_version(void) { return NST_ABI_VERSION; }
+extern "C" const char* nst_last_error(void) { return g_err; }
+
+static int g_num_sms = 0;
+extern "C" int nst_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(NST_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(NST_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(NST_ERR_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", dev,
+                prop.major, prop.minor);
+  if (g_num_sms == 0) {
+    e = conv_tc_init();
+    if (e == cudaSuccess) e = gram_init();
+    if (e != cudaSuccess) return fail(NST_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(e));
+    g_num_sms = prop.multiProcessorCount;
+  }
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// VGG-19 `features` configuration E (torchvision/models/vgg.py:94), first 16 convolutions
+// ------------------------------------------------------------------------------------------------
+static const int kCin[NST_MAX_CONV] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512};
+static const int kCout[NST_MAX_CONV] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512, 512};
+static const int kLevel[NST_MAX_CONV] = {0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+static const int kPoolAfter[NST_MAX_CONV] = {0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+struct nst_net {
+  int n_conv = 0;
+  float* w32[NST_MAX_CONV] = {};
+  float* b32[NST_MAX_CONV] = {};
+  __half* wf[NST_MAX_CONV] = {};         // [9][Cout][Cin]
+  __nv_bfloat16* wb[NST_MAX_CONV] = {};  // [9][Cin][Cout], taps flipped
+};
+
+extern "C" void nst_net_destroy(nst_net* net) {
+  if (!net) return;
+  for (int i = 0; i < NST_MAX_CONV; ++i) {
+    cudaFree(net->w32[i]);
+    cudaFree(net->b32[i]);
+    cudaFree(net->wf[i]);
+    cudaFree(net->wb[i]);
+  }
+  delete net;
+}
+
+extern "C" int nst_net_create(nst_net** out, const float* const* weights, const float* const* biases, int n_conv,
+                              void* stream) {
+  if (!out || !weights || !biases || n_conv < 1 || n_conv > NST_MAX_CONV) return fail(NST_ERR_ARG, "nst_net_create: bad arguments");
+  CKI(nst_device_check());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  nst_net* net = new nst_net();
+  net->n_conv = n_conv;
+  for (int i = 0; i < n_conv; ++i) {
+    const size_t nw = static_cast<size_t>(kCout[i]) * kCin[i] * 9;
+    cudaError_t e = cudaMalloc(&net->w32[i], nw * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&net->b32[i], kCout[i] * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(net->w32[i], weights[i], nw * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(net->b32[i], biases[i], kCout[i] * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && i >= 1) {
+      e = cudaMalloc(&net->wf[i], nw * sizeof(__half));
+      if (e == cudaSuccess) e = cudaMalloc(&net->wb[i], nw * sizeof(__nv_bfloat16));
+      if (e == cudaSuccess) e = launch_pack_weights(net->w32[i], net->wf[i], net->wb[i], kCout[i], kCin[i], s);
+    }
+    if (e != cudaSuccess) {
+      nst_net_destroy(net);
+      return fail(NST_ERR_CUDA, "nst_net_create: conv %d: %s", i, cudaGetErrorString(e));
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    nst_net_destroy(net);
+    return fail(NST_ERR_CUDA, "nst_net_create: %s", cudaGetErrorString(e));
+  }
+  *out = net;
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct nst_plan {
+  const nst_net* net = nullptr;
+  int H = 0, W = 0;
+  int n_layers = 0;
+  uint32_t tap_mask = 0, style_mask = 0, content_mask = 0;
+  int with_grad = 0;
+  int lh[5] = {}, lw[5] = {};  // resolution per pooling level
+  PixelConsts pc = {{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  float w_style = 0.f, w_content = 0.f, w_tv = 0.f, w_edge = 0.f;
+  size_t bytes = 0;
+  std::vector<void*> allocs;
+
+  // forward
+  __half* act[NST_MAX_CONV] = {};
+  __half* tap[NST_MAX_CONV] = {};
+  uint8_t* route[NST_MAX_CONV] = {};
+  ConvParams fwd[NST_MAX_CONV];
+  // backward
+  __nv_bfloat16* gpre[NST_MAX_CONV] = {};
+  __nv_bfloat16* gadd[NST_MAX_CONV] = {};
+  ConvParams dgrad[NST_MAX_CONV];
+  ConvParams scale[NST_MAX_CONV];
+  // style
+  int n_style = 0;
+  int style_conv[GRAM_MAX_LAYERS] = {};
+  float* style_target[GRAM_MAX_LAYERS] = {};
+  float* gdiff[GRAM_MAX_LAYERS] = {};
+  __half* dh[GRAM_MAX_LAYERS] = {};
+  float* alpha = nullptr;       // [GRAM_MAX_LAYERS]
+  float* style_loss = nullptr;  // [GRAM_MAX_LAYERS]
+  GramParams gram;
+  float* gram_ws = nullptr;
+  // content
+  int n_content = 0;
+  int content_conv[NST_MAX_CONV] = {};
+  float* content_target[NST_MAX_CONV] = {};
+  double* content_part = nullptr;
+  int content_part_off[NST_MAX_CONV + 1] = {};
+  // pixel
+  float* tedge = nullptr;
+  float* grad_pix = nullptr;
+  double* tv_part = nullptr;
+  double* edge_part = nullptr;
+  float* losses = nullptr;  // [NST_LOSS_COUNT]
+  // optimizer
+  LbfgsBuffers lb = {};
+  float* trace = nullptr;
+  int trace_cap = 0;
+  cudaGraphExec_t step_graph = nullptr;
+  int launches_per_step = 0;
+  // staging for nst_run_frame_host
+  uint8_t* u8_dev = nullptr;
+  float* img_dev = nullptr;
+  float* gate_dev = nullptr;
+  float* pooled_dev = nullptr;
+};
+
+static int plan_alloc(nst_plan* p, void** ptr, size_t bytes, bool zero) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  if (zero) {
+    e = cudaMemset(*ptr, 0, bytes);
+    if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+  }
+  p->allocs.push_back(*ptr);
+  p->bytes += bytes;
+  return NST_OK;
+}
+template <typename T>
+static int plan_alloc_t(nst_plan* p, T** ptr, size_t count, bool zero = false) {
+  return plan_alloc(p, reinterpret_cast<void**>(ptr), count * sizeof(T), zero);
+}
+
+static void drop_graph(nst_plan* p) {
+  if (p->step_graph) {
+    cudaGraphExecDestroy(p->step_graph);
+    p->step_graph = nullptr;
+  }
+}
+
+extern "C" void nst_plan_destroy(nst_plan* p) {
+  if (!p) return;
+  drop_graph(p);
+  for (void* a : p->allocs) cudaFree(a);
+  delete p;
+}
+extern "C" size_t nst_plan_bytes(const nst_plan* p) { return p ? p->bytes : 0; }
+
+static int style_index(const nst_plan* p, int conv) {
+  for (int l = 0; l < p->n_style; ++l)
+    if (p->style_conv[l] == conv) return l;
+  return -1;
+}
+static int content_index(const nst_plan* p, int conv) {
+  for (int l = 0; l < p->n_content; ++l)
+    if (p->content_conv[l] == conv) return l;
+  return -1;
+}
+
+static int build_conv_params(nst_plan* p) {
+  const nst_net* net = p->net;
+  for (int i = 1; i < p->n_layers; ++i) {
+    const int lv = kLevel[i];
+    const int H = p->lh[lv], W = p->lw[lv];
+    const bool pooled = kPoolAfter[i] && i < p->n_layers - 1;
+    // ---- forward
+    ConvParams& f = p->fwd[i];
+    memset(&f, 0, sizeof(f));
+    f.H = H;
+    f.W = W;
+    f.K = kCin[i];
+    f.N = kCout[i];
+    f.taps = 9;
+    if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
+    if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], conv_block_n(kCout[i])) != 0)
+      return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
+    f.bias = net->b32[i];
+    f.out_tap = p->tap[i];
+    f.out_act = p->act[i];
+    f.out_route = p->route[i];
+    f.pool = pooled ? 1 : 0;
+    conv_finalize_params(f, CONV_FWD);
+    if (!p->with_grad) continue;
+    // ---- data-gradient of conv i: consumes gpre[i], produces gpre[i-1]
+    ConvParams& d = p->dgrad[i];
+    memset(&d, 0, sizeof(d));
+    d.H = H;
+    d.W = W;
+    d.K = kCout[i];
+    d.N = kCin[i];
+    d.taps = 9;
+    if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
+    if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], conv_block_n(kCin[i])) != 0)
+      return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
+    const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
+    d.out_grad = p->gpre[i - 1];
+    if (prev_pooled) {
+      d.route = p->route[i - 1];
+      d.Hup = p->lh[kLevel[i - 1]];
+      d.Wup = p->lw[kLevel[i - 1]];
+    } else {
+      d.mask_act = p->act[i - 1];
+      d.addend = p->gadd[i - 1];
+    }
+    conv_finalize_params(d, CONV_DGRAD);
+  }
+  if (!p->with_grad) return NST_OK;
+  // ---- Gram backward as a 1x1 convolution: seed[l] = alpha_l * F_l * (G_l - T_l)/max|.|
+  for (int l = 0; l < p->n_style; ++l) {
+    const int i = p->style_conv[l];
+    const int lv = kLevel[i];
+    const int C = kCout[i];
+    ConvParams& c = p->scale[i];
+    memset(&c, 0, sizeof(c));
+    c.H = p->lh[lv];
+    c.W = p->lw[lv];
+    c.K = C;
+    c.N = C;
+    c.taps = 1;
+    if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
+    if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, conv_block_n(C)) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
+    c.alpha = p->alpha + l;
+    c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
+    conv_finalize_params(c, CONV_SCALE);
+  }
+  return NST_OK;
+}
+
+static int build_gram_params(nst_plan* p) {
+  GramParams& g = p->gram;
+  memset(&g, 0, sizeof(g));
+  g.num_layers = p->n_style;
+  for (int l = 0; l < p->n_style; ++l) {
+    const int i = p->style_conv[l];
+    const int lv = kLevel[i];
+    GramLayer& L = g.L[l];
+    L.C = kCout[i];
+    L.HW = p->lh[lv] * p->lw[lv];
+    L.inv_norm = 1.f / (static_cast<float>(L.C) * static_cast<float>(L.HW));
+    L.target = p->style_target[l];
+    L.gram_out = p->gdiff[l];
+    L.dh = p->dh[l];
+    L.alpha = p->alpha + l;
+    L.loss = p->style_loss + l;
+    // d/dF of w_s/n_style * mean((G-T)^2), G = F F^T / (C HW): 4 w_s (G-T) F / (n_style C^3 HW)
+    L.grad_coef = 4.f * p->w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) *
+                                      static_cast<float>(L.C) * static_cast<float>(L.C) * static_cast<float>(L.HW));
+    if (make_tmap_feat(&g.tm[l], p->tap[i], L.HW, L.C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
+  }
+  return NST_OK;
+}
+
+extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
+                               uint32_t content_mask, int with_grad) {
+  if (!out || !net || H < 1 || W < 1) return fail(NST_ERR_ARG, "nst_plan_create: bad arguments");
+  CKI(nst_device_check());
+  tap_mask |= style_mask | content_mask;
+  if (tap_mask == 0 || (tap_mask >> net->n_conv) != 0)
+    return fail(NST_ERR_ARG, "nst_plan_create: tap mask 0x%x outside the %d convolutions of the net", tap_mask, net->n_conv);
+  nst_plan* p = new nst_plan();
+  p->net = net;
+  p->H = H;
+  p->W = W;
+  p->tap_mask = tap_mask;
+  p->style_mask = style_mask;
+  p->content_mask = content_mask;
+  p->with_grad = with_grad ? 1 : 0;
+  int n_layers = 0;
+  for (int i = 0; i < NST_MAX_CONV; ++i)
+    if (tap_mask & (1u << i)) n_layers = i + 1;
+  p->n_layers = n_layers;
+  p->lh[0] = H;
+  p->lw[0] = W;
+  for (int l = 1; l < 5; ++l) {
+    p->lh[l] = p->lh[l - 1] / 2;  // MaxPool2d(2, 2), ceil_mode=False
+    p->lw[l] = p->lw[l - 1] / 2;
+  }
+  if (p->lh[kLevel[n_layers - 1]] < 1 || p->lw[kLevel[n_layers - 1]] < 1) {
+    delete p;
+    return fail(NST_ERR_ARG, "nst_plan_create: %dx%d is too small for conv index %d", H, W, n_layers - 1);
+  }
+#define PA(call)            \
+  do {                      \
+    int r__ = (call);       \
+    if (r__ != NST_OK) {    \
+      nst_plan_destroy(p);  \
+      return r__;           \
+    }                       \
+  } while (0)
+  for (int i = 0; i < n_layers; ++i) {
+    if (style_mask & (1u << i)) {
+      if (p->n_style == GRAM_MAX_LAYERS) {
+        nst_plan_destroy(p);
+        return fail(NST_ERR_UNSUPPORTED, "at most %d style layers", GRAM_MAX_LAYERS);
+      }
+      p->style_conv[p->n_style++] = i;
+    }
+    if (content_mask & (1u << i)) p->content_conv[p->n_content++] = i;
+  }
+  if (with_grad) {
+    const uint32_t tgt = style_mask | content_mask;
+    if (!(tgt & (1u << (n_layers - 1)))) {
+      nst_plan_destroy(p);
+      return fail(NST_ERR_ARG, "with_grad: the deepest tapped conv must carry a style or content target");
+    }
+    for (int i = 0; i < n_layers - 1; ++i)
+      if ((tgt & (1u << i)) && kPoolAfter[i]) {
+        nst_plan_destroy(p);
+        return fail(NST_ERR_UNSUPPORTED, "targets on a conv that is followed by a max-pool (conv index %d)", i);
+      }
+  }
+  // ---- activations
+  for (int i = 0; i < n_layers; ++i) {
+    const int lv = kLevel[i];
+    const size_t pix = static_cast<size_t>(p->lh[lv]) * p->lw[lv];
+    const int C = kCout[i];
+    const bool last = i == n_layers - 1;
+    const bool pooled = kPoolAfter[i] && !last;
+    if (tap_mask & (1u << i)) PA(plan_alloc_t(p, &p->tap[i], pix * C));
+    if (!last) {
+      const size_t opix = pooled ? static_cast<size_t>(p->lh[lv + 1]) * p->lw[lv + 1] : pix;
+      PA(plan_alloc_t(p, &p->act[i], opix * C));
+      if (pooled) PA(plan_alloc_t(p, &p->route[i], opix * C));
+    }
+    if (with_grad) {
+      PA(plan_alloc_t(p, &p->gpre[i], pix * C, true));
+      if (((style_mask | content_mask) & (1u << i)) && !last) PA(plan_alloc_t(p, &p->gadd[i], pix * C, true));
+    }
+  }
+  // ---- style / content / pixel state
+  PA(plan_alloc_t(p, &p->alpha, GRAM_MAX_LAYERS, true));
+  PA(plan_alloc_t(p, &p->style_loss, GRAM_MAX_LAYERS, true));
+  PA(plan_alloc_t(p, &p->losses, NST_LOSS_COUNT, true));
+  for (int l = 0; l < p->n_style; ++l) {
+    const size_t cc = static_cast<size_t>(kCout[p->style_conv[l]]) * kCout[p->style_conv[l]];
+    PA(plan_alloc_t(p, &p->style_target[l], cc, true));
+    PA(plan_alloc_t(p, &p->gdiff[l], cc, true));
+    PA(plan_alloc_t(p, &p->dh[l], cc, true));
+  }
+  int cpart = 0;
+  for (int l = 0; l < p->n_content; ++l) {
+    const int i = p->content_conv[l];
+    const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+    PA(plan_alloc_t(p, &p->content_target[l], numel, true));
+    p->content_part_off[l] = cpart;
+    cpart += content_blocks(numel);
+  }
+  p->content_part_off[p->n_content] = cpart;
+  PA(plan_alloc_t(p, &p->content_part, cpart > 0 ? cpart : 1, true));
+  const size_t n = static_cast<size_t>(3) * H * W;
+  PA(plan_alloc_t(p, &p->tedge, static_cast<size_t>(2) * H * W, true));
+  PA(plan_alloc_t(p, &p->grad_pix, n, true));
+  PA(plan_alloc_t(p, &p->tv_part, pixel_blocks(H, W), true));
+  PA(plan_alloc_t(p, &p->edge_part, pixel_blocks(H, W), true));
+  PA(build_gram_params(p));
+  if (p->n_style > 0) {
+    const size_t ws = gram_plan(p->gram, g_num_sms);
+    PA(plan_alloc_t(p, &p->gram_ws, ws));
+    p->gram.ws = p->gram_ws;
+    float* fin = nullptr;
+    PA(plan_alloc_t(p, &fin, static_cast<size_t>(2) * p->gram.num_fin_blocks));
+    p->gram.fin_part = fin;
+  }
+  // ---- optimizer
+  if (with_grad) {
+    LbfgsBuffers& b = p->lb;
+    b.n_pad = static_cast<int>((n + 3) / 4 * 4);
+    lbfgs_plan(b, g_num_sms);
+    PA(plan_alloc_t(p, &b.x, b.n_pad, true));
+    PA(plan_alloc_t(p, &b.g, b.n_pad, true));
+    PA(plan_alloc_t(p, &b.g_prev, b.n_pad, true));
+    PA(plan_alloc_t(p, &b.d, b.n_pad, true));
+    PA(plan_alloc_t(p, &b.S, static_cast<size_t>(NST_LBFGS_SLOTS) * b.n_pad, true));
+    PA(plan_alloc_t(p, &b.Y, static_cast<size_t>(NST_LBFGS_SLOTS) * b.n_pad, true));
+    PA(plan_alloc_t(p, &b.part, static_cast<size_t>(b.nblocks) * LB_PART_STRIDE, true));
+    PA(plan_alloc_t(p, &b.td_part, b.nblocks, true));
+    PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * 6, true));
+    PA(plan_alloc_t(p, &b.scal, NST_LBFGS_NSCAL, true));
+    PA(plan_alloc_t(p, &b.M, static_cast<size_t>(4) * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS, true));
+    PA(plan_alloc_t(p, &b.v, 2 * NST_LBFGS_SLOTS, true));
+    PA(plan_alloc_t(p, &b.ctl, 1, true));
+    b.eval_loss = p->losses;
+  }
+  PA(build_conv_params(p));
+#undef PA
+  *out = p;
+  return NST_OK;
+}
+
+extern "C" int nst_plan_set_norm(nst_plan* p, const float mean[3], const float std[3]) {
+  if (!p || !mean || !std) return fail(NST_ERR_ARG, "nst_plan_set_norm: bad arguments");
+  for (int c = 0; c < 3; ++c) {
+    p->pc.mean[c] = mean[c];
+    p->pc.stdv[c] = std[c];
+  }
+  drop_graph(p);
+  return NST_OK;
+}
+
+extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content, float w_tv, float w_edge) {
+  if (!p) return fail(NST_ERR_ARG, "nst_plan_set_weights: null plan");
+  p->w_style = w_style;
+  p->w_content = w_content;
+  p->w_tv = w_tv;
+  p->w_edge = w_edge;
+  for (int l = 0; l < p->n_style; ++l) {
+    GramLayer& L = p->gram.L[l];
+    L.grad_coef = 4.f * w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) * static_cast<float>(L.C) *
+                                   static_cast<float>(L.C) * static_cast<float>(L.HW));
+  }
+  drop_graph(p);
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward_enqueue(nst_plan* p, const float* x, cudaStream_t s) {
+  const nst_net* net = p->net;
+  CK(launch_conv1_fwd(x, net->w32[0], net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+  for (int i = 1; i < p->n_layers; ++i) CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
+  return NST_OK;
+}
+
+extern "C" int nst_plan_features(nst_plan* p, const float* x, void* stream) {
+  if (!p || !x) return fail(NST_ERR_ARG, "nst_plan_features: bad arguments");
+  return forward_enqueue(p, x, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nst_plan_tap_shape(const nst_plan* p, int conv, int* C, int* H, int* W) {
+  if (!p || conv < 0 || conv >= p->n_layers || !(p->tap_mask & (1u << conv))) return fail(NST_ERR_ARG, "conv %d is not tapped", conv);
+  if (C) *C = kCout[conv];
+  if (H) *H = p->lh[kLevel[conv]];
+  if (W) *W = p->lw[kLevel[conv]];
+  return NST_OK;
+}
+
+extern "C" int nst_plan_get_tap(nst_plan* p, int conv, float* out, void* stream) {
+  int C, H, W;
+  CKI(nst_plan_tap_shape(p, conv, &C, &H, &W));
+  if (!out) return fail(NST_ERR_ARG, "nst_plan_get_tap: null output");
+  CK(launch_nhwc_half_to_nchw_float(p->tap[conv], out, H, W, C, static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+// Gram of an NHWC fp16 [HW, C] matrix (C multiple of 64) -> [C, C] fp32, normalised by 1/(c_true * HW)
+static int gram_of(const __half* feat, int HW, int C, int c_true, float* out, cudaStream_t s) {
+  GramParams g;
+  memset(&g, 0, sizeof(g));
+  g.num_layers = 1;
+  GramLayer& L = g.L[0];
+  L.C = C;
+  L.HW = HW;
+  L.inv_norm = 1.f / (static_cast<float>(c_true) * static_cast<float>(HW));
+  L.gram_out = out;
+  if (make_tmap_feat(&g.tm[0], feat, HW, C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram)");
+  const size_t ws = gram_plan(g, g_num_sms);
+  float* wsp = nullptr;
+  float* fin = nullptr;
+  CK(cudaMalloc(&wsp, ws * sizeof(float)));
+  cudaError_t e = cudaMalloc(&fin, static_cast<size_t>(2) * g.num_fin_blocks * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(wsp);
+    return fail(NST_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+  }
+  g.ws = wsp;
+  g.fin_part = fin;
+  e = launch_gram(g, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(wsp);
+  cudaFree(fin);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "gram: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
+extern "C" int nst_plan_tap_gram(nst_plan* p, int conv, float* out, void* stream) {
+  int C, H, W;
+  CKI(nst_plan_tap_shape(p, conv, &C, &H, &W));
+  if (!out) return fail(NST_ERR_ARG, "nst_plan_tap_gram: null output");
+  return gram_of(p->tap[conv], H * W, C, C, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nst_gram_chw(const float* x, int C, int H, int W, float* out, void* stream) {
+  if (!x || !out || C < 1 || H < 1 || W < 1) return fail(NST_ERR_ARG, "nst_gram_chw: bad arguments");
+  CKI(nst_device_check());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Cp = (C + 63) / 64 * 64;
+  const size_t HW = static_cast<size_t>(H) * W;
+  __half* feat = nullptr;
+  float* tmp = nullptr;
+  CK(cudaMalloc(&feat, HW * Cp * sizeof(__half)));
+  cudaError_t e = cudaMemsetAsync(feat, 0, HW * Cp * sizeof(__half), s);
+  // rows of the padded matrix have stride Cp: convert plane by plane through the generic transpose
+  if (e == cudaSuccess && Cp != C) e = cudaMalloc(&tmp, static_cast<size_t>(Cp) * Cp * sizeof(float));
+  int rc = NST_OK;
+  if (e == cudaSuccess) {
+    if (Cp == C) {
+      e = launch_nchw_float_to_nhwc_half(x, feat, H, W, C, s);
+      if (e == cudaSuccess) rc = gram_of(feat, static_cast<int>(HW), Cp, C, out, s);
+    } else {
+      e = launch_nchw_float_to_nhwc_half_padded(x, feat, H, W, C, Cp, s);
+      if (e == cudaSuccess) rc = gram_of(feat, static_cast<int>(HW), Cp, C, tmp, s);
+      if (e == cudaSuccess && rc == NST_OK)
+        e = cudaMemcpy2DAsync(out, static_cast<size_t>(C) * sizeof(float), tmp, static_cast<size_t>(Cp) * sizeof(float),
+                              static_cast<size_t>(C) * sizeof(float), C, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+  }
+  cudaFree(feat);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_gram_chw: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+static int mix_common(nst_plan* a, nst_plan* b, int conv, float wb, __half** mixed, int* Ho, int* Wo, int* Cc,
+                      cudaStream_t s) {
+  int Ca, Ha, Wa, Cb, Hb, Wb;
+  CKI(nst_plan_tap_shape(a, conv, &Ca, &Ha, &Wa));
+  CKI(nst_plan_tap_shape(b, conv, &Cb, &Hb, &Wb));
+  // StyleMixer.py:31-32: np.array(shape_a) + np.array(shape_b) // 2  (operator precedence: Ha + Hb // 2)
+  *Ho = Ha + Hb / 2;
+  *Wo = Wa + Wb / 2;
+  *Cc = Ca;
+  CK(cudaMalloc(mixed, static_cast<size_t>(*Ho) * *Wo * Ca * sizeof(__half)));
+  cudaError_t e = launch_style_mix(a->tap[conv], Ha, Wa, b->tap[conv], Hb, Wb, *mixed, *Ho, *Wo, Ca, wb, s);
+  if (e != cudaSuccess) {
+    cudaFree(*mixed);
+    *mixed = nullptr;
+    return fail(NST_ERR_CUDA, "style mix: %s", cudaGetErrorString(e));
+  }
+  return NST_OK;
+}
+
+extern "C" int nst_style_mix_gram(nst_plan* a, nst_plan* b, int conv, float weight_b, float* out, void* stream) {
+  if (!a || !b || !out) return fail(NST_ERR_ARG, "nst_style_mix_gram: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __half* mixed = nullptr;
+  int Ho, Wo, C;
+  CKI(mix_common(a, b, conv, weight_b, &mixed, &Ho, &Wo, &C, s));
+  const int rc = gram_of(mixed, Ho * Wo, C, C, out, s);
+  cudaFree(mixed);
+  return rc;
+}
+
+extern "C" int nst_style_mix_chw(nst_plan* a, nst_plan* b, int conv, float weight_b, float* out_chw, void* stream) {
+  if (!a || !b || !out_chw) return fail(NST_ERR_ARG, "nst_style_mix_chw: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __half* mixed = nullptr;
+  int Ho, Wo, C;
+  CKI(mix_common(a, b, conv, weight_b, &mixed, &Ho, &Wo, &C, s));
+  cudaError_t e = launch_nhwc_half_to_nchw_float(mixed, out_chw, Ho, Wo, C, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(mixed);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_style_mix_chw: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// targets
+// ------------------------------------------------------------------------------------------------
+extern "C" int nst_plan_set_style_target(nst_plan* p, int conv, const float* gram, void* stream) {
+  if (!p || !gram) return fail(NST_ERR_ARG, "nst_plan_set_style_target: bad arguments");
+  const int l = style_index(p, conv);
+  if (l < 0) return fail(NST_ERR_ARG, "conv %d is not a style layer of this plan", conv);
+  const size_t cc = static_cast<size_t>(kCout[conv]) * kCout[conv];
+  CK(cudaMemcpyAsync(p->style_target[l], gram, cc * sizeof(float), cudaMemcpyDeviceToDevice,
+                     static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+extern "C" int nst_plan_set_content_target(nst_plan* p, int conv, nst_plan* src, const float* gate, void* stream) {
+  if (!p || !src) return fail(NST_ERR_ARG, "nst_plan_set_content_target: bad arguments");
+  const int l = content_index(p, conv);
+  if (l < 0) return fail(NST_ERR_ARG, "conv %d is not a content layer of this plan", conv);
+  int C, H, W, C2, H2, W2;
+  CKI(nst_plan_tap_shape(p, conv, &C, &H, &W));
+  CKI(nst_plan_tap_shape(src, conv, &C2, &H2, &W2));
+  if (H != H2 || W != W2) return fail(NST_ERR_ARG, "content target resolution %dx%d != plan %dx%d", H2, W2, H, W);
+  CK(launch_make_content_target(src->tap[conv], gate, p->content_target[l], static_cast<size_t>(H) * W, C,
+                                static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+extern "C" int nst_plan_channel_gate(nst_plan* p, int conv, const float* w1, const float* w2, int reduction,
+                                     float* gate_out, void* stream) {
+  int C, H, W;
+  CKI(nst_plan_tap_shape(p, conv, &C, &H, &W));
+  if (!w1 || !w2 || !gate_out || reduction < 1 || C % reduction != 0) return fail(NST_ERR_ARG, "nst_plan_channel_gate: bad arguments");
+  if (!p->pooled_dev) CKI(plan_alloc_t(p, &p->pooled_dev, 512, true));
+  CK(launch_channel_gate(p->tap[conv], w1, w2, p->pooled_dev, gate_out, static_cast<size_t>(H) * W, C, C / reduction,
+                         static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+extern "C" int nst_plan_set_edge_target(nst_plan* p, const float* content, void* stream) {
+  if (!p || !content) return fail(NST_ERR_ARG, "nst_plan_set_edge_target: bad arguments");
+  CK(launch_edge_target(content, p->tedge, p->H, p->W, p->pc, static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the closure
+// ------------------------------------------------------------------------------------------------
+static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
+                        cudaStream_t s) {
+  int nl = 0;
+  const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
+  CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s));
+  ++nl;
+  if (use_vgg) {
+    CKI(forward_enqueue(p, x, s));
+    nl += p->n_layers;
+    if (p->n_style > 0) {
+      CK(launch_gram(p->gram, s));
+      nl += 3;
+    }
+    for (int l = 0; l < p->n_content; ++l) {
+      const int i = p->content_conv[l];
+      const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+      // seed of the backward pass: d/dF of w_c/n_content * mean((F - Fc)^2).  A conv that is both a style
+      // and a content layer gets its Gram seed first (backward section), then this one in accumulate mode.
+      __nv_bfloat16* seed = nullptr;
+      if (grad != nullptr && style_index(p, i) < 0) seed = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
+      const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
+      CK(launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel,
+                             gcoef, 0, s));
+      ++nl;
+    }
+  }
+  LossAssembleArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tv_part = p->tv_part;
+  a.n_tv = pixel_blocks(p->H, p->W);
+  a.edge_part = p->edge_part;
+  a.n_edge = pixel_blocks(p->H, p->W);
+  a.content_part = p->content_part;
+  a.n_content = use_vgg ? p->content_part_off[p->n_content] : 0;
+  a.style_layer_loss = p->style_loss;
+  a.num_style = use_vgg ? p->n_style : 0;
+  a.w_style = p->w_style;
+  a.w_content = p->w_content;
+  a.w_tv = p->w_tv;
+  a.w_edge = p->w_edge;
+  a.tv_norm = 1.0 / (3.0 * p->H * p->W);
+  a.edge_norm = (p->H > 2 && p->W > 2) ? 1.0 / (static_cast<double>(p->H - 2) * (p->W - 2)) : 0.0;
+  if (p->n_content > 0) {
+    // all content layers are weighted equally by 1/(numel_l * n_content); with a single layer this is 1/numel
+    const int i = p->content_conv[0];
+    const double numel = static_cast<double>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+    a.content_norm = 1.0 / (numel * p->n_content);
+  }
+  a.out = p->losses;
+  a.counter = counter;
+  a.stop_flag = stop_flag;
+  a.trace = p->trace;
+  a.trace_cap = p->trace_cap;
+  CK(launch_loss_assemble(a, s));
+  ++nl;
+  if (grad != nullptr) {
+    if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
+    if (use_vgg) {
+      for (int l = 0; l < p->n_style; ++l) {
+        CK(launch_conv_tc(p->scale[p->style_conv[l]], CONV_SCALE, g_num_sms, s));
+        ++nl;
+      }
+      for (int l = 0; l < p->n_content; ++l) {
+        const int i = p->content_conv[l];
+        if (style_index(p, i) < 0) continue;
+        const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+        const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
+        __nv_bfloat16* seed = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
+        CK(launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel,
+                               gcoef, 1, s));
+        ++nl;
+      }
+      for (int i = p->n_layers - 1; i >= 1; --i) {
+        CK(launch_conv_tc(p->dgrad[i], CONV_DGRAD, g_num_sms, s));
+        ++nl;
+      }
+      CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
+      ++nl;
+    } else {
+      CK(cudaMemcpyAsync(grad, p->grad_pix, static_cast<size_t>(3) * p->H * p->W * sizeof(float),
+                         cudaMemcpyDeviceToDevice, s));
+      ++nl;
+    }
+  }
+  if (launches) *launches += nl;
+  return NST_OK;
+}
+
+extern "C" int nst_plan_eval(nst_plan* p, const float* x, float* losses, float* grad, void* stream) {
+  if (!p || !x) return fail(NST_ERR_ARG, "nst_plan_eval: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CKI(eval_enqueue(p, x, grad, nullptr, nullptr, nullptr, s));
+  if (losses) CK(cudaMemcpyAsync(losses, p->losses, NST_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// function-level mirrors
+// ------------------------------------------------------------------------------------------------
+__global__ void tv_edge_finish_kernel(const double* tv_part, const double* edge_part, int n, double tv_norm,
+                                      double edge_norm, float* out2) {
+  // single block of 32 threads: fixed-order sums
+  double tv = 0.0, ed = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) {
+    tv += tv_part[i];
+    ed += edge_part[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    tv += __shfl_xor_sync(0xffffffffu, tv, o);
+    ed += __shfl_xor_sync(0xffffffffu, ed, o);
+  }
+  if (threadIdx.x == 0) {
+    out2[0] = static_cast<float>(tv * tv_norm);
+    out2[1] = static_cast<float>(0.5 * ed * edge_norm);
+  }
+}
+
+extern "C" int nst_tv_edge(const float* x, const float* edge_target, int H, int W, const float mean[3],
+                           const float std[3], float* out2, void* stream) {
+  if (!x || !out2 || H < 1 || W < 1 || !mean || !std) return fail(NST_ERR_ARG, "nst_tv_edge: bad arguments");
+  CKI(nst_device_check());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PixelConsts pc;
+  for (int c = 0; c < 3; ++c) {
+    pc.mean[c] = mean[c];
+    pc.stdv[c] = std[c];
+  }
+  const int nb = pixel_blocks(H, W);
+  const size_t n = static_cast<size_t>(3) * H * W;
+  float* scratch = nullptr;
+  double* parts = nullptr;
+  float* tz = nullptr;
+  CK(cudaMalloc(&scratch, n * sizeof(float)));
+  cudaError_t e = cudaMalloc(&parts, static_cast<size_t>(2) * nb * sizeof(double));
+  if (e == cudaSuccess && !edge_target) {
+    e = cudaMalloc(&tz, static_cast<size_t>(2) * H * W * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemsetAsync(tz, 0, static_cast<size_t>(2) * H * W * sizeof(float), s);
+  }
+  if (e == cudaSuccess)
+    e = launch_pixel_losses(x, edge_target ? edge_target : tz, scratch, parts, parts + nb, H, W, pc, 1.f, 1.f, s);
+  if (e == cudaSuccess) {
+    const double en = (H > 2 && W > 2) ? 1.0 / (static_cast<double>(H - 2) * (W - 2)) : 0.0;
+    tv_edge_finish_kernel<<<1, 32, 0, s>>>(parts, parts + nb, nb, 1.0 / (3.0 * H * W), en, out2);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(scratch);
+  cudaFree(parts);
+  cudaFree(tz);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_tv_edge: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
+extern "C" int nst_edge_images(const float* img, int channels, int H, int W, float* out, void* stream) {
+  if (!img || !out || (channels != 1 && channels != 3)) return fail(NST_ERR_ARG, "nst_edge_images: channels must be 1 or 3");
+  CKI(nst_device_check());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PixelConsts pc = {{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  if (channels == 3) {
+    CK(launch_edge_target(img, out, H, W, pc, s));
+    return NST_OK;
+  }
+  // grayscale input: replicate the plane so that the channel mean returns it
+  float* tmp = nullptr;
+  const size_t plane = static_cast<size_t>(H) * W;
+  CK(cudaMalloc(&tmp, 3 * plane * sizeof(float)));
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < 3 && e == cudaSuccess; ++c)
+    e = cudaMemcpyAsync(tmp + c * plane, img, plane * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = launch_edge_target(tmp, out, H, W, pc, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_edge_images: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// L-BFGS loop
+// ------------------------------------------------------------------------------------------------
+__global__ void clamp_copy_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = fminf(fmaxf(in[i], 0.f), 1.f);
+}
+
+extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, void* stream) {
+  if (!p || !x0) return fail(NST_ERR_ARG, "nst_lbfgs_init: bad arguments");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LbfgsBuffers& b = p->lb;
+  const size_t n = static_cast<size_t>(3) * p->H * p->W;
+  if (trace_capacity > p->trace_cap) {
+    drop_graph(p);  // the trace pointer is baked into the captured evaluation
+    CKI(plan_alloc_t(p, &p->trace, static_cast<size_t>(trace_capacity) * 5, true));
+    p->trace_cap = trace_capacity;
+  }
+  NstLbfgsCtl h;
+  memset(&h, 0, sizeof(h));
+  h.lr = 1.0;
+  h.tol_grad = 1e-7;
+  h.tol_change = 1e-9;
+  h.history_size = NST_LBFGS_HISTORY;
+  h.H_diag = 1.0;
+  h.trace_cap = p->trace_cap;
+  CK(cudaMemcpyAsync(b.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // `h` lives on this stack frame
+  CK(cudaMemsetAsync(b.M, 0, static_cast<size_t>(4) * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS * sizeof(double), s));
+  CK(cudaMemsetAsync(b.v, 0, 2 * NST_LBFGS_SLOTS * sizeof(double), s));
+  CK(cudaMemsetAsync(b.x, 0, b.n_pad * sizeof(float), s));
+  CK(cudaMemsetAsync(b.g, 0, b.n_pad * sizeof(float), s));
+  CK(cudaMemsetAsync(b.g_prev, 0, b.n_pad * sizeof(float), s));
+  CK(cudaMemsetAsync(b.d, 0, b.n_pad * sizeof(float), s));
+  // the closure clamps before its first forward (run_style_transfer.py:108-109)
+  clamp_copy_kernel<<<592, 256, 0, s>>>(x0, b.x, n);
+  CK(cudaGetLastError());
+  return NST_OK;
+}
+
+static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s) {
+  LbfgsBuffers& b = p->lb;
+  int nl = 0;
+  CK(launch_lbfgs_step_begin(b, s));
+  ++nl;
+  CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));
+  const int max_iter = 20;  // torch.optim.LBFGS default, run_style_transfer.py:90
+  for (int k = 1; k <= max_iter; ++k) {
+    CK(launch_lbfgs_iteration(b, k == 1 ? NST_CTL_BEGIN : NST_CTL_MID, s));
+    nl += 4;
+    if (k != max_iter) CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));  // lbfgs.py:493-502
+  }
+  if (launches) *launches = nl;
+  return NST_OK;
+}
+
+extern "C" int nst_lbfgs_step(nst_plan* p, void* stream) {
+  if (!p) return fail(NST_ERR_ARG, "nst_lbfgs_step: null plan");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool no_graph = getenv("NST_NO_GRAPH") != nullptr;
+  if (no_graph || s == nullptr) {
+    // legacy default stream cannot be captured: enqueue directly
+    return step_enqueue(p, &p->launches_per_step, s);
+  }
+  if (!p->step_graph) {
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = step_enqueue(p, &p->launches_per_step, s);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc != NST_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&p->step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  CK(cudaGraphLaunch(p->step_graph, s));
+  return NST_OK;
+}
+
+extern "C" int nst_lbfgs_launches_per_step(const nst_plan* p) { return p ? p->launches_per_step : 0; }
+
+extern "C" int nst_lbfgs_status(nst_plan* p, nst_status* out, void* stream) {
+  if (!p || !out) return fail(NST_ERR_ARG, "nst_lbfgs_status: bad arguments");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static thread_local NstLbfgsCtl h;
+  CK(cudaMemcpyAsync(&h, p->lb.ctl, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->losses, p->losses, NST_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out->n_iter = h.n_iter;
+  out->func_evals = h.func_evals;
+  out->closure_calls = h.closure_calls;
+  out->stop = h.stop;
+  out->hist_len = h.hist_len;
+  out->reserved = 0;
+  out->loss = h.loss;
+  out->prev_loss = h.prev_loss;
+  out->t = h.t;
+  out->H_diag = h.H_diag;
+  out->gtd = h.gtd;
+  out->gmax = h.gmax;
+  out->max_td = h.max_td;
+  return NST_OK;
+}
+
+extern "C" int nst_lbfgs_get_x(nst_plan* p, float* out, void* stream) {
+  if (!p || !out) return fail(NST_ERR_ARG, "nst_lbfgs_get_x: bad arguments");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  clamp_copy_kernel<<<592, 256, 0, s>>>(p->lb.x, out, static_cast<size_t>(3) * p->H * p->W);  // run_style_transfer.py:153-155
+  CK(cudaGetLastError());
+  return NST_OK;
+}
+
+extern "C" int nst_lbfgs_trace(nst_plan* p, float* host_out, int max_rows, void* stream) {
+  if (!p || !host_out || max_rows < 0) return fail(NST_ERR_ARG, "nst_lbfgs_trace: bad arguments");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int calls = 0;
+  CK(cudaMemcpyAsync(&calls, &p->lb.ctl->closure_calls, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  int rows = calls < p->trace_cap ? calls : p->trace_cap;
+  if (rows > max_rows) rows = max_rows;
+  if (rows > 0) {
+    CK(cudaMemcpyAsync(host_out, p->trace, static_cast<size_t>(rows) * 5 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return rows;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer frame path
+// ------------------------------------------------------------------------------------------------
+__global__ void u8_hwc_to_f32_chw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int H, int W) {
+  const size_t HW = static_cast<size_t>(H) * W;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // transforms.ToTensor(): uint8 -> float32 / 255   (run_style_transfer.py:5-11)
+    out[i] = static_cast<float>(in[3 * i]) / 255.f;
+    out[HW + i] = static_cast<float>(in[3 * i + 1]) / 255.f;
+    out[2 * HW + i] = static_cast<float>(in[3 * i + 2]) / 255.f;
+  }
+}
+__global__ void f32_chw_to_u8_hwc_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int H, int W) {
+  const size_t HW = static_cast<size_t>(H) * W;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // transforms.ToPILImage(): clamp (already in [0,1]) . mul(255) . byte() -> truncation   (run_style_transfer.py:157)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(in[c * HW + i], 0.f), 1.f) * 255.f;
+      out[3 * i + c] = static_cast<uint8_t>(v);
+    }
+  }
+}
+
+extern "C" int nst_run_frame_host(nst_plan* p, const uint8_t* content_u8, uint8_t* out_u8, int num_steps,
+                                  int channel_attention, const float* ca_w1, const float* ca_w2, void* stream) {
+  if (!p || !content_u8 || !out_u8 || num_steps < 0) return fail(NST_ERR_ARG, "nst_run_frame_host: bad arguments");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  if (channel_attention && (!ca_w1 || !ca_w2)) return fail(NST_ERR_ARG, "channel attention needs its two weight matrices");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t HW = static_cast<size_t>(p->H) * p->W;
+  if (!p->u8_dev) CKI(plan_alloc_t(p, &p->u8_dev, 3 * HW));
+  if (!p->img_dev) CKI(plan_alloc_t(p, &p->img_dev, 3 * HW));
+  if (!p->gate_dev) CKI(plan_alloc_t(p, &p->gate_dev, 512, true));
+  CK(cudaMemcpyAsync(p->u8_dev, content_u8, 3 * HW, cudaMemcpyHostToDevice, s));
+  u8_hwc_to_f32_chw_kernel<<<592, 256, 0, s>>>(p->u8_dev, p->img_dev, p->H, p->W);
+  CK(cudaGetLastError());
+  // targets from the content image (run_style_transfer.py:71-80, 94-96)
+  CKI(nst_plan_set_edge_target(p, p->img_dev, s));
+  CKI(forward_enqueue(p, p->img_dev, s));
+  for (int l = 0; l < p->n_content; ++l) {
+    const int conv = p->content_conv[l];
+    const float* gate = nullptr;
+    if (channel_attention) {
+      CKI(nst_plan_channel_gate(p, conv, ca_w1, ca_w2, 2, p->gate_dev, s));
+      gate = p->gate_dev;
+    }
+    CKI(nst_plan_set_content_target(p, conv, p, gate, s));
+  }
+  const int evals = 20 * (num_steps / 20 + 1);
+  CKI(nst_lbfgs_init(p, p->img_dev, evals + 32, s));
+  nst_status st;
+  memset(&st, 0, sizeof(st));
+  int guard = 0;
+  while (st.closure_calls <= num_steps) {  // run_style_transfer.py:100
+    CKI(nst_lbfgs_step(p, s));
+    CKI(nst_lbfgs_status(p, &st, s));
+    if (st.stop == NST_STOP_NONFINITE) return fail(NST_ERR_STATE, "non-finite loss at evaluation %d", st.closure_calls);
+    if (++guard > num_steps + 2) break;  // every step() performs at least one evaluation
+  }
+  CKI(nst_lbfgs_get_x(p, p->img_dev, s));
+  f32_chw_to_u8_hwc_kernel<<<592, 256, 0, s>>>(p->img_dev, p->u8_dev, p->H, p->W);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_u8, p->u8_dev, 3 * HW, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return st.closure_calls;
+}

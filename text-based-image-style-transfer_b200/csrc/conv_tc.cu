@@ -1,0 +1,461 @@
+// tcgen05 implicit-GEMM convolution for the VGG-19 trunk (3x3 pad 1, and 1x1 for the Gram backward).
+//
+// Replaces, for the hot path of the reference, the library kernels behind
+//   multi_style_transfer/helper_functions.py:94-101 (Vgg19.forward: nn.Conv2d + ReLU + MaxPool2d)
+// and their autograd data-gradients (run_style_transfer.py:140, loss.backward()).
+//
+// Tiling: one CTA tile = 8 x 16 output pixels (M = 128) x BLOCK_N output channels.  For every
+// filter tap and every 64-channel slice of the input, TMA loads the shifted 8x16x64 activation patch
+// (out-of-bounds -> zero = padding) and the [BLOCK_N x 64] weight slice into 128B-swizzled shared
+// memory; one elected thread issues four tcgen05.mma (K = 16 each) accumulating in TMEM.  The kernel
+// is persistent with two TMEM accumulator stages, so the epilogue of tile i overlaps the main loop
+// of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+#include "conv_tc.cuh"
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+namespace nst {
+
+static constexpr int TILE_H = 8;
+static constexpr int TILE_W = 16;
+static constexpr int BLOCK_M = TILE_H * TILE_W;  // 128
+static constexpr int BLOCK_K = 64;               // 64 x 16-bit = one 128-byte swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+static constexpr int NUM_THREADS = 256;
+static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers (one thread = one pixel of the tile, 32 consecutive channels per call)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store_h32(__half* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_h2(v[8 * q + 0], v[8 * q + 1]);
+    u.y = pack_h2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_h2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack_h2(v[8 * q + 6], v[8 * q + 7]);
+    d[q] = u;
+  }
+}
+__device__ __forceinline__ void store_bf32(__nv_bfloat16* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf2(v[8 * q + 0], v[8 * q + 1]);
+    u.y = pack_bf2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack_bf2(v[8 * q + 6], v[8 * q + 7]);
+    d[q] = u;
+  }
+}
+
+// forward epilogue for 32 channels of one pixel
+__device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
+                                             int lane) {
+  // bias (same address across the warp -> broadcast load)
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 b = __ldg(b4 + q);
+    v[4 * q + 0] += b.x;
+    v[4 * q + 1] += b.y;
+    v[4 * q + 2] += b.z;
+    v[4 * q + 3] += b.w;
+  }
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  if (p.out_tap != nullptr && valid) store_h32(p.out_tap + pix * p.N + n, v);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+  if (!p.pool) {
+    if (p.out_act != nullptr && valid) store_h32(p.out_act + pix * p.N + n, v);
+    return;
+  }
+  // 2x2 max-pool across the four lanes {lane, lane^1, lane^16, lane^17}: tile rows are 16 pixels
+  // wide and a warp owns two consecutive rows.  The window position is folded into the two low
+  // mantissa bits so that one integer max gives both the value and PyTorch's first-max arg-max.
+  const uint32_t pos = ((lane >> 4) & 1) * 2 + (lane & 1);
+  float pooled[32];
+  uint32_t win[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    uint32_t key = (__float_as_uint(v[j]) & ~3u) | (3u - pos);
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
+    pooled[j] = __uint_as_float(key & ~3u);
+    win[j] = pooled[j] > 0.f ? 3u - (key & 3u) : 4u;
+  }
+  const int Hp = p.H >> 1, Wp = p.W >> 1;
+  const int hp = h >> 1, wp = w >> 1;
+  if (hp < Hp && wp < Wp) {
+    const size_t ppix = static_cast<size_t>(hp) * Wp + wp;
+    // each of the four lanes of a window stores 8 of the 32 channels
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      if (pos == static_cast<uint32_t>(jj)) {
+        uint4 u;
+        u.x = pack_h2(pooled[8 * jj + 0], pooled[8 * jj + 1]);
+        u.y = pack_h2(pooled[8 * jj + 2], pooled[8 * jj + 3]);
+        u.z = pack_h2(pooled[8 * jj + 4], pooled[8 * jj + 5]);
+        u.w = pack_h2(pooled[8 * jj + 6], pooled[8 * jj + 7]);
+        *reinterpret_cast<uint4*>(p.out_act + ppix * p.N + n + 8 * jj) = u;
+        uint2 r;
+        r.x = win[8 * jj + 0] | (win[8 * jj + 1] << 8) | (win[8 * jj + 2] << 16) | (win[8 * jj + 3] << 24);
+        r.y = win[8 * jj + 4] | (win[8 * jj + 5] << 8) | (win[8 * jj + 6] << 16) | (win[8 * jj + 7] << 24);
+        *reinterpret_cast<uint2*>(p.out_route + ppix * p.N + n + 8 * jj) = r;
+      }
+    }
+  }
+}
+
+// data-gradient epilogue for 32 channels of one pixel
+__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid) {
+  if (!valid) return;
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  if (p.route == nullptr) {
+    // ReLU mask from the stored post-ReLU activation (PyTorch: grad * (result > 0))
+    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 m = __ldg(m4 + q);
+      const __half2* hh = reinterpret_cast<const __half2*>(&m);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(hh[e]);
+        if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
+        if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+      }
+    }
+    if (p.addend != nullptr) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 a = __ldg(a4 + q);
+        const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(bb[e]);
+          v[8 * q + 2 * e] += f.x;
+          v[8 * q + 2 * e + 1] += f.y;
+        }
+      }
+    }
+    store_bf32(p.out_grad + pix * p.N + n, v);
+  } else {
+    // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
+    // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
+    uint32_t r[8];
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.route + pix * p.N + n);
+    uint4 ra = __ldg(r4), rb = __ldg(r4 + 1);
+    r[0] = ra.x; r[1] = ra.y; r[2] = ra.z; r[3] = ra.w;
+    r[4] = rb.x; r[5] = rb.y; r[6] = rb.z; r[7] = rb.w;
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t rj = (r[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        o[j] = rj == static_cast<uint32_t>(pos) ? v[j] : 0.f;
+      }
+      const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
+      store_bf32(p.out_grad + upix * p.N + n, o);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_scale(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
+                                               float alpha) {
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= alpha;
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  store_bf32(p.out_grad + pix * p.N + n, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tiles
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_slices = p.K / BLOCK_K;
+  const int num_k = p.taps * k_slices;
+  const int pad = p.taps == 9 ? 1 : 0;
+  const int sp_tiles = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile / sp_tiles;
+        const int sp = tile - nt * sp_tiles;
+        const int th = sp / p.tiles_w;
+        const int tw = sp - th * p.tiles_w;
+        const int h0 = th * TILE_H, w0 = tw * TILE_W, n0 = nt * BLOCK_N;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dr = p.taps == 9 ? tap / 3 : 0;
+          const int ds = p.taps == 9 ? tap - 3 * dr : 0;
+          for (int ks = 0; ks < k_slices; ++ks) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_3d(sA + stage * A_STAGE_BYTES, &p.tmA, &full_bar[stage], ks * BLOCK_K, w0 + ds - pad,
+                        h0 + dr - pad);
+            tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, &p.tmB, &full_bar[stage], ks * BLOCK_K, n0, tap);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            umma_f16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
+          if (kb == num_k - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int t = q * 32 + lane;
+    const int hl = t / TILE_W, wl = t % TILE_W;
+    int as = 0;
+    uint32_t aphase = 0;
+    float alpha = 0.f;
+    if (MODE == CONV_SCALE) alpha = __ldg(p.alpha);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile / sp_tiles;
+      const int sp = tile - nt * sp_tiles;
+      const int th = sp / p.tiles_w;
+      const int tw = sp - th * p.tiles_w;
+      const int h = th * TILE_H + hl, w = tw * TILE_W + wl, n0 = nt * BLOCK_N;
+      const bool valid = h < p.H && w < p.W;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int n = n0 + c * 32;
+        if (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane);
+        if (MODE == CONV_DGRAD) epilogue_dgrad(p, v, h, w, n, valid);
+        if (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  // FLOAT16 and BFLOAT16 only differ for NaN fill; both are 2-byte element moves
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(taps)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(N) * K * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_n), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+int conv_block_n(int N) { return N >= 256 ? 256 : (N >= 128 ? 128 : 64); }
+
+void conv_finalize_params(ConvParams& p, int mode) {
+  const int bn = conv_block_n(p.N);
+  p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+  p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+  p.tiles_n = p.N / bn;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.idesc = umma_idesc_f16(BLOCK_M, bn, mode == CONV_DGRAD ? 1 : 0, 0, 0);
+}
+
+template <int BLOCK_N, int MODE>
+static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  conv_tc_kernel<BLOCK_N, MODE><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int BLOCK_N, int MODE>
+static cudaError_t init_one() {
+  return cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              ConvCfg<BLOCK_N>::SMEM_BYTES);
+}
+template <int MODE>
+static cudaError_t init_mode() {
+  cudaError_t e = init_one<256, MODE>();
+  if (e == cudaSuccess) e = init_one<128, MODE>();
+  if (e == cudaSuccess) e = init_one<64, MODE>();
+  return e;
+}
+cudaError_t conv_tc_init() {
+  cudaError_t e = init_mode<CONV_FWD>();
+  if (e == cudaSuccess) e = init_mode<CONV_DGRAD>();
+  if (e == cudaSuccess) e = init_mode<CONV_SCALE>();
+  return e;
+}
+
+template <int MODE>
+static cudaError_t launch_mode(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  switch (conv_block_n(p.N)) {
+    case 256: return launch_one<256, MODE>(p, num_sms, stream);
+    case 128: return launch_one<128, MODE>(p, num_sms, stream);
+    default: return launch_one<64, MODE>(p, num_sms, stream);
+  }
+}
+
+cudaError_t launch_conv_tc(const ConvParams& p, int mode, int num_sms, cudaStream_t stream) {
+  if (p.K % BLOCK_K != 0 || p.N % 64 != 0 || p.num_tiles <= 0) return cudaErrorInvalidValue;
+  switch (mode) {
+    case CONV_FWD: return launch_mode<CONV_FWD>(p, num_sms, stream);
+    case CONV_DGRAD: return launch_mode<CONV_DGRAD>(p, num_sms, stream);
+    case CONV_SCALE: return launch_mode<CONV_SCALE>(p, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace nst

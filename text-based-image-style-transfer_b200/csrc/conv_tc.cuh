@@ -1,0 +1,58 @@
+// Interface of the tcgen05 implicit-GEMM 3x3 / 1x1 convolution kernel (conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace nst {
+
+enum ConvMode : int {
+  CONV_FWD = 0,    // fp16 operands; epilogue: +bias, optional pre-ReLU tap store, ReLU, optional 2x2 max-pool
+  CONV_DGRAD = 1,  // bf16 operands; epilogue: ReLU mask or max-pool routing of the previous layer, + tap gradient
+  CONV_SCALE = 2,  // fp16 operands; epilogue: out = alpha * acc as bf16 (Gram backward as a 1x1 convolution)
+};
+
+// One launch = one convolution layer as an implicit GEMM:
+//   D[pixel, n] = sum_{tap, k} A[pixel + offset(tap), k] * B[tap][n][k]
+// A is an NHWC activation tensor read through a 3-D TMA map (C, W, H) whose out-of-bounds
+// zero fill implements the padding; B is [taps][N][K] (K contiguous) read through a 3-D TMA map.
+struct ConvParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int H, W;        // pixel grid of the GEMM M dimension
+  int K, N;        // channels contracted per tap, output channels
+  int taps;        // 9 (3x3, pad 1) or 1 (1x1)
+  int tiles_w, tiles_h, tiles_n, num_tiles;
+  uint32_t idesc;
+  // ---- CONV_FWD
+  const float* bias;   // [N]
+  __half* out_tap;     // [H,W,N] pre-ReLU or nullptr
+  __half* out_act;     // [H,W,N] post-ReLU (pool == 0) or [H/2,W/2,N] pooled (pool == 1); nullptr = skip
+  uint8_t* out_route;  // [H/2,W/2,N] arg-max position 0..3 in the window, 4 = pooled value <= 0 (pool == 1)
+  int pool;
+  // ---- CONV_DGRAD
+  const __half* mask_act;    // [H,W,N] post-ReLU activation whose gradient is produced (route == nullptr)
+  const uint8_t* route;      // [H,W,N] routing bytes of the pooled layer whose gradient is produced
+  const __nv_bfloat16* addend;  // [H,W,N] gradient injected at this tap, or nullptr
+  __nv_bfloat16* out_grad;   // [H,W,N], or [Hup,Wup,N] when route != nullptr
+  int Hup, Wup;
+  // ---- CONV_SCALE
+  const float* alpha;  // device scalar
+};
+
+// tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
+int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
+int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n);
+
+// picks the N tile for a layer
+int conv_block_n(int N);
+// fills tiles_* / idesc from H, W, K, N, taps and mode
+void conv_finalize_params(ConvParams& p, int mode);
+// sets the kernel attributes (opt-in shared memory) of every instantiation; call once per process
+cudaError_t conv_tc_init();
+// enqueue
+cudaError_t launch_conv_tc(const ConvParams& p, int mode, int num_sms, cudaStream_t stream);
+
+}  // namespace nst

@@ -1,0 +1,338 @@
+// Gram matrices on tcgen05 with split-K, fused with the style-loss reduction.
+//
+// Replaces, on the hot path of the reference,
+//   gram_matrix   multi_style_transfer/style_transfer_losses.py:70-95   (bmm(X, X^T) / (b*c*h*w))
+//   style_loss    multi_style_transfer/style_transfer_losses.py:98-146  (MSELoss(mean) per layer, / #layers)
+// The feature map is NHWC fp16, i.e. a [HW x C] matrix with C contiguous, so F^T F contracts over rows:
+// both MMA operands are "MN-major" views of the same 128B-swizzled tile (64 pixels x 64 channels per
+// TMA box).  Split-K partial tiles go to a workspace; two small kernels reduce them in a fixed order
+// (deterministic), form G - T, the per-layer MSE and the scaled fp16 operand of the backward GEMM.
+#include "gram.cuh"
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace nst {
+
+static constexpr int G_THREADS = 256;
+static constexpr int G_KCHUNK = 64;                       // pixels per pipeline stage
+static constexpr int G_BOX_BYTES = G_KCHUNK * 128;        // 64 pixels x 64 channels x 2 B
+static constexpr int G_STAGE_BYTES = 4 * G_BOX_BYTES;     // A: 2 boxes, B: up to 2 boxes
+static constexpr int G_STAGES = 5;
+static constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 1024 + 256;
+static constexpr int G_TMEM_COLS = 128;
+
+__device__ __forceinline__ int gram_find_layer_by_item(const GramParams& p, int item) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < GRAM_MAX_LAYERS; ++i)
+    if (i < p.num_layers && item >= p.L[i].item0) l = i;
+  return l;
+}
+__device__ __forceinline__ int gram_find_layer_by_finblk(const GramParams& p, int blk) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < GRAM_MAX_LAYERS; ++i)
+    if (i < p.num_layers && blk >= p.L[i].fin_blk0) l = i;
+  return l;
+}
+__device__ __forceinline__ void gram_pair_to_blocks(int pair, int nblk, int& bi, int& bj) {
+  bi = 0;
+  int rowlen = nblk;
+  while (pair >= rowlen) {
+    pair -= rowlen;
+    ++bi;
+    --rowlen;
+  }
+  bj = bi + pair;
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid_constant__ GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + G_STAGES;
+  uint64_t* done_bar = bars + 2 * G_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int item = blockIdx.x;
+  const int l = gram_find_layer_by_item(p, item);
+  const GramLayer& L = p.L[l];
+  const int local = item - L.item0;
+  const int pair = local / L.splits;
+  const int split = local - pair * L.splits;
+  int bi, bj;
+  gram_pair_to_blocks(pair, L.nblk, bi, bj);
+  const int c_begin = static_cast<int>((static_cast<long long>(split) * L.chunks) / L.splits);
+  const int c_end = static_cast<int>((static_cast<long long>(split + 1) * L.chunks) / L.splits);
+  const int a_boxes = L.C >= 128 ? 2 : 1;
+  const int b_boxes = bi == bj ? 0 : L.bn / 64;
+  const CUtensorMap* tm = &p.tm[l];
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(tm);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, G_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = static_cast<uint32_t>((a_boxes + b_boxes) * G_BOX_BYTES);
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        uint8_t* sa = smem + stage * G_STAGE_BYTES;
+        uint8_t* sb = sa + 2 * G_BOX_BYTES;
+        for (int b = 0; b < a_boxes; ++b)
+          tma_load_2d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], bi * 128 + b * 64, c * G_KCHUNK);
+        for (int b = 0; b < b_boxes; ++b)
+          tma_load_2d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], bj * 128 + b * 64, c * G_KCHUNK);
+        if (++stage == G_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t idesc = umma_idesc_f16(128, L.bn, 0, 1, 1);
+    for (int c = c_begin; c < c_end; ++c) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + stage * G_STAGE_BYTES);
+        const uint32_t b_addr = bi == bj ? a_addr : a_addr + 2 * G_BOX_BYTES;
+#pragma unroll
+        for (int k = 0; k < G_KCHUNK / 16; ++k) {
+          // MN-major: LBO = distance between the two 64-channel boxes, SBO = 8 pixel rows
+          const uint64_t da = umma_desc_sw128(a_addr + k * 16 * 128, G_BOX_BYTES, 1024);
+          const uint64_t db = umma_desc_sw128(b_addr + k * 16 * 128, G_BOX_BYTES, 1024);
+          umma_f16(tmem_base, da, db, idesc, (c > c_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (c == c_end - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == G_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* dst = p.ws + L.ws_off + (static_cast<size_t>(local) * 128 + row) * L.bn;
+    const bool row_ok = bi * 128 + row < L.C;
+#pragma unroll 1
+    for (int c = 0; c < L.bn / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, G_TMEM_COLS);
+  }
+}
+
+// element of the upper-triangular block list handled by (block, thread)
+struct FinElem {
+  int gi, gj;
+  bool ok, offdiag;
+  float g;
+};
+
+__device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const GramLayer& L, int blk_in_layer) {
+  FinElem e;
+  const int tile = 128 * L.bn;
+  const int id = blk_in_layer * GRAM_FIN_THREADS + threadIdx.x;
+  e.ok = id < L.pairs * tile;
+  e.gi = e.gj = 0;
+  e.offdiag = false;
+  e.g = 0.f;
+  if (!e.ok) return e;
+  const int pair = id / tile;
+  const int rem = id - pair * tile;
+  const int li = rem / L.bn, lj = rem - li * L.bn;
+  int bi, bj;
+  gram_pair_to_blocks(pair, L.nblk, bi, bj);
+  e.gi = bi * 128 + li;
+  e.gj = bj * 128 + lj;
+  e.offdiag = bi != bj;
+  if (e.gi >= L.C || e.gj >= L.C) {
+    e.ok = false;
+    return e;
+  }
+  const float* src = p.ws + L.ws_off + (static_cast<size_t>(pair) * L.splits * 128 + li) * L.bn + lj;
+  float acc = 0.f;
+  for (int s = 0; s < L.splits; ++s) acc += src[static_cast<size_t>(s) * tile];
+  e.g = acc * L.inv_norm;
+  return e;
+}
+
+// pass 1: reduce split-K partials, G or G - T, per-block (sum of squares, max abs)
+__global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize1_kernel(const __grid_constant__ GramParams p) {
+  __shared__ float scratch[GRAM_FIN_THREADS / 32];
+  const int l = gram_find_layer_by_finblk(p, blockIdx.x);
+  const GramLayer& L = p.L[l];
+  FinElem e = gram_fin_elem(p, L, blockIdx.x - L.fin_blk0);
+  float sq = 0.f, mx = 0.f;
+  if (e.ok) {
+    float d = e.g;
+    if (L.target != nullptr) d -= L.target[static_cast<size_t>(e.gi) * L.C + e.gj];
+    L.gram_out[static_cast<size_t>(e.gi) * L.C + e.gj] = d;
+    if (e.offdiag) L.gram_out[static_cast<size_t>(e.gj) * L.C + e.gi] = d;
+    sq = e.offdiag ? 2.f * d * d : d * d;
+    mx = fabsf(d);
+  }
+  sq = block_sum(sq, scratch);
+  mx = block_max(mx, scratch);
+  if (threadIdx.x == 0) {
+    p.fin_part[2 * blockIdx.x] = sq;
+    p.fin_part[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+// pass 2: per-layer loss, scale, fp16 backward operand
+__global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize2_kernel(const __grid_constant__ GramParams p) {
+  __shared__ float scratch[GRAM_FIN_THREADS / 32];
+  __shared__ float s_bcast[2];
+  const int l = gram_find_layer_by_finblk(p, blockIdx.x);
+  const GramLayer& L = p.L[l];
+  if (L.target == nullptr) return;
+  float sq = 0.f, mx = 0.f;
+  for (int b = threadIdx.x; b < L.fin_blocks; b += GRAM_FIN_THREADS) {
+    sq += p.fin_part[2 * (L.fin_blk0 + b)];
+    mx = fmaxf(mx, p.fin_part[2 * (L.fin_blk0 + b) + 1]);
+  }
+  sq = block_sum(sq, scratch);
+  mx = block_max(mx, scratch);
+  if (threadIdx.x == 0) {
+    s_bcast[0] = sq;
+    s_bcast[1] = mx;
+  }
+  __syncthreads();
+  sq = s_bcast[0];
+  mx = s_bcast[1];
+  if (blockIdx.x == L.fin_blk0 && threadIdx.x == 0) {
+    *L.loss = sq / (static_cast<float>(L.C) * static_cast<float>(L.C));
+    *L.alpha = L.grad_coef * mx;
+  }
+  if (L.dh == nullptr) return;
+  const float inv = mx > 0.f ? 1.f / mx : 0.f;
+  const int tile = 128 * L.bn;
+  const int id = (blockIdx.x - L.fin_blk0) * GRAM_FIN_THREADS + threadIdx.x;
+  if (id >= L.pairs * tile) return;
+  const int pair = id / tile;
+  const int rem = id - pair * tile;
+  const int li = rem / L.bn, lj = rem - li * L.bn;
+  int bi, bj;
+  gram_pair_to_blocks(pair, L.nblk, bi, bj);
+  const int gi = bi * 128 + li, gj = bj * 128 + lj;
+  if (gi >= L.C || gj >= L.C) return;
+  const float d = L.gram_out[static_cast<size_t>(gi) * L.C + gj] * inv;
+  L.dh[static_cast<size_t>(gi) * L.C + gj] = __float2half_rn(d);
+  if (bi != bj) L.dh[static_cast<size_t>(gj) * L.C + gi] = __float2half_rn(d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C) {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || ptr == nullptr)
+    return -1;
+  auto fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(HW)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(G_KCHUNK)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+size_t gram_plan(GramParams& p, int target_ctas) {
+  long long total_units = 0;
+  for (int l = 0; l < p.num_layers; ++l) {
+    GramLayer& L = p.L[l];
+    L.nblk = (L.C + 127) / 128;
+    L.pairs = L.nblk * (L.nblk + 1) / 2;
+    L.bn = L.C < 128 ? L.C : 128;
+    L.chunks = (L.HW + G_KCHUNK - 1) / G_KCHUNK;
+    total_units += static_cast<long long>(L.pairs) * L.chunks;
+  }
+  const long long per_cta = (total_units + target_ctas - 1) / target_ctas;
+  int item = 0, fin = 0;
+  size_t ws = 0;
+  for (int l = 0; l < p.num_layers; ++l) {
+    GramLayer& L = p.L[l];
+    long long s = (L.chunks + per_cta - 1) / (per_cta > 0 ? per_cta : 1);
+    if (s < 1) s = 1;
+    if (s > L.chunks) s = L.chunks;
+    L.splits = static_cast<int>(s);
+    L.item0 = item;
+    item += L.pairs * L.splits;
+    L.fin_blk0 = fin;
+    L.fin_blocks = (L.pairs * 128 * L.bn + GRAM_FIN_THREADS - 1) / GRAM_FIN_THREADS;
+    fin += L.fin_blocks;
+    L.ws_off = ws;
+    ws += static_cast<size_t>(L.pairs) * L.splits * 128 * L.bn;
+  }
+  p.num_items = item;
+  p.num_fin_blocks = fin;
+  return ws;
+}
+
+cudaError_t gram_init() {
+  return cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+}
+
+cudaError_t launch_gram(const GramParams& p, cudaStream_t stream) {
+  gram_partial_kernel<<<p.num_items, G_THREADS, G_SMEM_BYTES, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  gram_finalize1_kernel<<<p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  gram_finalize2_kernel<<<p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace nst

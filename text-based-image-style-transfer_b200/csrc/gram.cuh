@@ -1,0 +1,53 @@
+// Interface of the Gram-matrix kernels (gram.cu): G = F^T F / (C*H*W) on tcgen05 with split-K,
+// fused with the style-MSE reduction and the preparation of the backward operand.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace nst {
+
+static constexpr int GRAM_MAX_LAYERS = 5;
+static constexpr int GRAM_FIN_THREADS = 256;
+
+struct GramLayer {
+  int C;          // channels
+  int HW;         // pixels
+  float inv_norm; // 1 / (b * c * h * w) of gram_matrix (style_transfer_losses.py:84-93); c may be < C when C is padded
+  int nblk;       // ceil(C / 128) channel blocks
+  int pairs;      // nblk * (nblk + 1) / 2 upper-triangular block pairs
+  int bn;         // N of the MMA: min(C, 128)
+  int splits;     // split-K factor over pixels
+  int chunks;     // ceil(HW / 64) 64-pixel K chunks
+  int item0;      // first work item of this layer
+  int fin_blk0;   // first finalize block of this layer
+  int fin_blocks; // finalize blocks of this layer
+  size_t ws_off;  // float offset of this layer's partial tiles in the workspace
+  // finalize inputs / outputs
+  const float* target;  // [C,C] target Gram or nullptr (then `gram_out` receives G itself)
+  float* gram_out;      // [C,C] G (if target == nullptr) or G - T
+  __half* dh;           // [C,C] (G - T) / max|G - T| as fp16 (backward operand), or nullptr
+  float* alpha;         // device scalar: coefficient of the backward 1x1 convolution
+  float* loss;          // device scalar: mean((G - T)^2)
+  float grad_coef;      // 4 * w_style / (num_layers * C^3 * HW)
+};
+
+struct GramParams {
+  CUtensorMap tm[GRAM_MAX_LAYERS];  // 2-D maps (C, HW) of the fp16 NHWC feature maps
+  GramLayer L[GRAM_MAX_LAYERS];
+  int num_layers;
+  int num_items;
+  int num_fin_blocks;
+  float* ws;        // split-K partial tiles [item][128][bn]
+  float* fin_part;  // [num_fin_blocks][2] partial (sum sq, max abs)
+};
+
+int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C);
+// fills nblk/pairs/bn/splits/chunks/item0/fin_* /ws_off and the totals; returns workspace floats needed
+size_t gram_plan(GramParams& p, int target_ctas);
+cudaError_t launch_gram(const GramParams& p, cudaStream_t stream);
+// sets the kernel attributes (opt-in shared memory); call once per process before any capture
+cudaError_t gram_init();
+
+}  // namespace nst

@@ -1,0 +1,318 @@
+// Bandwidth-bound vector kernels of the pixel-space L-BFGS update.
+//
+// Replaces the ~4m+15 small ATen launches and 4-5 host syncs per iteration of
+//   torch.optim.LBFGS.step   torch/optim/lbfgs.py:388-526   (called from run_style_transfer.py:151)
+// by two streaming passes over the stored (s, y) pairs plus a one-warp controller (lbfgs_ctl.h):
+//   pass 1  y = g - g_prev, s = t d (written to the spare history slot), and every dot product of
+//           {s, y, g} with every stored s_i / y_i, with max|g| and sum|g|          reads (2m + 3) n floats
+//   pass 2  d = sum_k coef_k basis_k, x <- clamp(x + t d, 0, 1), g_prev <- g, max|t d|   reads (2m + 2) n floats
+// The [0,1] clamp of run_style_transfer.py:108-109 is folded into the update.
+// No host synchronisation: loop bounds and the stop flag are read from the device control block.
+#include "lbfgs.cuh"
+#include "common.cuh"
+
+namespace nst {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+// Reduces 8 per-lane values across the warp with 9 shuffles (recursive halving);
+// on return lane 4*k (k = 0..7) holds the warp-wide sum of value k in a[0].
+__device__ __forceinline__ void warp_reduce8(float (&a)[8], int lane) {
+  const bool up16 = (lane & 16) != 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = up16 ? a[k] : a[k + 4];
+    const float keep = up16 ? a[k + 4] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  const bool up8 = (lane & 8) != 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = up8 ? a[k] : a[k + 2];
+    const float keep = up8 ? a[k + 2] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const bool up4 = (lane & 4) != 0;
+  {
+    const float send = up4 ? a[0] : a[1];
+    const float keep = up4 ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
+__global__ void lbfgs_step_begin_kernel(NstLbfgsCtl* ctl) {
+  ctl->stop = NST_RUN;
+  ctl->run_pass2 = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuffers b) {
+  __shared__ float wpart[LB_THREADS / 32][NST_LBFGS_SLOTS][6];
+  __shared__ float wscal[LB_THREADS / 32][NST_LBFGS_NSCAL];
+  const NstLbfgsCtl* ctl = b.ctl;
+  if (ctl->stop != NST_RUN) return;
+  const int len = ctl->hist_len, head = ctl->hist_head;
+  const bool first = ctl->n_iter == 0;
+  const float t = static_cast<float>(ctl->t);
+  const int pn = (head + len) % NST_LBFGS_SLOTS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  const int nv = b.n_pad >> 2;
+  const int v0 = blockIdx.x * b.vec_per_blk;
+  const int v1 = min(nv, v0 + b.vec_per_blk);
+
+  float4 s4[LB_VEC_PER_THREAD], y4[LB_VEC_PER_THREAD], g4[LB_VEC_PER_THREAD];
+  size_t off[LB_VEC_PER_THREAD];
+  bool ok[LB_VEC_PER_THREAD];
+  float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < LB_VEC_PER_THREAD; ++i) {
+    const int vi = v0 + i * LB_THREADS + threadIdx.x;
+    ok[i] = vi < v1;
+    off[i] = static_cast<size_t>(ok[i] ? vi : v0) * 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    g4[i] = ok[i] ? ld4(b.g + off[i]) : z;
+    s4[i] = z;
+    y4[i] = z;
+    if (!first && ok[i]) {
+      const float4 gp = ld4(b.g_prev + off[i]);
+      const float4 dd = ld4(b.d + off[i]);
+      y4[i] = make_float4(g4[i].x - gp.x, g4[i].y - gp.y, g4[i].z - gp.z, g4[i].w - gp.w);  // lbfgs.py:404
+      s4[i] = make_float4(dd.x * t, dd.y * t, dd.z * t, dd.w * t);                          // lbfgs.py:405
+      st4(b.S + static_cast<size_t>(pn) * b.n_pad + off[i], s4[i]);
+      st4(b.Y + static_cast<size_t>(pn) * b.n_pad + off[i], y4[i]);
+    }
+    sc[0] = dot4(s4[i], s4[i], sc[0]);
+    sc[1] = dot4(s4[i], y4[i], sc[1]);
+    sc[2] = dot4(y4[i], y4[i], sc[2]);
+    sc[3] = dot4(s4[i], g4[i], sc[3]);
+    sc[4] = dot4(y4[i], g4[i], sc[4]);
+    sc[5] = dot4(g4[i], g4[i], sc[5]);
+    sc[7] += fabsf(g4[i].x) + fabsf(g4[i].y) + fabsf(g4[i].z) + fabsf(g4[i].w);
+    gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(g4[i].x), fabsf(g4[i].y)), fmaxf(fabsf(g4[i].z), fabsf(g4[i].w))));
+  }
+  gmax = warp_max(gmax);
+  warp_reduce8(sc, lane);
+  if ((lane & 3) == 0) wscal[warp][lane >> 2] = (lane >> 2) == 6 ? gmax : sc[0];
+
+#pragma unroll 2
+  for (int i = 0; i < len; ++i) {
+    int p = head + i;
+    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    const float* Sp = b.S + static_cast<size_t>(p) * b.n_pad;
+    const float* Yp = b.Y + static_cast<size_t>(p) * b.n_pad;
+    float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
+      a4[k] = ok[k] ? ld4_stream(Sp + off[k]) : z;
+      c4[k] = ok[k] ? ld4_stream(Yp + off[k]) : z;
+    }
+    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
+      r[0] = dot4(a4[k], s4[k], r[0]);
+      r[1] = dot4(a4[k], y4[k], r[1]);
+      r[2] = dot4(a4[k], g4[k], r[2]);
+      r[3] = dot4(c4[k], s4[k], r[3]);
+      r[4] = dot4(c4[k], y4[k], r[4]);
+      r[5] = dot4(c4[k], g4[k], r[5]);
+    }
+    warp_reduce8(r, lane);
+    if ((lane & 3) == 0 && (lane >> 2) < 6) wpart[warp][p][lane >> 2] = r[0];
+  }
+  __syncthreads();
+  // cross-warp sums in a fixed order -> per-block partials
+  float* out = b.part + static_cast<size_t>(blockIdx.x) * LB_PART_STRIDE;
+  for (int idx = threadIdx.x; idx < len * 6; idx += LB_THREADS) {
+    const int i = idx / 6, q = idx - 6 * i;
+    int p = head + i;
+    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w) acc += wpart[w][p][q];
+    out[p * 6 + q] = acc;
+  }
+  if (threadIdx.x < NST_LBFGS_NSCAL) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w)
+      acc = threadIdx.x == 6 ? fmaxf(acc, wscal[w][threadIdx.x]) : acc + wscal[w][threadIdx.x];
+    out[NST_LBFGS_SLOTS * 6 + threadIdx.x] = acc;
+  }
+}
+
+// one warp per output: sums the per-block partials in fp64 in a fixed order
+__global__ void __launch_bounds__(256) lbfgs_pass1_reduce_kernel(const LbfgsBuffers b) {
+  const NstLbfgsCtl* ctl = b.ctl;
+  if (ctl->stop != NST_RUN) return;
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= LB_PART_STRIDE) return;
+  const bool is_scal = o >= NST_LBFGS_SLOTS * 6;
+  if (!is_scal) {
+    // skip slots that hold no stored pair
+    const int p = o / 6;
+    int rel = p - ctl->hist_head;
+    if (rel < 0) rel += NST_LBFGS_SLOTS;
+    if (rel >= ctl->hist_len) return;
+  }
+  const bool is_max = o == NST_LBFGS_SLOTS * 6 + 6;
+  double acc = 0.0;
+  for (int blk = lane; blk < b.nblocks; blk += 32) {
+    const double val = static_cast<double>(b.part[static_cast<size_t>(blk) * LB_PART_STRIDE + o]);
+    acc = is_max ? fmax(acc, val) : acc + val;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, acc, s);
+    acc = is_max ? fmax(acc, other) : acc + other;
+  }
+  if (lane == 0) {
+    if (is_scal) b.scal[o - NST_LBFGS_SLOTS * 6] = acc;
+    else b.dots[o] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(32) lbfgs_control_kernel(const LbfgsBuffers b, int mode) {
+  __shared__ double cf[NST_LBFGS_NB + 1];
+  nst_lbfgs_control(b.ctl, b.M, b.v, cf, b.dots, b.scal, *b.eval_loss, b.td_part, b.nblocks, mode, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuffers b) {
+  __shared__ float coef[NST_LBFGS_NB + 3];
+  __shared__ float wmax[LB_THREADS / 32];
+  const NstLbfgsCtl* ctl = b.ctl;
+  if (ctl->run_pass2 == 0) return;
+  const int len = ctl->hist_len, head = ctl->hist_head;
+  const float t = ctl->t_apply;
+  for (int k = threadIdx.x; k < NST_LBFGS_NB; k += LB_THREADS) coef[k] = ctl->coef[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  const int nv = b.n_pad >> 2;
+  const int v0 = blockIdx.x * b.vec_per_blk;
+  const int v1 = min(nv, v0 + b.vec_per_blk);
+
+  float4 acc[LB_VEC_PER_THREAD];
+  size_t off[LB_VEC_PER_THREAD];
+  bool ok[LB_VEC_PER_THREAD];
+  const float cg = coef[NST_LBFGS_G];
+#pragma unroll
+  for (int i = 0; i < LB_VEC_PER_THREAD; ++i) {
+    const int vi = v0 + i * LB_THREADS + threadIdx.x;
+    ok[i] = vi < v1;
+    off[i] = static_cast<size_t>(ok[i] ? vi : v0) * 4;
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok[i]) {
+      const float4 g = ld4(b.g + off[i]);
+      st4(b.g_prev + off[i], g);  // lbfgs.py:444-447
+      acc[i] = make_float4(cg * g.x, cg * g.y, cg * g.z, cg * g.w);
+    }
+  }
+#pragma unroll 2
+  for (int i = 0; i < len; ++i) {
+    int p = head + i;
+    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    const float cs = coef[p], cy = coef[NST_LBFGS_SLOTS + p];
+    const float* Sp = b.S + static_cast<size_t>(p) * b.n_pad;
+    const float* Yp = b.Y + static_cast<size_t>(p) * b.n_pad;
+    float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
+      a4[k] = ok[k] ? ld4_stream(Sp + off[k]) : z;
+      c4[k] = ok[k] ? ld4_stream(Yp + off[k]) : z;
+    }
+#pragma unroll
+    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
+      acc[k].x = fmaf(cs, a4[k].x, fmaf(cy, c4[k].x, acc[k].x));
+      acc[k].y = fmaf(cs, a4[k].y, fmaf(cy, c4[k].y, acc[k].y));
+      acc[k].z = fmaf(cs, a4[k].z, fmaf(cy, c4[k].z, acc[k].z));
+      acc[k].w = fmaf(cs, a4[k].w, fmaf(cy, c4[k].w, acc[k].w));
+    }
+  }
+  float mtd = 0.f;
+#pragma unroll
+  for (int i = 0; i < LB_VEC_PER_THREAD; ++i) {
+    if (!ok[i]) continue;
+    st4(b.d + off[i], acc[i]);
+    float4 x = ld4(b.x + off[i]);
+    // lbfgs.py:492 (_add_grad) followed by the closure's clamp_(0, 1), run_style_transfer.py:108-109
+    x.x = fminf(fmaxf(fmaf(t, acc[i].x, x.x), 0.f), 1.f);
+    x.y = fminf(fmaxf(fmaf(t, acc[i].y, x.y), 0.f), 1.f);
+    x.z = fminf(fmaxf(fmaf(t, acc[i].z, x.z), 0.f), 1.f);
+    x.w = fminf(fmaxf(fmaf(t, acc[i].w, x.w), 0.f), 1.f);
+    st4(b.x + off[i], x);
+    mtd = fmaxf(mtd, fmaxf(fmaxf(fabsf(acc[i].x * t), fabsf(acc[i].y * t)),
+                           fmaxf(fabsf(acc[i].z * t), fabsf(acc[i].w * t))));
+  }
+  mtd = warp_max(mtd);
+  if (lane == 0) wmax[warp] = mtd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w) m = fmaxf(m, wmax[w]);
+    b.td_part[blockIdx.x] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+void lbfgs_plan(LbfgsBuffers& b, int num_sms) {
+  const int nv = b.n_pad >> 2;
+  int r = (nv + LB_MAX_VEC_PER_BLOCK * num_sms - 1) / (LB_MAX_VEC_PER_BLOCK * num_sms);
+  if (r < 1) r = 1;
+  // two resident blocks per SM keep more loads in flight at small sizes
+  int nblocks = num_sms * r * 2;
+  if (nblocks > nv) nblocks = nv > 0 ? nv : 1;
+  b.nblocks = nblocks;
+  b.vec_per_blk = (nv + nblocks - 1) / nblocks;
+}
+
+cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s) {
+  lbfgs_step_begin_kernel<<<1, 1, 0, s>>>(b.ctl);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s) {
+  lbfgs_pass1_kernel<<<b.nblocks, LB_THREADS, 0, s>>>(b);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int warps_per_blk = 8;
+  lbfgs_pass1_reduce_kernel<<<(LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s>>>(b);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  lbfgs_control_kernel<<<1, 32, 0, s>>>(b, mode);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  lbfgs_pass2_kernel<<<b.nblocks, LB_THREADS, 0, s>>>(b);
+  return cudaGetLastError();
+}
+
+}  // namespace nst

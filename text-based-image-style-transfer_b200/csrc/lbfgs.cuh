@@ -1,0 +1,41 @@
+// Interface of the bandwidth-bound L-BFGS vector kernels (lbfgs.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lbfgs_ctl.h"
+
+namespace nst {
+
+static constexpr int LB_THREADS = 256;
+static constexpr int LB_VEC_PER_THREAD = 4;                        // float4 per thread per vector
+static constexpr int LB_MAX_VEC_PER_BLOCK = LB_THREADS * LB_VEC_PER_THREAD;
+static constexpr int LB_PART_STRIDE = NST_LBFGS_SLOTS * 6 + NST_LBFGS_NSCAL;  // floats per block in pass-1 partials
+
+struct LbfgsBuffers {
+  int n_pad;        // vector length, multiple of 4; elements >= n are zero everywhere
+  int nblocks;      // pass-1 / pass-2 grid
+  int vec_per_blk;  // float4 per block (<= LB_MAX_VEC_PER_BLOCK)
+  float* x;         // [n_pad] image being optimised (flat [3,H,W])
+  float* g;         // [n_pad] gradient of the latest evaluation
+  float* g_prev;    // [n_pad]
+  float* d;         // [n_pad] direction
+  float* S;         // [SLOTS][n_pad] steps      (torch old_stps)
+  float* Y;         // [SLOTS][n_pad] grad diffs (torch old_dirs)
+  float* part;      // [nblocks][LB_PART_STRIDE] pass-1 per-block partial dots
+  float* td_part;   // [nblocks] pass-2 per-block max|t d|
+  double* dots;     // [SLOTS*6] reduced
+  double* scal;     // [NSCAL] reduced
+  double* M;        // [2*SLOTS][2*SLOTS]
+  double* v;        // [2*SLOTS]
+  NstLbfgsCtl* ctl;
+  const float* eval_loss;  // device scalar written by the evaluation (total loss)
+};
+
+// picks nblocks / vec_per_blk for a vector of n_pad floats
+void lbfgs_plan(LbfgsBuffers& b, int num_sms);
+// clears ctl.stop at step() entry
+cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s);
+// pass 1 + reduction + controller + pass 2 : one L-BFGS iteration after an evaluation
+cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s);
+
+}  // namespace nst

@@ -1,0 +1,200 @@
+"""Mirror of multi_style_transfer/run_style_transfer.py.
+
+run_multi_style_transfer keeps the reference's 15-parameter signature, PIL in / PIL out, its two prints and
+its loop semantics (run_style_transfer.py:27-159): `num_steps` counts closure evaluations, tested between
+optimizer.step() calls, each of which performs up to 20 evaluations.  The work happens on the device:
+one CUDA-graph launch per optimizer.step(), no host synchronisation inside it.
+
+StyleTransferSession is the reusable form used for video frames and benchmarks: it keeps the VGG trunk,
+the style Gram targets and the per-resolution plan alive across calls (the reference rebuilds all three
+per call, app.py:794-798).
+"""
+import contextlib
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import engine
+from ..engine import Plan, _require_cuda
+from .helper_functions import get_net, seed_everything
+
+CONTENT_LAYERS = ['conv4_2']                                              # run_style_transfer.py:56
+STYLE_LAYERS = ['conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1']    # run_style_transfer.py:57
+
+
+def PIL_to_tensor(image):
+    """transforms.ToTensor() + unsqueeze(0) (run_style_transfer.py:5-11): HWC uint8 -> (1,C,H,W) float in [0,1]."""
+    arr = np.asarray(image)
+    if arr.ndim == 2:
+        arr = arr[:, :, None]
+    t = torch.from_numpy(np.ascontiguousarray(arr)).permute(2, 0, 1).contiguous()
+    if t.dtype == torch.uint8:
+        t = t.to(torch.float32).div(255)
+    return t.unsqueeze(0)
+
+
+def tensor_to_PIL(img):
+    """transforms.ToPILImage() of a (3,H,W) float tensor (run_style_transfer.py:157): mul(255).byte() truncates."""
+    from PIL import Image
+    arr = img.detach().cpu().mul(255).byte().permute(1, 2, 0).contiguous().numpy()
+    return Image.fromarray(arr)
+
+
+def _as_tensor3(v, what):
+    t = torch.as_tensor(v, dtype=torch.float32).reshape(-1).cpu()
+    if t.numel() != 3:
+        raise ValueError("%s must have 3 entries" % what)
+    return [float(x) for x in t]
+
+
+def channel_attention_weights(channels, reduction_ratio=2):
+    """The two bias-free nn.Linear weights ChannelAttention.__init__ draws (ChannelAttention.py:16-17), from
+    the CPU generator like `ChannelAttention(c).to(device)` does."""
+    fc1 = torch.nn.Linear(channels, channels // reduction_ratio, bias=False)
+    fc2 = torch.nn.Linear(channels // reduction_ratio, channels, bias=False)
+    return fc1.weight.detach(), fc2.weight.detach()
+
+
+class StyleTransferSession:
+    """VGG trunk + style targets + plan for one (content resolution, style set, weights) configuration."""
+
+    def __init__(self, vgg_mean, vgg_std, content_hw, style_imgs: List[torch.Tensor], w_style, w_content, w_tv, w_edge,
+                 style_img_weight=0.5, device="cuda", content_layers=CONTENT_LAYERS, style_layers=STYLE_LAYERS,
+                 style_targets: Optional[dict] = None):
+        self.device = _require_cuda(device)
+        self.mean = _as_tensor3(vgg_mean, "vgg_mean")
+        self.std = _as_tensor3(vgg_std, "vgg_std")
+        self.content_layers = list(content_layers)
+        self.style_layers = list(style_layers)
+        self.weights = (float(w_style), float(w_content), float(w_tv), float(w_edge))
+        self.net = get_net(self.device)
+        self.stream = torch.cuda.Stream(self.device)
+        H, W = int(content_hw[0]), int(content_hw[1])
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.plan = Plan(self.net, H, W, self.content_layers + self.style_layers, self.style_layers,
+                             self.content_layers, with_grad=True, mean=self.mean, std=self.std)
+            self.plan.set_weights(*self.weights)
+            if style_targets is None:
+                style_targets = self.compute_style_targets(style_imgs, style_img_weight)
+            self.style_targets = {k: v.to(self.device) for k, v in style_targets.items()}
+            for name in self.style_layers:
+                self.plan.set_style_target(name, self.style_targets[name])
+            self.stream.synchronize()
+
+    def compute_style_targets(self, style_imgs, style_img_weight):
+        """Gram targets of style_loss (style_transfer_losses.py:122-135), once instead of once per evaluation."""
+        plans = []
+        for img in style_imgs:
+            h, w = int(img.shape[2]), int(img.shape[3])
+            if (h, w) == (self.plan.H, self.plan.W) and not plans:
+                p = self.plan  # same resolution: reuse the main plan's buffers
+            else:
+                p = Plan(self.net, h, w, self.style_layers, mean=self.mean, std=self.std)
+            p.features(img)
+            plans.append(p)
+        out = {}
+        for name in self.style_layers:
+            if len(plans) == 1:
+                out[name] = plans[0].tap_gram(name)          # :127-129 (style_img_weight ignored)
+            else:
+                out[name] = engine.style_mix_gram(plans[0], plans[1], name, style_img_weight)  # :130-135
+        torch.cuda.current_stream(self.device).synchronize()
+        for p in plans:
+            if p is not self.plan:
+                p.close()
+        return out
+
+    def prepare(self, content: torch.Tensor, x0: Optional[torch.Tensor] = None, channel_attention=False,
+                trace_capacity=0):
+        """Content / edge targets from the content image and optimizer reset (run_style_transfer.py:71-96)."""
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            plan = self.plan
+            plan.features(content)
+            for name in self.content_layers:
+                gate = None
+                if channel_attention:
+                    c, _, _ = plan.tap_shape(name)
+                    w1, w2 = channel_attention_weights(c)      # :13-25, fresh module per layer
+                    gate = plan.channel_gate(name, w1, w2)
+                plan.set_content_target(name, plan, gate)
+            if self.weights[3] > 0:
+                plan.set_edge_target(content)
+            plan.lbfgs_init(content if x0 is None else x0, trace_capacity)
+
+    def step(self):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.plan.lbfgs_step()
+
+    def status(self):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            return self.plan.lbfgs_status()
+
+    def run(self, num_steps, print_iter=None):
+        """The training loop (run_style_transfer.py:98-151).  Returns the number of closure evaluations."""
+        calls = 0
+        guard = 0
+        while calls <= num_steps:
+            self.step()
+            st = self.status()
+            if st.stop == 6:
+                raise engine.NstError("non-finite loss at evaluation %d" % st.closure_calls)
+            if print_iter:
+                for k in range(calls + 1, st.closure_calls + 1):
+                    if k % print_iter == 0:
+                        print(f'Reached iteration {k}/{num_steps}')
+            calls = st.closure_calls
+            guard += 1
+            if guard > num_steps + 2:
+                break
+        return calls
+
+    def result(self) -> torch.Tensor:
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            x = self.plan.lbfgs_x()
+            self.stream.synchronize()
+        return x
+
+    def trace(self, max_rows=4096) -> torch.Tensor:
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            return self.plan.lbfgs_trace(max_rows)
+
+    def close(self):
+        self.plan.close()
+
+
+def run_multi_style_transfer(vgg_mean, vgg_std, content_img, num_steps, random_init, w_style, w_content, w_tv,
+                             w_edge, style_img1, style_img2=None, style_img_weight=0.5, print_iter=50,
+                             channel_attention=False, device="cpu"):
+    """ Neural Style Transfer optimization procedure (reference: run_style_transfer.py:27-159).
+
+    Same parameters and return value as the reference: PIL images in, the style-transferred PIL image out.
+    `device` must be a CUDA device (a B200); the reference's default "cpu" raises because this implementation
+    has no CPU path.
+    """
+    dev = _require_cuda(device)
+    seed_everything(101)                                                   # :52
+
+    content = PIL_to_tensor(content_img).to(dev)                           # :59
+    styles = [PIL_to_tensor(style_img1).to(dev)]                           # :60
+    if style_img2:
+        styles.append(PIL_to_tensor(style_img2).to(dev))                   # :61-63
+    if content.shape[1] != 3 or any(s.shape[1] != 3 for s in styles):
+        raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (3) at non-singleton "
+                           "dimension 1" % content.shape[1])               # normalize() broadcast error of the reference
+
+    session = StyleTransferSession(vgg_mean, vgg_std, content.shape[2:], styles, w_style, w_content, w_tv, w_edge,
+                                   style_img_weight, dev)
+    try:
+        if random_init:
+            x0 = torch.randn(content.size(), device=dev)                   # :84
+        else:
+            x0 = None                                                      # :87 content.clone()
+        print("Channel attention enabled: " + str(channel_attention))      # :92
+        evals = 20 * (int(num_steps) // 20 + 1)
+        session.prepare(content, x0, channel_attention, trace_capacity=evals + 32)
+        session.run(int(num_steps), print_iter)
+        out = session.result()
+    finally:
+        session.close()
+    return tensor_to_PIL(out[0])                                           # :157
