@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Benchmark of the style-transfer hot path (BASELINE.json: "style-transfer steps/s @512^2").
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU implementation (oracle port) on host cores
+
+A "step" is one closure evaluation = one L-BFGS inner iteration (VGG-19 forward, Gram/content/TV/edge losses, backward
+to the pixels, optimizer update): run_style_transfer.py:102-148 + torch/optim/lbfgs.py:388-526.  Workload at every N:
+BASELINE configs[1] - one 512x512 content/style pair per GPU, conv1_1..conv5_1 style layers, app.py's loss weights,
+random-init VGG-19 (seed 1234), seeded 1/f^2 synthetic images.  N > 1 = one independent pair per GPU (the path shards
+across images only: weak scaling, no collective inside the step; NCCL broadcasts the shared style Gram targets once).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "style-transfer steps/s @512x512 (closure evaluations per second)"
+UNIT = "evals/s"
+
+
+def workload_name(size):
+    return ("%dx%d single pair per GPU, conv1_1-conv5_1 style layers + conv4_2 content, app.py loss weights, L-BFGS history 100"
+            "%s" % (size, size, " (BASELINE configs[1])" if size == 512 else ""))
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tc_burst=p["bf16_tflops"], tc_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(power), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU path on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def time_oracle(size, budget_s, max_evals, warm_evals=1):
+    """Evaluations per second of the reference's algorithm on the CPU at size x size, measured on a bounded sample:
+    as many closure evaluations of the first optimizer.step() as fit `budget_s` (at most max_evals)."""
+    import torch
+    from oracle import nst_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ws, bs = O.vgg19_random_weights(1234, 13)
+    content, style = O.synth_image(size, size, 0), O.synth_image(size, size, 1)
+    stamps = []
+
+    def on_eval(k):
+        stamps.append(time.perf_counter())
+        # stop once the budget is spent (never before 2 timed evaluations) or max_evals timed evaluations are done
+        timed = len(stamps) - warm_evals
+        return timed >= max_evals or (timed >= 2 and stamps[-1] - stamps[warm_evals - 1] >= budget_s)
+
+    O.run_oracle(ws, bs, content, [style], 10 ** 9, emulate_reference_cost=True, on_eval=on_eval, **O.APP_WEIGHTS)
+    # setup (VGG target features) and the first evaluation (allocator / thread-pool warm-up) are excluded
+    dt = stamps[-1] - stamps[warm_evals - 1]
+    evals = len(stamps) - warm_evals
+    return dict(value=evals / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d closure evaluations (+ L-BFGS updates) of one %dx%d run after 1 untimed evaluation; oracle/nst_oracle.py "
+                       "with the reference's dead weight-gradients and per-eval style targets emulated; torch %s CPU fp32, %d threads"
+                       % (evals, size, size, torch.__version__, cores)), evals, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base, evals, dt = time_oracle(args.size, budget_s=max(20.0, min(150.0, 0.5 * (args.steps + args.warmup))),
+                                  max_evals=max(2, min(args.steps, 60)))
+    line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 / base["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=workload_name(args.size),
+                            note="reference's CPU path (oracle port; /root/reference is Python and cannot travel to the GPU box), "
+                                 "host cores only, bounded sample"),
+                cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the CUDA path
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import nst_b200
+    from nst_b200 import synth
+    from importlib import import_module
+    hf = import_module("text-based-image-style-transfer_b200.multi_style_transfer.helper_functions")
+    rst = import_module("text-based-image-style-transfer_b200.multi_style_transfer.run_style_transfer")
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.size
+    K, Wm = args.steps, args.warmup
+    ws, bs = synth.vgg19_random_weights(1234, 13)
+    hf.set_vgg_weight_provider(lambda: (ws, bs))
+    style = torch.from_numpy(synth.synth_image(S, S, 1)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
+    content_u8 = synth.synth_image(S, S, 0 if rank == 0 else 100 + rank)   # one independent image per GPU
+    content = torch.from_numpy(content_u8).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
+
+    # shared style Gram targets: rank 0 computes them, NCCL broadcasts (2.44 MB); outside the step loop
+    targets = None
+    if world > 1:
+        names = rst.STYLE_LAYERS
+        chans = [64, 128, 256, 512, 512]
+        if rank == 0:
+            s0 = rst.StyleTransferSession(synth.VGG_MEAN, synth.VGG_STD, (S, S), [style], device=dev, **synth.APP_WEIGHTS)
+            bufs = [s0.style_targets[n].contiguous() for n in names]
+            s0.close()
+        else:
+            bufs = [torch.empty((1, c, c), device=dev) for c in chans]
+        for b in bufs:
+            dist.broadcast(b, src=0)
+        targets = dict(zip(names, bufs))
+    sess = rst.StyleTransferSession(synth.VGG_MEAN, synth.VGG_STD, (S, S), [style], device=dev, style_targets=targets,
+                                    **synth.APP_WEIGHTS)
+    plan = sess.plan
+    stream = sess.stream
+
+    def enqueue_evals(n):
+        """exactly n closure evaluations: whole optimizer.step() graphs (20 each) + one truncated step; returns launches"""
+        launches = 0
+        with torch.cuda.stream(stream):
+            for _ in range(n // 20):
+                plan.lbfgs_step()
+                launches += plan.launches_per_step()
+            if n % 20:
+                launches += plan.lbfgs_partial_step(n % 20)
+        return launches
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up (also captures the CUDA graph and fills part of the L-BFGS history)
+    sess.prepare(content, trace_capacity=Wm + K + 64)
+    enqueue_evals(max(Wm, 3))
+    stream.synchronize()
+
+    # ---- timed region: K evaluations, CUDA events on the launching stream, barrier + sync on both sides
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+    launches = enqueue_evals(K)
+    with torch.cuda.stream(stream):
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    st = sess.status()
+    hist_len = st.hist_len
+    final_loss = st.loss
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    value = world * K / (ms * 1e-3)
+
+    # ---- e2e: the public host-buffer call (uint8 image in pinned host memory -> stylised uint8 image in pinned host memory)
+    evals_e2e = max(20, (K // 20) * 20)
+    pin_in = torch.from_numpy(content_u8).contiguous().pin_memory()
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    with torch.cuda.stream(stream):
+        plan.run_frame_host(pin_in, pin_out, 0)              # warm: graph already captured; 20 evals
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        n_e2e = plan.run_frame_host(pin_in, pin_out, evals_e2e - 20)
+    torch.cuda.synchronize()
+    dt_e2e = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t[0])
+    status_bytes = 2700 + 4 * 16  # control block + loss vector read back after every optimizer.step()
+    e2e = dict(value=world * n_e2e / dt_e2e, unit=UNIT, h2d_bytes_per_step=3 * S * S / n_e2e,
+               d2h_bytes_per_step=(3 * S * S + status_bytes * (n_e2e // 20)) / n_e2e,
+               call="nst_run_frame_host: H2D uint8 image, content/edge targets, %d evaluations, D2H uint8 result; wall clock" % n_e2e)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class, measured live with CUDA events (one event after every launch)
+    pk = peaks()
+    sess.prepare(content, trace_capacity=Wm + K + 64)
+    enqueue_evals(40)
+    stream.synchronize()
+    with torch.cuda.stream(stream):
+        x_now = plan.lbfgs_x()
+        rows = None
+        for _ in range(3):
+            r = plan.eval_timed(x_now)
+            rows = r if rows is None else [(a[0], a[1], min(a[2], b[2])) for a, b in zip(rows, r)]
+        lb_rows = plan.lbfgs_iteration_timed()
+    conv_ms = sum(ms_ for k, l, ms_ in rows if k in ("conv_fwd", "conv_dgrad", "gram_bwd"))
+    conv_launches = sum(1 for k, l, ms_ in rows if k in ("conv_fwd", "conv_dgrad", "gram_bwd"))
+    conv_fl = 2.0 * sum(synth.conv_flops(i, S, S) for i in range(1, 13)) + sum(synth.gram_flops(i, S, S) for i in synth._STYLE)
+    eval_ms = sum(ms_ for _, _, ms_ in rows)
+    achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12
+    roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient + 5 Gram-backward launches per evaluation)",
+                    achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
+                    traffic=None, peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                    flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
+                    ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms)
+    m_now = sess.status().hist_len
+    lb_ms = sum(ms_ for k, _, ms_ in lb_rows if k in ("lbfgs_pass1", "lbfgs_pass2"))
+    lb_gbs = synth.lbfgs_bytes(S, S, m_now) / (lb_ms * 1e-3) / 1e9 if lb_ms > 0 else None
+    by_kind = {}
+    for k, l, ms_ in rows + lb_rows:
+        by_kind[k] = by_kind.get(k, 0.0) + ms_
+    roofline_hbm = dict(bound="hbm", kernel="lbfgs_pass1_kernel + lbfgs_pass2_kernel", achieved=lb_gbs, peak=pk["hbm"], unit="GB/s",
+                        frac=(lb_gbs / pk["hbm"]) if lb_gbs else None, history_pairs=m_now,
+                        bytes_per_iteration=synth.lbfgs_bytes(S, S, m_now), ms=lb_ms)
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _, _ = time_oracle(S, budget_s=args.cpu_budget, max_evals=20)
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms / K,
+                higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f16", data="synthetic",
+                config=dict(workload=workload_name(S),
+                            precision="fp16 operands / fp32 accumulate (VGG forward, Gram), bf16 operands (data gradients), fp32 pixel terms and optimizer",
+                            l2="working set per evaluation (activations ~0.3 GB + L-BFGS history up to 0.63 GB) exceeds the 126 MB L2; no flush needed",
+                            history_pairs_at_end=hist_len, final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S)),
+                clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
+                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if args.kernel_table:
+        with open(args.kernel_table, "w") as f:
+            f.write("kind,conv,ms,gflop,tflops\n")
+            for k, l, ms_ in rows + lb_rows:
+                fl = 0.0
+                if k in ("conv_fwd", "conv_dgrad"):
+                    fl = synth.conv_flops(l, S, S)
+                elif k == "gram_bwd":
+                    fl = synth.gram_flops(l, S, S)
+                elif k == "gram":
+                    fl = sum(synth.gram_flops(i, S, S) for i in synth._STYLE)
+                f.write("%s,%d,%.5f,%.3f,%.1f\n" % (k, l, ms_, fl / 1e9, fl / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=320, help="closure evaluations to time (num_steps=300 runs 320)")
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-launch timing table (CSV) here")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.stderr.write("bench.py: --gpus %d needs torchrun (one rank per GPU); running rank 0 alone as N=1\n" % args.gpus)
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

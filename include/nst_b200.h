@@ -151,6 +151,38 @@ int nst_lbfgs_trace(nst_plan* plan, float* host_out, int max_rows, void* stream)
 /* number of kernels one nst_lbfgs_step enqueues (for launch accounting) */
 int nst_lbfgs_launches_per_step(const nst_plan* plan);
 
+/* the first n_evals (1..20) evaluations of an optimizer.step(), enqueued directly (no graph); returns the number
+ * of kernels launched.  Lets a benchmark time an exact number of evaluations. */
+int nst_lbfgs_partial_step(nst_plan* plan, int n_evals, void* stream);
+
+/* ---- per-launch timing with CUDA events (measurement only) ----------------------------------------- */
+enum {
+  NST_K_START = 0,
+  NST_K_PIXEL = 1,       /* TV + edge losses and gradient */
+  NST_K_CONV1_FWD = 2,   /* conv1_1 forward (CUDA cores) */
+  NST_K_CONV_FWD = 3,    /* tcgen05 implicit-GEMM forward, `layer` = conv index */
+  NST_K_GRAM = 4,        /* Gram split-K + both finalize kernels (3 launches) */
+  NST_K_CONTENT = 5,
+  NST_K_ASSEMBLE = 6,
+  NST_K_GRAM_BWD = 7,    /* Gram backward as a tcgen05 1x1 convolution */
+  NST_K_CONV_DGRAD = 8,  /* tcgen05 implicit-GEMM data gradient */
+  NST_K_CONV1_DGRAD = 9,
+  NST_K_LBFGS_PASS1 = 10,
+  NST_K_LBFGS_REDUCE = 11,
+  NST_K_LBFGS_CONTROL = 12,
+  NST_K_LBFGS_PASS2 = 13
+};
+typedef struct nst_launch_time {
+  int kind;
+  int layer;
+  float ms;
+} nst_launch_time;
+/* one closure evaluation with an event after every launch; returns the number of rows written */
+int nst_plan_eval_timed(nst_plan* plan, const float* x, float* grad, nst_launch_time* out, int max_out, void* stream);
+/* one L-BFGS iteration (pass 1, reduce, controller, pass 2) on the current optimizer state, timed per launch.
+ * It advances the optimizer like a regular iteration. */
+int nst_lbfgs_iteration_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
+
 /* ---- host-buffer convenience (the e2e path: copies inside) ---------------------------------------
  * content_u8: [H,W,3] uint8 host; out_u8: [H,W,3] uint8 host (truncating, like ToPILImage).
  * Requires style / content / edge targets to be refreshed from the content image, which this call

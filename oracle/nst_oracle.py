@@ -356,17 +356,26 @@ class ClosureOracle:
 
     def __init__(self, weights, biases, content: torch.Tensor, styles: List[torch.Tensor], *, w_style, w_content,
                  w_tv, w_edge, style_img_weight=0.5, channel_attention_on=False, mean=VGG_MEAN, std=VGG_STD,
-                 content_layers=CONTENT_LAYERS, style_layers=STYLE_LAYERS, ca_seed: Optional[int] = 101):
+                 content_layers=CONTENT_LAYERS, style_layers=STYLE_LAYERS, ca_seed: Optional[int] = 101,
+                 emulate_reference_cost: bool = False):
         self.dtype = content.dtype
         self.mean, self.std = mean, std
         self.w = dict(style=w_style, content=w_content, tv=w_tv, edge=w_edge)
         self.content_layers, self.style_layers = list(content_layers), list(style_layers)
+        # emulate_reference_cost (timing only; values are unchanged): the reference leaves the VGG weights with
+        # requires_grad=True, so backward() also computes 13 weight gradients nobody reads, and it
+        # recomputes the constant style targets inside every evaluation (quirk 6)
+        self.emulate_reference_cost = emulate_reference_cost
+        if emulate_reference_cost:
+            weights = [w.detach().clone().requires_grad_(True) for w in weights]
+            biases = [b.detach().clone().requires_grad_(True) for b in biases]
         self.vgg = VggFeatures(weights, biases, self.content_layers + self.style_layers)
         normed_content = normalize(content, mean, std)
         self.edge_target = get_gradient_imgs(to_grayscale(normed_content)).detach() if w_edge > 0 else None
         with torch.no_grad():
             sfeats = [self.vgg(normalize(s, mean, std)) for s in styles]
             cfeats = self.vgg(normed_content)
+            self._sfeats, self._mix_w = sfeats, style_img_weight
             self.style_t = style_targets(sfeats, self.style_layers, style_img_weight)
             if channel_attention_on:
                 # run_style_transfer.py:13-25: a fresh randomly initialised gate per content layer
@@ -387,7 +396,10 @@ class ClosureOracle:
         c = self.w["content"] * content_loss(feats, self.content_t, self.content_layers) if self.w["content"] > 0 else zero
         per = []
         if self.w["style"] > 0:
-            sl, per = style_loss_from_targets(feats, self.style_t, self.style_layers)
+            targets = self.style_t
+            if self.emulate_reference_cost:
+                targets = style_targets(self._sfeats, self.style_layers, self._mix_w)
+            sl, per = style_loss_from_targets(feats, targets, self.style_layers)
             s = self.w["style"] * sl
         else:
             s = zero
@@ -409,7 +421,8 @@ class ClosureOracle:
 
 def run_oracle(weights, biases, content_u8: np.ndarray, style_u8: List[np.ndarray], num_steps: int, *,
                random_init=False, w_style, w_content, w_tv, w_edge, style_img_weight=0.5, channel_attention_on=False,
-               mean=VGG_MEAN, std=VGG_STD, dtype=torch.float32, keep_iterates=False, max_evals=None) -> OracleResult:
+               mean=VGG_MEAN, std=VGG_STD, dtype=torch.float32, keep_iterates=False, max_evals=None,
+               emulate_reference_cost=False, on_eval=None) -> OracleResult:
     """run_multi_style_transfer (run_style_transfer.py:27-159) on uint8 HWC arrays."""
     torch.manual_seed(101)                                                  # :52 seed_everything
     np.random.seed(101)
@@ -423,27 +436,37 @@ def run_oracle(weights, biases, content_u8: np.ndarray, style_u8: List[np.ndarra
         x0 = content.clone()                                                # :87
     co = ClosureOracle(weights, biases, content, styles, w_style=w_style, w_content=w_content, w_tv=w_tv, w_edge=w_edge,
                        style_img_weight=style_img_weight, channel_attention_on=channel_attention_on, mean=mean, std=std,
-                       ca_seed=None if random_init else 101)
+                       ca_seed=None if random_init else 101, emulate_reference_cost=emulate_reference_cost)
     x = x0.reshape(-1).clone()
     shape = content.shape
     opt = LbfgsOracle(x)
     res = OracleResult(image=None, losses=[], iterates=[] if keep_iterates else None, grads=[] if keep_iterates else None)
     counter = [0]
 
+    class _Stop(Exception):
+        pass
+
+    stop_req = [False]
+
     def closure():
+        if stop_req[0] or (max_evals is not None and counter[0] >= max_evals):
+            raise _Stop()
         opt.x.clamp_(0, 1)                                                  # :108-109
         out = co.evaluate(opt.x.reshape(shape))
         counter[0] += 1                                                     # :143
+        if on_eval is not None:
+            stop_req[0] = bool(on_eval(counter[0]))     # a true return value ends the run before the next evaluation
         res.losses.append([out["total"], out["content"], out["style"], out["tv"], out["edge"]])
         if keep_iterates:
             res.iterates.append(opt.x.reshape(shape).clone())
             res.grads.append(out["grad"].clone())
         return out["total"], out["grad"].reshape(-1)
 
-    while counter[0] <= num_steps:                                          # :100
-        opt.step(closure)
-        if max_evals is not None and counter[0] >= max_evals:
-            break
+    try:
+        while counter[0] <= num_steps:                                      # :100
+            opt.step(closure)
+    except _Stop:
+        pass
     opt.x.clamp_(0, 1)                                                      # :154-155
     res.image = opt.x.reshape(shape).clone()
     res.evals = counter[0]

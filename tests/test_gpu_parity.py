@@ -1,0 +1,314 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the golden vectors written by the
+reference itself.  Tolerances are the ones BASELINE.json's north_star states:
+  * per-layer Gram matrices and loss values within 1e-3 relative at step 0,
+  * the loss curve within 1e-2 relative over the run,
+  * the final image at >= 40 dB PSNR against the reference.
+The CUDA path computes the VGG trunk with fp16 operands / fp32 accumulation (forward) and bf16 operands (data
+gradients); pixel-space terms and the optimizer are fp32."""
+import importlib
+import io
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+GRAM_TOL = 1e-3
+LOSS_TOL = 1e-3
+CURVE_TOL = 1e-2
+PSNR_MIN = 40.0
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def nst(built_libs, vgg_weights):
+    pkg = importlib.import_module("text-based-image-style-transfer_b200")
+    hf = importlib.import_module("text-based-image-style-transfer_b200.multi_style_transfer.helper_functions")
+    hf.set_vgg_weight_provider(lambda: vgg_weights)
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def rst():
+    return importlib.import_module("text-based-image-style-transfer_b200.multi_style_transfer.run_style_transfer")
+
+
+def session(rst, O, content, styles, weights=None, mix_w=0.5):
+    weights = weights or O.APP_WEIGHTS
+    c = O.to_tensor_u8(content).cuda()
+    s = rst.StyleTransferSession(O.VGG_MEAN, O.VGG_STD, c.shape[2:], [O.to_tensor_u8(x).cuda() for x in styles],
+                                 weights["w_style"], weights["w_content"], weights["w_tv"], weights["w_edge"], mix_w, "cuda")
+    return s, c
+
+
+def noisy(c, seed=3):
+    return (c.cpu() + 0.05 * torch.randn(c.shape, generator=torch.Generator().manual_seed(seed))).clamp(0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ step 0
+@pytest.mark.parametrize("hw", [(64, 64), (50, 38), (96, 130)])
+def test_vgg_taps_match_oracle(nst, oracle, vgg_weights, hw):
+    """Vgg19.forward: six pre-ReLU taps, odd sizes exercise the floor of MaxPool2d and partial tiles."""
+    O = oracle
+    ws, bs = vgg_weights
+    c = O.to_tensor_u8(O.synth_image(hw[0], hw[1], 11))
+    names = O.STYLE_LAYERS + O.CONTENT_LAYERS
+    ref = O.VggFeatures(ws, bs, names)(O.normalize(c, O.VGG_MEAN, O.VGG_STD))
+    plan = nst.Plan(nst.multi_style_transfer.helper_functions.get_net("cuda"), hw[0], hw[1], names, mean=O.VGG_MEAN, std=O.VGG_STD)
+    plan.features(c.cuda())
+    for n in ref:
+        got = plan.get_tap(n)
+        assert got.shape == ref[n].shape
+        assert rel(got, ref[n]) < 2e-3, n
+        assert float(got.min()) < 0  # pre-ReLU
+    plan.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 16, 16), (128, 33, 31), (256, 24, 20), (512, 16, 16), (512, 3, 2), (96, 20, 20)])
+def test_gram_kernel(nst, shape):
+    C, H, W = shape
+    x = torch.randn((1, C, H, W), generator=torch.Generator().manual_seed(C + H)) * 0.3
+    ref = torch.bmm(x.double().reshape(1, C, -1), x.double().reshape(1, C, -1).transpose(1, 2)) / (C * H * W)
+    got = nst.gram_chw(x.cuda())
+    assert got.shape == (1, C, C)
+    assert rel(got, ref) < GRAM_TOL
+    assert torch.equal(got, got.transpose(1, 2))           # exactly symmetric: one triangle is computed, then mirrored
+    xh = x.half().double()
+    exact = torch.bmm(xh.reshape(1, C, -1), xh.reshape(1, C, -1).transpose(1, 2)) / (C * H * W)
+    assert rel(got, exact) < 5e-6                          # fp32 accumulation of fp16-rounded operands
+
+
+@pytest.mark.parametrize("name", ["single_64", "odd_50x38", "mix_ca_48x40"])
+def test_step0_against_reference_golden(nst, rst, oracle, name):
+    """Per-term losses, per-layer Gram MSE and Gram matrices at x = content against the REFERENCE's own numbers."""
+    from test_oracle import CASES
+    O = oracle
+    g = golden(name)
+    cspec, sspecs, steps, wgt, ca = CASES[name]
+    s, c = session(rst, O, O.synth_image(*cspec), [O.synth_image(*x) for x in sspecs], mix_w=wgt)
+    torch.manual_seed(101)
+    s.prepare(c, channel_attention=ca)
+    with torch.cuda.stream(s.stream):
+        losses, grad = s.plan.eval(c)
+        grams = {n: s.plan.tap_gram(n) for n in O.STYLE_LAYERS}
+    l = losses.cpu().tolist()
+    for idx, term in ((0, "total"), (1, "content"), (2, "style"), (3, "tv"), (4, "edge")):
+        assert l[idx] == pytest.approx(float(g["s0_" + term]), rel=LOSS_TOL, abs=1e-7), term
+    for i, layer in enumerate(O.STYLE_LAYERS):
+        assert l[5 + i] == pytest.approx(float(g["s0_gram_mse_" + layer]), rel=LOSS_TOL), layer
+        blk = torch.from_numpy(g["s0_gram_" + layer])
+        assert rel(grams[layer][0][:blk.shape[0], :blk.shape[1]], blk) < GRAM_TOL, layer
+        assert float(grams[layer].norm()) == pytest.approx(float(g["s0_gram_fro_" + layer]), rel=GRAM_TOL)
+        assert float(s.style_targets[layer].norm()) == pytest.approx(float(g["s0_target_fro_" + layer]), rel=GRAM_TOL)
+    assert rel(grad, torch.from_numpy(g["s0_grad"])) < 1e-3
+    s.close()
+
+
+def test_gradient_teacher_forced(nst, rst, oracle, vgg_weights):
+    """Same iterate in, loss and gradient out - with and without the pixel-space terms that dominate the total."""
+    O = oracle
+    ws, bs = vgg_weights
+    content, style = O.synth_image(64, 80, 0), O.synth_image(72, 64, 1)
+    for wts, tol in ((O.APP_WEIGHTS, 1e-3), (dict(w_style=5e5, w_content=1.0, w_tv=0.0, w_edge=0.0), 5e-2),
+                     (dict(w_style=0.0, w_content=0.0, w_tv=20.0, w_edge=20.0), 1e-6)):
+        s, c = session(rst, O, content, [style], wts)
+        s.prepare(c)
+        co = O.ClosureOracle(ws, bs, c.cpu(), [O.to_tensor_u8(style)], **wts)
+        for seed in (3, 4):
+            x = noisy(c, seed)
+            ref = co.evaluate(x)
+            with torch.cuda.stream(s.stream):
+                losses, grad = s.plan.eval(x.cuda())
+            assert float(losses[0]) == pytest.approx(ref["total"], rel=LOSS_TOL)
+            assert rel(grad, ref["grad"]) < tol
+            cos = float((grad.cpu().double().flatten() @ ref["grad"].double().flatten()) /
+                        (grad.double().norm().cpu() * ref["grad"].double().norm()))
+            assert cos > 1 - tol
+        s.close()
+
+
+def test_eval_is_deterministic(nst, rst, oracle):
+    O = oracle
+    s, c = session(rst, O, O.synth_image(64, 64, 0), [O.synth_image(64, 64, 1)])
+    s.prepare(c)
+    x = noisy(c).cuda()
+    with torch.cuda.stream(s.stream):
+        l1, g1 = s.plan.eval(x)
+        l2, g2 = s.plan.eval(x)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ trajectories
+@pytest.mark.parametrize("name", ["single_64", "odd_50x38", "mix_ca_48x40"])
+def test_trajectory_against_reference_golden(nst, rst, oracle, name):
+    """run_multi_style_transfer end to end (PIL in, PIL out) against the reference's recorded run."""
+    from PIL import Image
+    from test_oracle import CASES
+    O = oracle
+    g = golden(name)
+    cspec, sspecs, steps, wgt, ca = CASES[name]
+    content = O.synth_image(*cspec)
+    styles = [O.synth_image(*x) for x in sspecs]
+    # session form first: gives the loss trace and the float image
+    s, c = session(rst, O, content, styles, mix_w=wgt)
+    torch.manual_seed(101)
+    s.prepare(c, channel_attention=ca, trace_capacity=256)
+    n = s.run(steps)
+    assert n == int(g["n_evals"])
+    tr = s.trace()[:, 0].double().numpy()
+    ref = g["loss_trace"]
+    assert np.abs(tr - ref).max() <= CURVE_TOL * np.abs(ref).max()
+    assert np.all(np.abs(tr - ref) <= CURVE_TOL * np.abs(ref))
+    x = s.result().cpu()
+    assert O.psnr(x, torch.from_numpy(g["x_last"])) >= PSNR_MIN
+    st = s.status()
+    assert st.n_iter == n and st.closure_calls == n and st.stop == 0 and st.hist_len <= 100
+    s.close()
+    # drop-in form
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = nst.run_multi_style_transfer(torch.tensor(O.VGG_MEAN), torch.tensor(O.VGG_STD), Image.fromarray(content), steps,
+                                           False, style_img1=Image.fromarray(styles[0]),
+                                           style_img2=Image.fromarray(styles[1]) if len(styles) > 1 else None,
+                                           style_img_weight=wgt, print_iter=20, channel_attention=ca, device="cuda",
+                                           **O.APP_WEIGHTS)
+    text = buf.getvalue()
+    assert "Channel attention enabled: " + str(ca) in text                 # run_style_transfer.py:92
+    assert f"Reached iteration 20/{steps}" in text                        # :144-146
+    assert isinstance(out, Image.Image) and out.size == (cspec[1], cspec[0]) and out.mode == "RGB"
+    diff = np.abs(np.asarray(out).astype(int) - g["final_u8"].astype(int))
+    assert diff.max() <= 12 and diff.mean() < 1.0
+    assert np.array_equal(np.asarray(out), O.to_u8(x))                     # both forms run the same device loop
+
+
+def test_pixel_only_trajectory_is_tight(nst, rst, oracle, vgg_weights):
+    """With the VGG terms off the path is fp32 end to end: the device L-BFGS must track the oracle's closely."""
+    O = oracle
+    ws, bs = vgg_weights
+    wts = dict(w_style=0.0, w_content=0.0, w_tv=20.0, w_edge=20.0)
+    content, style = O.synth_image(48, 56, 0), O.synth_image(48, 56, 1)
+    ref = O.run_oracle(ws, bs, content, [style], 30, **wts)
+    s, c = session(rst, O, content, [style], wts)
+    s.prepare(c, trace_capacity=128)
+    assert s.run(30) == ref.evals == 40
+    tr = s.trace()[:, 0].double().numpy()
+    rl = np.array([l[0] for l in ref.losses])
+    assert np.abs(tr[:10] - rl[:10]).max() <= 1e-5 * rl[0]
+    assert np.abs(tr - rl).max() <= 5e-3 * rl[0]
+    assert O.psnr(s.result().cpu(), ref.image) > 50.0
+    s.close()
+
+
+def test_random_init_and_num_steps_semantics(nst, rst, oracle):
+    """num_steps counts closure evaluations between optimizer.step() calls (20 each); random_init starts from randn,
+    which the first closure clamps (run_style_transfer.py:84,108-109)."""
+    O = oracle
+    s, c = session(rst, O, O.synth_image(32, 32, 0), [O.synth_image(32, 32, 1)])
+    for n, want in ((0, 20), (19, 20), (20, 40), (45, 60)):
+        s.prepare(c, trace_capacity=128)
+        assert s.run(n) == want
+    x0 = torch.randn(c.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    s.prepare(c, x0, trace_capacity=64)
+    assert s.run(0) == 20
+    x = s.result()
+    assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+    tr = s.trace()[:, 0]
+    assert torch.isfinite(tr).all()
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ function-level mirror
+def test_function_level_mirrors(nst, oracle, vgg_weights):
+    """The seven loss functions + Vgg19 / StyleMixer / ChannelAttention called the way the reference's closure calls them."""
+    O = oracle
+    ws, bs = vgg_weights
+    L = importlib.import_module("text-based-image-style-transfer_b200.multi_style_transfer.style_transfer_losses")
+    CA = importlib.import_module("text-based-image-style-transfer_b200.multi_style_transfer.ChannelAttention")
+    mean, std = torch.tensor(O.VGG_MEAN), torch.tensor(O.VGG_STD)
+    c = O.to_tensor_u8(O.synth_image(40, 52, 0))
+    s1 = O.to_tensor_u8(O.synth_image(36, 44, 1))
+    s2 = O.to_tensor_u8(O.synth_image(48, 40, 2))
+    model = L.Vgg19(O.CONTENT_LAYERS, O.STYLE_LAYERS, "cuda")
+    assert model.layer_names == ["conv1_1", "conv2_1", "conv3_1", "conv4_1", "conv4_2", "conv5_1"]
+    normed = L.normalize(c.cuda(), mean, std)
+    assert rel(normed, O.normalize(c, O.VGG_MEAN, O.VGG_STD)) < 1e-7
+    feats = model(normed)
+    sfeats = [model(L.normalize(s.cuda(), mean, std)) for s in (s1, s2)]
+    ovgg = O.VggFeatures(ws, bs, O.CONTENT_LAYERS + O.STYLE_LAYERS)
+    ofeats = ovgg(O.normalize(c, O.VGG_MEAN, O.VGG_STD))
+    osf = [ovgg(O.normalize(s, O.VGG_MEAN, O.VGG_STD)) for s in (s1, s2)]
+    for n in ofeats:
+        assert rel(feats[n], ofeats[n]) < 2e-3
+    assert float(L.total_variation_loss(normed)) == pytest.approx(float(O.total_variation_loss(O.normalize(c, O.VGG_MEAN, O.VGG_STD))), rel=1e-5)
+    gi = L.get_gradient_imgs(L.to_grayscale(c.cuda()))
+    ogi = O.get_gradient_imgs(O.to_grayscale(c))
+    assert gi.shape == ogi.shape and rel(gi, ogi) < 1e-6
+    gi2 = L.get_gradient_imgs(L.to_grayscale(s1.cuda()[:, :, :, :]))
+    assert float(L.edge_loss(gi, gi * 0.5)) == pytest.approx(float(O.edge_loss(ogi, ogi * 0.5)), rel=1e-5)
+    assert gi2.shape == (1, 2, 34, 42)
+    assert float(L.content_loss(feats, sfeats[0] if False else {k: v * 0.9 for k, v in feats.items()}, O.CONTENT_LAYERS)) == \
+        pytest.approx(float(O.content_loss(ofeats, {k: v * 0.9 for k, v in ofeats.items()}, O.CONTENT_LAYERS)), rel=3e-3)
+    # single style: style_img_weight is ignored (style_transfer_losses.py:127-129)
+    one = float(L.style_loss(feats, sfeats[:1], O.STYLE_LAYERS, 0.9))
+    oone, _ = O.style_loss_from_targets(ofeats, O.style_targets(osf[:1], O.STYLE_LAYERS, 0.9), O.STYLE_LAYERS)
+    assert one == pytest.approx(float(oone), rel=3e-3)
+    two = float(L.style_loss(feats, sfeats, O.STYLE_LAYERS, 0.3))
+    otwo, _ = O.style_loss_from_targets(ofeats, O.style_targets(osf, O.STYLE_LAYERS, 0.3), O.STYLE_LAYERS)
+    assert two == pytest.approx(float(otwo), rel=3e-3)
+    mixed = L.StyleMixer([sfeats[0]["conv2_1"], sfeats[1]["conv2_1"]], 0.3).mix()
+    omixed = O.style_mix(osf[0]["conv2_1"], osf[1]["conv2_1"], 0.3)
+    assert mixed.shape == omixed.shape == (1, 128, 18 + 24 // 2, 22 + 20 // 2)
+    assert rel(mixed, omixed) < 2e-3
+    torch.manual_seed(101)
+    ca = CA.ChannelAttention(512)
+    w1, w2 = ca.fc1.weight.detach(), ca.fc2.weight.detach()
+    got = ca(feats["conv4_2"])
+    want = O.channel_attention(ofeats["conv4_2"], w1, w2)
+    assert rel(got, want) < 2e-3
+    with pytest.raises(Exception):
+        L.Vgg19(["conv9_9"], O.STYLE_LAYERS, "cuda")
+    with pytest.raises(RuntimeError):
+        L.normalize(torch.zeros(1, 4, 8, 8, device="cuda"), mean, std)     # RGBA input breaks the 3-channel broadcast
+
+
+# ------------------------------------------------------------------------------------------------ full size: properties
+def test_full_size_512_properties(nst, rst, oracle):
+    """BASELINE config 2 (512x512, 300 steps): too slow for the CPU oracle inside a unit test, so size-independent
+    properties: 320 evaluations exactly, monotone-ish decreasing loss, iterate in [0,1], Gram symmetry and
+    quadratic scaling, bounded history, bit-reproducibility of the whole run."""
+    O = oracle
+    content, style = O.synth_image(512, 512, 0), O.synth_image(512, 512, 1)
+    s, c = session(rst, O, content, [style])
+    finals = []
+    for rep in range(2):
+        s.prepare(c, trace_capacity=400)
+        assert s.run(300) == 320
+        tr = s.trace()[:, 0].double().numpy()
+        assert tr.shape[0] == 320 and np.isfinite(tr).all()
+        assert tr[-1] < 0.5 * tr[0]
+        assert (np.diff(tr) < 0).mean() > 0.9
+        st = s.status()
+        assert st.hist_len == 100 and st.n_iter == 320 and st.stop == 0
+        x = s.result()
+        assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+        finals.append((x.clone(), tr.copy()))
+    assert torch.equal(finals[0][0], finals[1][0]) and np.array_equal(finals[0][1], finals[1][1])
+    with torch.cuda.stream(s.stream):
+        s.plan.features(c)
+        g1 = s.plan.tap_gram("conv1_1")
+        s.plan.features(c * 0.0 + 0.5)
+        g_flat = s.plan.tap_gram("conv3_1")
+    assert torch.equal(g1, g1.transpose(1, 2))
+    ev = torch.linalg.eigvalsh(g1[0].double().cpu())
+    assert float(ev.min()) > -1e-6 * float(ev.max())                       # Gram matrices are positive semi-definite
+    assert torch.isfinite(g_flat).all()
+    s.close()

@@ -23,6 +23,14 @@ class NstStatus(C.Structure):
                 ("losses", C.c_float * NST_LOSS_COUNT)]
 
 
+class NstLaunchTime(C.Structure):
+    _fields_ = [("kind", C.c_int), ("layer", C.c_int), ("ms", C.c_float)]
+
+
+KIND_NAMES = {1: "pixel", 2: "conv1_fwd", 3: "conv_fwd", 4: "gram", 5: "content", 6: "assemble", 7: "gram_bwd",
+              8: "conv_dgrad", 9: "conv1_dgrad", 10: "lbfgs_pass1", 11: "lbfgs_reduce", 12: "lbfgs_control",
+              13: "lbfgs_pass2"}
+
 _P = C.c_void_p
 _F3 = C.POINTER(C.c_float)
 # name -> (restype, argtypes); mirrors include/nst_b200.h one to one
@@ -63,6 +71,9 @@ PROTOTYPES = {
     "nst_lbfgs_get_x": (C.c_int, [_P, _P, _P]),
     "nst_lbfgs_trace": (C.c_int, [_P, _P, C.c_int, _P]),
     "nst_lbfgs_launches_per_step": (C.c_int, [_P]),
+    "nst_lbfgs_partial_step": (C.c_int, [_P, C.c_int, _P]),
+    "nst_plan_eval_timed": (C.c_int, [_P, _P, _P, C.POINTER(NstLaunchTime), C.c_int, _P]),
+    "nst_lbfgs_iteration_timed": (C.c_int, [_P, C.POINTER(NstLaunchTime), C.c_int, _P]),
     "nst_run_frame_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
 }
 

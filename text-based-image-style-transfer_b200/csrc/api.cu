@@ -678,18 +678,49 @@ extern "C" int nst_plan_set_edge_target(nst_plan* p, const float* content, void*
 // ------------------------------------------------------------------------------------------------
 // the closure
 // ------------------------------------------------------------------------------------------------
+// optional per-launch timing (nst_plan_eval_timed): an event is recorded after every launch
+struct LaunchTimer {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind, layer;
+  cudaStream_t s = nullptr;
+  int mark(int k, int l) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    if (cudaEventRecord(e, s) != cudaSuccess) return -1;
+    ev.push_back(e);
+    kind.push_back(k);
+    layer.push_back(l);
+    return 0;
+  }
+  ~LaunchTimer() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+#define TM(k, l)                                                                     \
+  do {                                                                               \
+    if (tm && tm->mark((k), (l)) != 0) return fail(NST_ERR_CUDA, "event record failed"); \
+  } while (0)
+
 static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
-                        cudaStream_t s) {
+                        cudaStream_t s, LaunchTimer* tm = nullptr) {
   int nl = 0;
+  TM(NST_K_START, -1);
   const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
   CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s));
   ++nl;
+  TM(NST_K_PIXEL, -1);
   if (use_vgg) {
-    CKI(forward_enqueue(p, x, s));
+    CK(launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+    TM(NST_K_CONV1_FWD, 0);
+    for (int i = 1; i < p->n_layers; ++i) {
+      CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
+      TM(NST_K_CONV_FWD, i);
+    }
     nl += p->n_layers;
     if (p->n_style > 0) {
       CK(launch_gram(p->gram, s));
       nl += 3;
+      TM(NST_K_GRAM, -1);
     }
     for (int l = 0; l < p->n_content; ++l) {
       const int i = p->content_conv[l];
@@ -702,6 +733,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       CK(launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel,
                              gcoef, 0, s));
       ++nl;
+      TM(NST_K_CONTENT, i);
     }
   }
   LossAssembleArgs a;
@@ -733,12 +765,14 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   a.trace_cap = p->trace_cap;
   CK(launch_loss_assemble(a, s));
   ++nl;
+  TM(NST_K_ASSEMBLE, -1);
   if (grad != nullptr) {
     if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
     if (use_vgg) {
       for (int l = 0; l < p->n_style; ++l) {
         CK(launch_conv_tc(p->scale[p->style_conv[l]], CONV_SCALE, g_num_sms, s));
         ++nl;
+        TM(NST_K_GRAM_BWD, p->style_conv[l]);
       }
       for (int l = 0; l < p->n_content; ++l) {
         const int i = p->content_conv[l];
@@ -749,13 +783,16 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
         CK(launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel,
                                gcoef, 1, s));
         ++nl;
+        TM(NST_K_CONTENT, i);
       }
       for (int i = p->n_layers - 1; i >= 1; --i) {
         CK(launch_conv_tc(p->dgrad[i], CONV_DGRAD, g_num_sms, s));
         ++nl;
+        TM(NST_K_CONV_DGRAD, i);
       }
       CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
       ++nl;
+      TM(NST_K_CONV1_DGRAD, 0);
     } else {
       CK(cudaMemcpyAsync(grad, p->grad_pix, static_cast<size_t>(3) * p->H * p->W * sizeof(float),
                          cudaMemcpyDeviceToDevice, s));
@@ -772,6 +809,60 @@ extern "C" int nst_plan_eval(nst_plan* p, const float* x, float* losses, float* 
   CKI(eval_enqueue(p, x, grad, nullptr, nullptr, nullptr, s));
   if (losses) CK(cudaMemcpyAsync(losses, p->losses, NST_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return NST_OK;
+}
+
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+
+static int timer_collect(LaunchTimer& tm, nst_launch_time* out, int max_out, cudaStream_t s) {
+  CK(cudaStreamSynchronize(s));
+  int n = 0;
+  for (size_t i = 1; i < tm.ev.size() && n < max_out; ++i) {
+    if (tm.kind[i] == NST_K_START) continue;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, tm.ev[i - 1], tm.ev[i]));
+    out[n].kind = tm.kind[i];
+    out[n].layer = tm.layer[i];
+    out[n].ms = ms;
+    ++n;
+  }
+  return n;
+}
+
+extern "C" int nst_plan_eval_timed(nst_plan* p, const float* x, float* grad, nst_launch_time* out, int max_out,
+                                   void* stream) {
+  if (!p || !x || !out || max_out < 1) return fail(NST_ERR_ARG, "nst_plan_eval_timed: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LaunchTimer tm;
+  tm.s = s;
+  // let the host run ahead of the device so that event-to-event times contain no launch gaps
+  spin_kernel<<<1, 1, 0, s>>>(600000);
+  CK(cudaGetLastError());
+  CKI(eval_enqueue(p, x, grad, nullptr, nullptr, nullptr, s, &tm));
+  return timer_collect(tm, out, max_out, s);
+}
+
+extern "C" int nst_lbfgs_iteration_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
+  if (!p || !out || max_out < 4) return fail(NST_ERR_ARG, "nst_lbfgs_iteration_timed: bad arguments");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LaunchTimer tm;
+  tm.s = s;
+  spin_kernel<<<1, 1, 0, s>>>(200000);
+  CK(cudaGetLastError());
+  if (tm.mark(NST_K_START, -1) != 0) return fail(NST_ERR_CUDA, "event record failed");
+  CK(launch_lbfgs_pass1(p->lb, s));
+  tm.mark(NST_K_LBFGS_PASS1, -1);
+  CK(launch_lbfgs_reduce(p->lb, s));
+  tm.mark(NST_K_LBFGS_REDUCE, -1);
+  CK(launch_lbfgs_control(p->lb, NST_CTL_MID, s));
+  tm.mark(NST_K_LBFGS_CONTROL, -1);
+  CK(launch_lbfgs_pass2(p->lb, s));
+  tm.mark(NST_K_LBFGS_PASS2, -1);
+  return timer_collect(tm, out, max_out, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -896,20 +987,34 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
   return NST_OK;
 }
 
-static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s) {
+// One optimizer.step(closure).  max_evals < 20 truncates the step after that many evaluations (used to time an
+// exact number of evaluations; the optimizer state stays valid - it looks like a step that ended early).
+static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals = 20) {
   LbfgsBuffers& b = p->lb;
-  int nl = 0;
+  int nl = 0, evals = 0;
   CK(launch_lbfgs_step_begin(b, s));
   ++nl;
   CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));
+  ++evals;
   const int max_iter = 20;  // torch.optim.LBFGS default, run_style_transfer.py:90
-  for (int k = 1; k <= max_iter; ++k) {
+  for (int k = 1; k <= max_iter && evals < max_evals + (max_evals >= 20 ? 1 : 0); ++k) {
     CK(launch_lbfgs_iteration(b, k == 1 ? NST_CTL_BEGIN : NST_CTL_MID, s));
     nl += 4;
-    if (k != max_iter) CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));  // lbfgs.py:493-502
+    if (k != max_iter) {
+      CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));  // lbfgs.py:493-502
+      ++evals;
+    }
   }
   if (launches) *launches = nl;
   return NST_OK;
+}
+
+extern "C" int nst_lbfgs_partial_step(nst_plan* p, int n_evals, void* stream) {
+  if (!p || n_evals < 1 || n_evals > 20) return fail(NST_ERR_ARG, "nst_lbfgs_partial_step: n_evals must be 1..20");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  int nl = 0;
+  CKI(step_enqueue(p, &nl, static_cast<cudaStream_t>(stream), n_evals));
+  return nl;
 }
 
 extern "C" int nst_lbfgs_step(nst_plan* p, void* stream) {

@@ -300,19 +300,30 @@ cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s) {
+cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s) {
   lbfgs_pass1_kernel<<<b.nblocks, LB_THREADS, 0, s>>>(b);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s) {
   const int warps_per_blk = 8;
   lbfgs_pass1_reduce_kernel<<<(LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s>>>(b);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+cudaError_t launch_lbfgs_control(const LbfgsBuffers& b, int mode, cudaStream_t s) {
   lbfgs_control_kernel<<<1, 32, 0, s>>>(b, mode);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s) {
   lbfgs_pass2_kernel<<<b.nblocks, LB_THREADS, 0, s>>>(b);
   return cudaGetLastError();
+}
+
+cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s) {
+  cudaError_t e = launch_lbfgs_pass1(b, s);
+  if (e == cudaSuccess) e = launch_lbfgs_reduce(b, s);
+  if (e == cudaSuccess) e = launch_lbfgs_control(b, mode, s);
+  if (e == cudaSuccess) e = launch_lbfgs_pass2(b, s);
+  return e;
 }
 
 }  // namespace nst

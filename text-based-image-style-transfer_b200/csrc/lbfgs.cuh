@@ -35,7 +35,12 @@ struct LbfgsBuffers {
 void lbfgs_plan(LbfgsBuffers& b, int num_sms);
 // clears ctl.stop at step() entry
 cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s);
-// pass 1 + reduction + controller + pass 2 : one L-BFGS iteration after an evaluation
+// the four launches of one iteration, individually (timing) ...
+cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s);
+cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s);
+cudaError_t launch_lbfgs_control(const LbfgsBuffers& b, int mode, cudaStream_t s);
+cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s);
+// ... and together: pass 1 + reduction + controller + pass 2 = one L-BFGS iteration after an evaluation
 cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s);
 
 }  // namespace nst

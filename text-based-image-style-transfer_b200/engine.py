@@ -218,6 +218,25 @@ class Plan:
                                                   _stream_ptr(self.device)))
         return buf[:rows].clone()
 
+    def lbfgs_partial_step(self, n_evals: int) -> int:
+        with torch.cuda.device(self.device):
+            return check(self.lib.nst_lbfgs_partial_step(self.handle, int(n_evals), _stream_ptr(self.device)))
+
+    def eval_timed(self, x: torch.Tensor):
+        """One evaluation with a CUDA event after every launch -> list of (kind name, conv index, ms)."""
+        x = self._img(x)
+        grad = torch.empty((1, 3, self.H, self.W), device=self.device, dtype=torch.float32)
+        buf = (_lib.NstLaunchTime * 128)()
+        with torch.cuda.device(self.device):
+            n = check(self.lib.nst_plan_eval_timed(self.handle, _ptr(x), _ptr(grad), buf, 128, _stream_ptr(self.device)))
+        return [(_lib.KIND_NAMES.get(buf[i].kind, str(buf[i].kind)), buf[i].layer, buf[i].ms) for i in range(n)]
+
+    def lbfgs_iteration_timed(self):
+        buf = (_lib.NstLaunchTime * 8)()
+        with torch.cuda.device(self.device):
+            n = check(self.lib.nst_lbfgs_iteration_timed(self.handle, buf, 8, _stream_ptr(self.device)))
+        return [(_lib.KIND_NAMES.get(buf[i].kind, str(buf[i].kind)), buf[i].layer, buf[i].ms) for i in range(n)]
+
     def launches_per_step(self) -> int:
         return int(self.lib.nst_lbfgs_launches_per_step(self.handle))
 
