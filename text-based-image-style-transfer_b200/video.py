@@ -1,0 +1,122 @@
+"""Frame / image-pair sharding across the GPUs of one box.
+
+The path shards across independent images only: one optimisation is a strictly sequential chain, but video frames
+(apply_video_process, app.py:784-815) and batches of content/style pairs are independent - the reference processes
+them one after another, rebuilding the VGG trunk and the style targets for every frame (app.py:794-798).  Here every
+rank (one process per GPU, torch.distributed) takes a contiguous block of frames, the style Gram targets are computed
+once on rank 0 and broadcast (5 matrices, 2.44 MB), and the finished uint8 frames are all-gathered in frame order.
+No collective sits inside the optimisation step.  The JPEG round trip of app.py:790-791 and the video container I/O
+(app.py:777-779, 843-859) are outside this path.
+"""
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+STYLE_CHANNELS = {"conv1_1": 64, "conv2_1": 128, "conv3_1": 256, "conv4_1": 512, "conv5_1": 512}
+
+
+def shard_range(n_items: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of rank `rank`: blocks differ by at most one item, earlier ranks take the remainder."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def broadcast_style_targets(targets: Optional[Dict[str, torch.Tensor]], layers: Sequence[str], device, src: int = 0):
+    """Rank `src` passes its Gram targets {layer: (1,C,C)}; every rank returns the same dict.  One broadcast of the
+    concatenated matrices (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return targets
+    sizes = [STYLE_CHANNELS[n] for n in layers]
+    flat = torch.empty(sum(c * c for c in sizes), device=device, dtype=torch.float32)
+    if dist.get_rank() == src:
+        flat.copy_(torch.cat([targets[n].reshape(-1).to(device=device, dtype=torch.float32) for n in layers]))
+    dist.broadcast(flat, src=src)
+    out, off = {}, 0
+    for n, c in zip(layers, sizes):
+        out[n] = flat[off:off + c * c].reshape(1, c, c).clone()
+        off += c * c
+    return out
+
+
+def gather_frames(local: torch.Tensor, n_total: int, device) -> Optional[torch.Tensor]:
+    """local: this rank's finished frames (k, H, W, 3) uint8 in frame order.  Returns all frames (n_total, H, W, 3)
+    on every rank (all_gather of equal-sized, zero-padded blocks; 2.76 MB per 720p frame)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    per = (n_total + world - 1) // world
+    shape = tuple(local.shape[1:])
+    pad = torch.zeros((per,) + shape, dtype=torch.uint8, device=device)
+    pad[:local.shape[0]].copy_(local.to(device))
+    out = torch.empty((world * per,) + shape, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, pad)
+    pieces = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, world, r)
+        pieces.append(out[r * per:r * per + (hi - lo)])
+    return torch.cat(pieces, 0)
+
+
+def run_sharded(frames: torch.Tensor, process_frame: Callable[[int, torch.Tensor], torch.Tensor], device) -> torch.Tensor:
+    """frames: (N, H, W, 3) uint8 (host).  process_frame(index, frame_u8) -> stylised (H, W, 3) uint8 tensor.
+    Every rank processes its block; returns all stylised frames in order."""
+    dist = _dist()
+    world = dist.get_world_size() if dist else 1
+    rank = dist.get_rank() if dist else 0
+    lo, hi = shard_range(frames.shape[0], world, rank)
+    done = [process_frame(k, frames[k]) for k in range(lo, hi)]
+    local = torch.stack(done, 0) if done else torch.empty((0,) + tuple(frames.shape[1:]), dtype=torch.uint8)
+    return gather_frames(local, frames.shape[0], device)
+
+
+class FrameStyler:
+    """Per-GPU worker for a stream of equally sized frames sharing one style: the per-frame body of
+    apply_video_process (app.py:794-798 -> run_multi_style_transfer) with everything frame-independent hoisted."""
+
+    def __init__(self, vgg_mean, vgg_std, frame_hw, style_imgs: List[torch.Tensor], w_style, w_content, w_tv, w_edge,
+                 num_steps: int, style_img_weight=0.5, channel_attention=False, device="cuda"):
+        from .multi_style_transfer.run_style_transfer import StyleTransferSession, STYLE_LAYERS, channel_attention_weights
+        from .engine import _require_cuda
+        self.device = _require_cuda(device)
+        dist = _dist()
+        rank = dist.get_rank() if dist else 0
+        targets = None
+        if dist is not None and dist.get_world_size() > 1:
+            if rank == 0:
+                s0 = StyleTransferSession(vgg_mean, vgg_std, frame_hw, style_imgs, w_style, w_content, w_tv, w_edge,
+                                          style_img_weight, self.device)
+                targets = s0.style_targets
+                self.session = s0
+            targets = broadcast_style_targets(targets, STYLE_LAYERS, self.device)
+        if not hasattr(self, "session"):
+            self.session = StyleTransferSession(vgg_mean, vgg_std, frame_hw, style_imgs, w_style, w_content, w_tv, w_edge,
+                                                style_img_weight, self.device, style_targets=targets)
+        self.num_steps = int(num_steps)
+        self.ca = None
+        if channel_attention:
+            # ChannelAttention is re-created (re-seeded, run_style_transfer.py:52) for every call of the reference:
+            # the gate weights are the same for every frame
+            torch.manual_seed(101)
+            w1, w2 = channel_attention_weights(512)
+            self.ca = (w1.to(self.device).contiguous(), w2.to(self.device).contiguous())
+        H, W = int(frame_hw[0]), int(frame_hw[1])
+        self._in = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        self._out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def __call__(self, index: int, frame_u8: torch.Tensor) -> torch.Tensor:
+        self._in.copy_(frame_u8)
+        s = self.session
+        with torch.cuda.device(self.device), torch.cuda.stream(s.stream):
+            s.plan.run_frame_host(self._in, self._out, self.num_steps, *(self.ca or (None, None)))
+        return self._out.clone()
+
+    def close(self):
+        self.session.close()
