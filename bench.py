@@ -265,37 +265,46 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel class, measured live with CUDA events (one event after every launch)
+    # ---- roofline of the dominant kernel class, measured live with CUDA events: two whole optimizer.step()s are run
+    #      with an event after every launch (single stream, no graph), so every kernel is timed inside a long busy stream
     pk = peaks()
     sess.prepare(content, trace_capacity=Wm + K + 64)
-    enqueue_evals(40)
+    enqueue_evals(120)                                            # history full (m = 100): steady state of a 320-evaluation run
     stream.synchronize()
     with torch.cuda.stream(stream):
-        x_now = plan.lbfgs_x()
-        rows = None
-        for _ in range(3):
-            r = plan.eval_timed(x_now)
-            rows = r if rows is None else [(a[0], a[1], min(a[2], b[2])) for a, b in zip(rows, r)]
-        lb_rows = plan.lbfgs_iteration_timed()
-    conv_ms = sum(ms_ for k, l, ms_ in rows if k in ("conv_fwd", "conv_dgrad", "gram_bwd"))
-    conv_launches = sum(1 for k, l, ms_ in rows if k in ("conv_fwd", "conv_dgrad", "gram_bwd"))
+        raw = plan.lbfgs_step_timed() + plan.lbfgs_step_timed()
+    m_now = sess.status().hist_len
+    acc = {}
+    for k, l, ms_ in raw:
+        a = acc.setdefault((k, l), [0.0, 0])
+        a[0] += ms_
+        a[1] += 1
+    rows = [(k, l, v[0] / v[1]) for (k, l), v in acc.items()]         # mean ms per launch of each (kind, conv)
+    n_evals_timed = acc[("pixel", -1)][1]
+    per_eval = lambda kinds: sum(v[0] for (k, l), v in acc.items() if k in kinds) / n_evals_timed  # noqa: E731
+    conv_kinds = ("conv_fwd", "conv_dgrad", "gram_bwd")
+    conv_ms = per_eval(conv_kinds)
+    conv_launches = sum(1 for (k, l) in acc if k in conv_kinds)
     conv_fl = 2.0 * sum(synth.conv_flops(i, S, S) for i in range(1, 13)) + sum(synth.gram_flops(i, S, S) for i in synth._STYLE)
-    eval_ms = sum(ms_ for _, _, ms_ in rows)
+    lb_kinds = ("lbfgs_pass1", "lbfgs_reduce", "lbfgs_control", "lbfgs_pass2")
+    eval_ms = sum(v[0] for (k, l), v in acc.items() if k not in lb_kinds) / n_evals_timed
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient + 5 Gram-backward launches per evaluation)",
                     achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
                     traffic=None, peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
-                    ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms)
-    m_now = sess.status().hist_len
-    lb_ms = sum(ms_ for k, _, ms_ in lb_rows if k in ("lbfgs_pass1", "lbfgs_pass2"))
-    lb_gbs = synth.lbfgs_bytes(S, S, m_now) / (lb_ms * 1e-3) / 1e9 if lb_ms > 0 else None
+                    ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms,
+                    how="CUDA events after every launch of 2 x 20 evaluations run back to back on one stream (nst_lbfgs_step_timed)")
+    lb_ms = per_eval(("lbfgs_pass1", "lbfgs_pass2"))
+    m_avg = m_now                                                 # 100: the history was full while the timed steps ran
+    lb_gbs = synth.lbfgs_bytes(S, S, m_avg) / (lb_ms * 1e-3) / 1e9 if lb_ms > 0 else None
     by_kind = {}
-    for k, l, ms_ in rows + lb_rows:
-        by_kind[k] = by_kind.get(k, 0.0) + ms_
+    for (k, l), v in acc.items():
+        by_kind[k] = by_kind.get(k, 0.0) + v[0] / n_evals_timed
     roofline_hbm = dict(bound="hbm", kernel="lbfgs_pass1_kernel + lbfgs_pass2_kernel", achieved=lb_gbs, peak=pk["hbm"], unit="GB/s",
-                        frac=(lb_gbs / pk["hbm"]) if lb_gbs else None, history_pairs=m_now,
-                        bytes_per_iteration=synth.lbfgs_bytes(S, S, m_now), ms=lb_ms)
+                        frac=(lb_gbs / pk["hbm"]) if lb_gbs else None, history_pairs=m_avg,
+                        bytes_per_iteration=synth.lbfgs_bytes(S, S, m_avg), ms=lb_ms)
+    lb_rows = []
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu = None

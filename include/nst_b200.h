@@ -179,9 +179,10 @@ typedef struct nst_launch_time {
 } nst_launch_time;
 /* one closure evaluation with an event after every launch; returns the number of rows written */
 int nst_plan_eval_timed(nst_plan* plan, const float* x, float* grad, nst_launch_time* out, int max_out, void* stream);
-/* one L-BFGS iteration (pass 1, reduce, controller, pass 2) on the current optimizer state, timed per launch.
- * It advances the optimizer like a regular iteration. */
-int nst_lbfgs_iteration_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
+/* one whole optimizer.step() (20 evaluations + 20 L-BFGS iterations, single stream, no graph) with an event after every
+ * launch, i.e. every kernel timed in the middle of a long busy stream; it advances the optimizer like nst_lbfgs_step.
+ * Returns the number of rows written (about 900). */
+int nst_lbfgs_step_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
 
 /* ---- host-buffer convenience (the e2e path: copies inside) ---------------------------------------
  * content_u8: [H,W,3] uint8 host; out_u8: [H,W,3] uint8 host (truncating, like ToPILImage).

@@ -19,8 +19,7 @@ class HostLbfgs:
         lib = C.CDLL(HOST_LIB)
         lib.nst_ctl_new.restype = C.c_void_p
         lib.nst_ctl_free.argtypes = [C.c_void_p]
-        lib.nst_ctl_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
-                                    C.c_int, C.c_int]
+        lib.nst_ctl_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int]
         lib.nst_ctl_begin_step.argtypes = [C.c_void_p]
         lib.nst_ctl_get_int.argtypes = [C.c_void_p, C.c_int]
         lib.nst_ctl_get_double.argtypes = [C.c_void_p, C.c_int]
@@ -37,9 +36,9 @@ class HostLbfgs:
         self.d = np.zeros(n, np.float32)
         self.S = np.zeros((self.slots, n), np.float32)
         self.Y = np.zeros((self.slots, n), np.float32)
-        self.M = np.zeros((2 * self.slots, 2 * self.slots), np.float64)
-        self.v = np.zeros(2 * self.slots, np.float64)
-        self.dots = np.zeros(self.slots * 6, np.float64)
+        self.ndot = lib.nst_ctl_ndot()
+        self.work = np.zeros(lib.nst_ctl_work_doubles(), np.float64)
+        self.dots = np.zeros(self.slots * self.ndot, np.float64)
         self.scal = np.zeros(8, np.float64)
         self.td_part = np.zeros(1, np.float32)
         self.closure = closure
@@ -95,11 +94,11 @@ class HostLbfgs:
         for i in range(hist_len):
             p = (head + i) % self.slots
             Sp, Yp = self.S[p].astype(f), self.Y[p].astype(f)
-            self.dots[6 * p:6 * p + 6] = [Sp @ s, Sp @ y, Sp @ g, Yp @ s, Yp @ y, Yp @ g]
+            self.dots[4 * p:4 * p + 4] = [Sp @ y, Sp @ g, Yp @ y, Yp @ g]
 
     def _ctl(self, mode):
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        self.lib.nst_ctl_run(self.ctl, p(self.M), p(self.v), p(self.dots), p(self.scal), C.c_float(float(self.loss)),
+        self.lib.nst_ctl_run(self.ctl, p(self.work), p(self.dots), p(self.scal), C.c_float(float(self.loss)),
                              p(self.td_part), 1, mode)
 
     def _pass2(self):

@@ -66,6 +66,7 @@ extern "C" int nst_device_check(void) {
   if (g_num_sms == 0) {
     e = conv_tc_init();
     if (e == cudaSuccess) e = gram_init();
+    if (e == cudaSuccess) e = lbfgs_init();
     if (e != cudaSuccess) return fail(NST_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(e));
     g_num_sms = prop.multiProcessorCount;
   }
@@ -164,8 +165,11 @@ struct nst_plan {
   __half* dh[GRAM_MAX_LAYERS] = {};
   float* alpha = nullptr;       // [GRAM_MAX_LAYERS]
   float* style_loss = nullptr;  // [GRAM_MAX_LAYERS]
-  GramParams gram;
+  GramParams gram_shallow;  // every style layer except a style layer on the deepest conv (side stream)
+  GramParams gram_deep;     // the style layer on the deepest conv, if any (critical path)
   float* gram_ws = nullptr;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[8] = {};
   // content
   int n_content = 0;
   int content_conv[NST_MAX_CONV] = {};
@@ -218,6 +222,9 @@ static void drop_graph(nst_plan* p) {
 extern "C" void nst_plan_destroy(nst_plan* p) {
   if (!p) return;
   drop_graph(p);
+  if (p->side) cudaStreamDestroy(p->side);
+  for (int k = 0; k < 8; ++k)
+    if (p->ev[k]) cudaEventDestroy(p->ev[k]);
   for (void* a : p->allocs) cudaFree(a);
   delete p;
 }
@@ -249,7 +256,8 @@ static int build_conv_params(nst_plan* p) {
     f.N = kCout[i];
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
-    if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], conv_block_n(kCout[i])) != 0)
+    f.block_n = conv_block_n(kCout[i], H, W, g_num_sms);
+    if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
     f.out_tap = p->tap[i];
@@ -267,7 +275,8 @@ static int build_conv_params(nst_plan* p) {
     d.N = kCin[i];
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
-    if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], conv_block_n(kCin[i])) != 0)
+    d.block_n = conv_block_n(kCin[i], H, W, g_num_sms);
+    if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
     d.out_grad = p->gpre[i - 1];
@@ -295,7 +304,8 @@ static int build_conv_params(nst_plan* p) {
     c.N = C;
     c.taps = 1;
     if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
-    if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, conv_block_n(C)) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
+    c.block_n = conv_block_n(C, c.H, c.W, g_num_sms);
+    if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
     c.alpha = p->alpha + l;
     c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
     conv_finalize_params(c, CONV_SCALE);
@@ -303,14 +313,17 @@ static int build_conv_params(nst_plan* p) {
   return NST_OK;
 }
 
+// Two parameter sets: the style layer on the deepest conv (critical path, main stream) and all the others (side stream).
 static int build_gram_params(nst_plan* p) {
-  GramParams& g = p->gram;
-  memset(&g, 0, sizeof(g));
-  g.num_layers = p->n_style;
+  GramParams* sets[2] = {&p->gram_shallow, &p->gram_deep};
+  memset(sets[0], 0, sizeof(GramParams));
+  memset(sets[1], 0, sizeof(GramParams));
   for (int l = 0; l < p->n_style; ++l) {
     const int i = p->style_conv[l];
     const int lv = kLevel[i];
-    GramLayer& L = g.L[l];
+    GramParams& g = *sets[i == p->n_layers - 1 ? 1 : 0];
+    const int k = g.num_layers++;
+    GramLayer& L = g.L[k];
     L.C = kCout[i];
     L.HW = p->lh[lv] * p->lw[lv];
     L.inv_norm = 1.f / (static_cast<float>(L.C) * static_cast<float>(L.HW));
@@ -322,7 +335,7 @@ static int build_gram_params(nst_plan* p) {
     // d/dF of w_s/n_style * mean((G-T)^2), G = F F^T / (C HW): 4 w_s (G-T) F / (n_style C^3 HW)
     L.grad_coef = 4.f * p->w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) *
                                       static_cast<float>(L.C) * static_cast<float>(L.C) * static_cast<float>(L.HW));
-    if (make_tmap_feat(&g.tm[l], p->tap[i], L.HW, L.C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
+    if (make_tmap_feat(&g.tm[k], p->tap[i], L.HW, L.C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
   }
   return NST_OK;
 }
@@ -430,13 +443,32 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
   PA(plan_alloc_t(p, &p->tv_part, pixel_blocks(H, W), true));
   PA(plan_alloc_t(p, &p->edge_part, pixel_blocks(H, W), true));
   PA(build_gram_params(p));
-  if (p->n_style > 0) {
-    const size_t ws = gram_plan(p->gram, g_num_sms);
-    PA(plan_alloc_t(p, &p->gram_ws, ws));
-    p->gram.ws = p->gram_ws;
-    float* fin = nullptr;
-    PA(plan_alloc_t(p, &fin, static_cast<size_t>(2) * p->gram.num_fin_blocks));
-    p->gram.fin_part = fin;
+  {
+    GramParams* sets[2] = {&p->gram_shallow, &p->gram_deep};
+    for (int k = 0; k < 2; ++k) {
+      if (sets[k]->num_layers == 0) continue;
+      // the side-stream set shares the SMs with the forward convolutions of the deeper layers: plan it for all
+      // SMs anyway (its CTAs run wherever a conv tile is not resident)
+      const size_t ws = gram_plan(*sets[k], g_num_sms);
+      float* wsp = nullptr;
+      float* fin = nullptr;
+      PA(plan_alloc_t(p, &wsp, ws));
+      PA(plan_alloc_t(p, &fin, static_cast<size_t>(2) * sets[k]->num_fin_blocks));
+      sets[k]->ws = wsp;
+      sets[k]->fin_part = fin;
+    }
+  }
+  {
+    cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      nst_plan_destroy(p);
+      return fail(NST_ERR_CUDA, "side stream / events: %s", cudaGetErrorString(e));
+    }
+    if (getenv("NST_NO_SIDE_STREAM") != nullptr) {
+      cudaStreamDestroy(p->side);
+      p->side = nullptr;
+    }
   }
   // ---- optimizer
   if (with_grad) {
@@ -451,10 +483,10 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.Y, static_cast<size_t>(NST_LBFGS_SLOTS) * b.n_pad, true));
     PA(plan_alloc_t(p, &b.part, static_cast<size_t>(b.nblocks) * LB_PART_STRIDE, true));
     PA(plan_alloc_t(p, &b.td_part, b.nblocks, true));
-    PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * 6, true));
+    PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * NST_LBFGS_NDOT, true));
     PA(plan_alloc_t(p, &b.scal, NST_LBFGS_NSCAL, true));
-    PA(plan_alloc_t(p, &b.M, static_cast<size_t>(4) * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS, true));
-    PA(plan_alloc_t(p, &b.v, 2 * NST_LBFGS_SLOTS, true));
+    PA(plan_alloc_t(p, &b.R, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS, true));
+    PA(plan_alloc_t(p, &b.YY, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS, true));
     PA(plan_alloc_t(p, &b.ctl, 1, true));
     b.eval_loss = p->losses;
   }
@@ -480,11 +512,13 @@ extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content,
   p->w_content = w_content;
   p->w_tv = w_tv;
   p->w_edge = w_edge;
-  for (int l = 0; l < p->n_style; ++l) {
-    GramLayer& L = p->gram.L[l];
-    L.grad_coef = 4.f * w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) * static_cast<float>(L.C) *
-                                   static_cast<float>(L.C) * static_cast<float>(L.HW));
-  }
+  GramParams* sets[2] = {&p->gram_shallow, &p->gram_deep};
+  for (int k = 0; k < 2; ++k)
+    for (int l = 0; l < sets[k]->num_layers; ++l) {
+      GramLayer& L = sets[k]->L[l];
+      L.grad_coef = 4.f * w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) * static_cast<float>(L.C) *
+                                     static_cast<float>(L.C) * static_cast<float>(L.HW));
+    }
   drop_graph(p);
   return NST_OK;
 }
@@ -701,41 +735,124 @@ struct LaunchTimer {
     if (tm && tm->mark((k), (l)) != 0) return fail(NST_ERR_CUDA, "event record failed"); \
   } while (0)
 
+// Enqueues one closure evaluation.  With a side stream (p->side, default) the evaluation is a small DAG: the
+// critical path conv forward -> Gram of the deepest style layer -> data gradients runs on `s`; everything that
+// only feeds it sideways (pixel-space losses, Gram + finalize + Gram-backward seeds of the shallower style layers,
+// content loss, loss assembly) runs on the side stream and fills the SMs that layers with fewer than 148 tiles
+// leave idle.  Under stream capture this becomes parallel branches of the CUDA graph.
 static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
                         cudaStream_t s, LaunchTimer* tm = nullptr) {
   int nl = 0;
   TM(NST_K_START, -1);
   const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
-  CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s));
+  if (grad != nullptr && !p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
+  const bool conc = tm == nullptr && p->side != nullptr && use_vgg;
+  cudaStream_t s2 = conc ? p->side : s;
+  enum { EV_FORK = 0, EV_TAPS = 1, EV_CONTENT_IN = 2, EV_CONTENT = 3, EV_SEEDS = 4, EV_GRAM = 5, EV_JOIN = 6 };
+  // record on `from`, make `to` wait
+  auto edge = [&](int ev, cudaStream_t from, cudaStream_t to) -> cudaError_t {
+    if (!conc) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(p->ev[ev], from);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(to, p->ev[ev], 0);
+    return e;
+  };
+  const int last = p->n_layers - 1;
+  const bool deep_style = use_vgg && p->n_style > 0 && p->style_conv[p->n_style - 1] == last;
+  const int n_shallow = use_vgg ? p->n_style - (deep_style ? 1 : 0) : 0;
+  const int max_shallow = n_shallow > 0 ? p->style_conv[n_shallow - 1] : -1;
+  int max_content = -1;
+  for (int l = 0; l < p->n_content; ++l)
+    if (p->content_conv[l] != last && p->content_conv[l] > max_content) max_content = p->content_conv[l];
+
+  auto content_launch = [&](int l, int accumulate, cudaStream_t st) -> cudaError_t {
+    const int i = p->content_conv[l];
+    const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+    // seed of the backward pass: d/dF of w_c/n_content * mean((F - Fc)^2).  A conv that is both a style and a
+    // content layer gets its Gram seed first, then this one in accumulate mode.
+    __nv_bfloat16* seed = nullptr;
+    if (grad != nullptr && (accumulate || style_index(p, i) < 0)) seed = i == last ? p->gpre[i] : p->gadd[i];
+    const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
+    return launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel, gcoef,
+                               accumulate, st);
+  };
+
+  // ---- side: pixel-space terms
+  CK(edge(EV_FORK, s, s2));
+  CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
   ++nl;
   TM(NST_K_PIXEL, -1);
   if (use_vgg) {
+    // ---- main: VGG forward
     CK(launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
     TM(NST_K_CONV1_FWD, 0);
+    if (max_shallow == 0) CK(edge(EV_TAPS, s, s2));
+    if (max_content == 0) CK(edge(EV_CONTENT_IN, s, s2));
     for (int i = 1; i < p->n_layers; ++i) {
       CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
       TM(NST_K_CONV_FWD, i);
+      if (i == max_shallow) {
+        // ---- side: Gram, style MSE and backward operand of the shallower style layers
+        CK(edge(EV_TAPS, s, s2));
+        CK(launch_gram(p->gram_shallow, s2));
+        nl += 3;
+        TM(NST_K_GRAM, 0);
+      }
+      if (i == max_content) {
+        CK(edge(EV_CONTENT_IN, s, s2));
+        for (int l = 0; l < p->n_content; ++l) {
+          if (p->content_conv[l] == last) continue;
+          CK(content_launch(l, 0, s2));
+          ++nl;
+          TM(NST_K_CONTENT, p->content_conv[l]);
+        }
+        if (grad != nullptr && conc) CK(cudaEventRecord(p->ev[EV_CONTENT], s2));
+      }
     }
     nl += p->n_layers;
-    if (p->n_style > 0) {
-      CK(launch_gram(p->gram, s));
+    if (max_shallow == 0) {
+      CK(launch_gram(p->gram_shallow, s2));
       nl += 3;
-      TM(NST_K_GRAM, -1);
+      TM(NST_K_GRAM, 0);
+    }
+    if (max_content == 0) {
+      for (int l = 0; l < p->n_content; ++l) {
+        if (p->content_conv[l] == last) continue;
+        CK(content_launch(l, 0, s2));
+        ++nl;
+      }
+      if (grad != nullptr && conc) CK(cudaEventRecord(p->ev[EV_CONTENT], s2));
+    }
+    // ---- main: the deepest layer's targets
+    if (deep_style) {
+      CK(launch_gram(p->gram_deep, s));
+      nl += 3;
+      TM(NST_K_GRAM, last);
     }
     for (int l = 0; l < p->n_content; ++l) {
-      const int i = p->content_conv[l];
-      const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
-      // seed of the backward pass: d/dF of w_c/n_content * mean((F - Fc)^2).  A conv that is both a style
-      // and a content layer gets its Gram seed first (backward section), then this one in accumulate mode.
-      __nv_bfloat16* seed = nullptr;
-      if (grad != nullptr && style_index(p, i) < 0) seed = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
-      const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
-      CK(launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel,
-                             gcoef, 0, s));
+      if (p->content_conv[l] != last) continue;
+      CK(content_launch(l, 0, s));
       ++nl;
-      TM(NST_K_CONTENT, i);
+      TM(NST_K_CONTENT, last);
     }
   }
+  // ---- side: Gram-backward seeds of the shallower style layers (deepest first: needed first)
+  if (grad != nullptr && use_vgg) {
+    for (int l = n_shallow - 1; l >= 0; --l) {
+      const int i = p->style_conv[l];
+      CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
+      ++nl;
+      TM(NST_K_GRAM_BWD, i);
+      const int cl = content_index(p, i);
+      if (cl >= 0) {
+        CK(content_launch(cl, 1, s2));
+        ++nl;
+        TM(NST_K_CONTENT, i);
+      }
+    }
+    if (conc) CK(cudaEventRecord(p->ev[EV_SEEDS], s2));
+  }
+  // ---- side: loss assembly (needs the deepest layer's Gram MSE / content partials from main)
+  CK(edge(EV_GRAM, s, s2));
   LossAssembleArgs a;
   memset(&a, 0, sizeof(a));
   a.tv_part = p->tv_part;
@@ -763,33 +880,33 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   a.stop_flag = stop_flag;
   a.trace = p->trace;
   a.trace_cap = p->trace_cap;
-  CK(launch_loss_assemble(a, s));
+  CK(launch_loss_assemble(a, s2));
   ++nl;
   TM(NST_K_ASSEMBLE, -1);
+  if (conc) CK(cudaEventRecord(p->ev[EV_JOIN], s2));
+  // ---- main: backward chain
   if (grad != nullptr) {
-    if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
     if (use_vgg) {
-      for (int l = 0; l < p->n_style; ++l) {
-        CK(launch_conv_tc(p->scale[p->style_conv[l]], CONV_SCALE, g_num_sms, s));
+      if (deep_style) {
+        CK(launch_conv_tc(p->scale[last], CONV_SCALE, g_num_sms, s));
         ++nl;
-        TM(NST_K_GRAM_BWD, p->style_conv[l]);
+        TM(NST_K_GRAM_BWD, last);
+        const int cl = content_index(p, last);
+        if (cl >= 0) {
+          CK(content_launch(cl, 1, s));
+          ++nl;
+          TM(NST_K_CONTENT, last);
+        }
       }
-      for (int l = 0; l < p->n_content; ++l) {
-        const int i = p->content_conv[l];
-        if (style_index(p, i) < 0) continue;
-        const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
-        const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
-        __nv_bfloat16* seed = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
-        CK(launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel,
-                               gcoef, 1, s));
-        ++nl;
-        TM(NST_K_CONTENT, i);
-      }
-      for (int i = p->n_layers - 1; i >= 1; --i) {
+      for (int i = last; i >= 1; --i) {
+        // conv i's data gradient adds the seed of conv i-1
+        if (conc && i - 1 == max_content) CK(cudaStreamWaitEvent(s, p->ev[EV_CONTENT], 0));
+        if (conc && i - 1 == max_shallow) CK(cudaStreamWaitEvent(s, p->ev[EV_SEEDS], 0));
         CK(launch_conv_tc(p->dgrad[i], CONV_DGRAD, g_num_sms, s));
         ++nl;
         TM(NST_K_CONV_DGRAD, i);
       }
+      if (conc) CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
       CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
       ++nl;
       TM(NST_K_CONV1_DGRAD, 0);
@@ -798,6 +915,8 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
                          cudaMemcpyDeviceToDevice, s));
       ++nl;
     }
+  } else if (conc) {
+    CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
   }
   if (launches) *launches += nl;
   return NST_OK;
@@ -845,23 +964,20 @@ extern "C" int nst_plan_eval_timed(nst_plan* p, const float* x, float* grad, nst
   return timer_collect(tm, out, max_out, s);
 }
 
-extern "C" int nst_lbfgs_iteration_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
-  if (!p || !out || max_out < 4) return fail(NST_ERR_ARG, "nst_lbfgs_iteration_timed: bad arguments");
+// forward declaration (defined with the L-BFGS loop below)
+static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm);
+
+extern "C" int nst_lbfgs_step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
+  if (!p || !out || max_out < 64) return fail(NST_ERR_ARG, "nst_lbfgs_step_timed: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   LaunchTimer tm;
   tm.s = s;
-  spin_kernel<<<1, 1, 0, s>>>(200000);
+  // let the host run ahead of the device so that event-to-event times contain no launch gaps
+  spin_kernel<<<1, 1, 0, s>>>(3000000);
   CK(cudaGetLastError());
-  if (tm.mark(NST_K_START, -1) != 0) return fail(NST_ERR_CUDA, "event record failed");
-  CK(launch_lbfgs_pass1(p->lb, s));
-  tm.mark(NST_K_LBFGS_PASS1, -1);
-  CK(launch_lbfgs_reduce(p->lb, s));
-  tm.mark(NST_K_LBFGS_REDUCE, -1);
-  CK(launch_lbfgs_control(p->lb, NST_CTL_MID, s));
-  tm.mark(NST_K_LBFGS_CONTROL, -1);
-  CK(launch_lbfgs_pass2(p->lb, s));
-  tm.mark(NST_K_LBFGS_PASS2, -1);
+  int nl = 0;
+  CKI(step_enqueue(p, &nl, s, 20, &tm));
   return timer_collect(tm, out, max_out, s);
 }
 
@@ -975,8 +1091,8 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
   h.trace_cap = p->trace_cap;
   CK(cudaMemcpyAsync(b.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));  // `h` lives on this stack frame
-  CK(cudaMemsetAsync(b.M, 0, static_cast<size_t>(4) * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS * sizeof(double), s));
-  CK(cudaMemsetAsync(b.v, 0, 2 * NST_LBFGS_SLOTS * sizeof(double), s));
+  CK(cudaMemsetAsync(b.R, 0, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS * sizeof(double), s));
+  CK(cudaMemsetAsync(b.YY, 0, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS * sizeof(double), s));
   CK(cudaMemsetAsync(b.x, 0, b.n_pad * sizeof(float), s));
   CK(cudaMemsetAsync(b.g, 0, b.n_pad * sizeof(float), s));
   CK(cudaMemsetAsync(b.g_prev, 0, b.n_pad * sizeof(float), s));
@@ -989,19 +1105,32 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
 
 // One optimizer.step(closure).  max_evals < 20 truncates the step after that many evaluations (used to time an
 // exact number of evaluations; the optimizer state stays valid - it looks like a step that ended early).
-static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals = 20) {
+static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm) {
   LbfgsBuffers& b = p->lb;
   int nl = 0, evals = 0;
   CK(launch_lbfgs_step_begin(b, s));
   ++nl;
-  CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));
+  CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s, tm));
   ++evals;
   const int max_iter = 20;  // torch.optim.LBFGS default, run_style_transfer.py:90
   for (int k = 1; k <= max_iter && evals < max_evals + (max_evals >= 20 ? 1 : 0); ++k) {
-    CK(launch_lbfgs_iteration(b, k == 1 ? NST_CTL_BEGIN : NST_CTL_MID, s));
+    const int mode = k == 1 ? NST_CTL_BEGIN : NST_CTL_MID;
+    if (tm == nullptr) {
+      CK(launch_lbfgs_iteration(b, mode, s));
+    } else {
+      TM(NST_K_START, -1);
+      CK(launch_lbfgs_pass1(b, s));
+      TM(NST_K_LBFGS_PASS1, -1);
+      CK(launch_lbfgs_reduce(b, s));
+      TM(NST_K_LBFGS_REDUCE, -1);
+      CK(launch_lbfgs_control(b, mode, s));
+      TM(NST_K_LBFGS_CONTROL, -1);
+      CK(launch_lbfgs_pass2(b, s));
+      TM(NST_K_LBFGS_PASS2, -1);
+    }
     nl += 4;
     if (k != max_iter) {
-      CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s));  // lbfgs.py:493-502
+      CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s, tm));  // lbfgs.py:493-502
       ++evals;
     }
   }
@@ -1013,7 +1142,7 @@ extern "C" int nst_lbfgs_partial_step(nst_plan* p, int n_evals, void* stream) {
   if (!p || n_evals < 1 || n_evals > 20) return fail(NST_ERR_ARG, "nst_lbfgs_partial_step: n_evals must be 1..20");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
   int nl = 0;
-  CKI(step_enqueue(p, &nl, static_cast<cudaStream_t>(stream), n_evals));
+  CKI(step_enqueue(p, &nl, static_cast<cudaStream_t>(stream), n_evals, nullptr));
   return nl;
 }
 
@@ -1024,12 +1153,12 @@ extern "C" int nst_lbfgs_step(nst_plan* p, void* stream) {
   static const bool no_graph = getenv("NST_NO_GRAPH") != nullptr;
   if (no_graph || s == nullptr) {
     // legacy default stream cannot be captured: enqueue directly
-    return step_enqueue(p, &p->launches_per_step, s);
+    return step_enqueue(p, &p->launches_per_step, s, 20, nullptr);
   }
   if (!p->step_graph) {
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int rc = step_enqueue(p, &p->launches_per_step, s);
+    const int rc = step_enqueue(p, &p->launches_per_step, s, 20, nullptr);
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (rc != NST_OK) {
       if (graph) cudaGraphDestroy(graph);

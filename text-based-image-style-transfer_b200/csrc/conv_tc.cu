@@ -401,10 +401,31 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, in
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-int conv_block_n(int N) { return N >= 256 ? 256 : (N >= 128 ? 128 : 64); }
+// Picks the N tile that minimises (waves over the SMs) x (time per tile).  The per-tile time model is the shared-memory
+// traffic of one K=16 MMA step (operand reads + the TMA writes that refill them, 128 B/clk): 192 / 128 / 96 cycles
+// for N = 256 / 128 / 64 - wide tiles are cheaper per FLOP, narrow tiles fill the 148 SMs when the image is small.
+int conv_block_n(int N, int H, int W, int num_sms) {
+  const int sp = ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
+  if (num_sms < 1) num_sms = 148;
+  int best = 64;
+  long best_cost = -1;
+  const int cand[3] = {256, 128, 64};
+  const int cyc[3] = {192, 128, 96};
+  for (int i = 0; i < 3; ++i) {
+    if (cand[i] > N || N % cand[i] != 0) continue;
+    const long tiles = static_cast<long>(sp) * (N / cand[i]);
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    const long cost = waves * cyc[i];
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = cand[i];
+    }
+  }
+  return best;
+}
 
 void conv_finalize_params(ConvParams& p, int mode) {
-  const int bn = conv_block_n(p.N);
+  const int bn = p.block_n;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_n = p.N / bn;
@@ -441,7 +462,7 @@ cudaError_t conv_tc_init() {
 
 template <int MODE>
 static cudaError_t launch_mode(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  switch (conv_block_n(p.N)) {
+  switch (p.block_n) {
     case 256: return launch_one<256, MODE>(p, num_sms, stream);
     case 128: return launch_one<128, MODE>(p, num_sms, stream);
     default: return launch_one<64, MODE>(p, num_sms, stream);

@@ -24,6 +24,7 @@ struct ConvParams {
   int H, W;        // pixel grid of the GEMM M dimension
   int K, N;        // channels contracted per tap, output channels
   int taps;        // 9 (3x3, pad 1) or 1 (1x1)
+  int block_n;     // N tile: 64, 128 or 256 (conv_block_n)
   int tiles_w, tiles_h, tiles_n, num_tiles;
   uint32_t idesc;
   // ---- CONV_FWD
@@ -46,8 +47,8 @@ struct ConvParams {
 int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n);
 
-// picks the N tile for a layer
-int conv_block_n(int N);
+// picks the N tile for a layer of N output channels on an H x W pixel grid
+int conv_block_n(int N, int H, int W, int num_sms);
 // fills tiles_* / idesc from H, W, K, N, taps and mode
 void conv_finalize_params(ConvParams& p, int mode);
 // sets the kernel attributes (opt-in shared memory) of every instantiation; call once per process

@@ -168,47 +168,65 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   }
 }
 
-// element of the upper-triangular block list handled by (block, thread)
+// element of the upper-triangular block list handled by a thread: 64 consecutive elements per block, the split-K
+// partials of each element are summed by 4 threads (splits s = q mod 4) and combined in a fixed order
 struct FinElem {
   int gi, gj;
   bool ok, offdiag;
   float g;
 };
+static constexpr int FIN_ELEMS = GRAM_FIN_THREADS / 4;
 
-__device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const GramLayer& L, int blk_in_layer) {
+__device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const GramLayer& L, int blk_in_layer, float* s_part) {
   FinElem e;
   const int tile = 128 * L.bn;
-  const int id = blk_in_layer * GRAM_FIN_THREADS + threadIdx.x;
+  const int el = threadIdx.x % FIN_ELEMS, q = threadIdx.x / FIN_ELEMS;
+  const int id = blk_in_layer * FIN_ELEMS + el;
   e.ok = id < L.pairs * tile;
   e.gi = e.gj = 0;
   e.offdiag = false;
   e.g = 0.f;
-  if (!e.ok) return e;
-  const int pair = id / tile;
-  const int rem = id - pair * tile;
-  const int li = rem / L.bn, lj = rem - li * L.bn;
-  int bi, bj;
-  gram_pair_to_blocks(pair, L.nblk, bi, bj);
-  e.gi = bi * 128 + li;
-  e.gj = bj * 128 + lj;
-  e.offdiag = bi != bj;
-  if (e.gi >= L.C || e.gj >= L.C) {
-    e.ok = false;
-    return e;
+  int pair = 0, li = 0, lj = 0;
+  if (e.ok) {
+    pair = id / tile;
+    const int rem = id - pair * tile;
+    li = rem / L.bn;
+    lj = rem - li * L.bn;
+    int bi, bj;
+    gram_pair_to_blocks(pair, L.nblk, bi, bj);
+    e.gi = bi * 128 + li;
+    e.gj = bj * 128 + lj;
+    e.offdiag = bi != bj;
+    if (e.gi >= L.C || e.gj >= L.C) e.ok = false;
   }
-  const float* src = p.ws + L.ws_off + (static_cast<size_t>(pair) * L.splits * 128 + li) * L.bn + lj;
-  float acc = 0.f;
-  for (int s = 0; s < L.splits; ++s) acc += src[static_cast<size_t>(s) * tile];
-  e.g = acc * L.inv_norm;
+  float a0 = 0.f, a1 = 0.f;
+  if (e.ok) {
+    const float* src = p.ws + L.ws_off + (static_cast<size_t>(pair) * L.splits * 128 + li) * L.bn + lj;
+    int s = q;
+    for (; s + 4 < L.splits; s += 8) {
+      a0 += src[static_cast<size_t>(s) * tile];
+      a1 += src[static_cast<size_t>(s + 4) * tile];
+    }
+    if (s < L.splits) a0 += src[static_cast<size_t>(s) * tile];
+  }
+  s_part[q * FIN_ELEMS + el] = a0 + a1;
+  __syncthreads();
+  if (q == 0 && e.ok) {
+    const float acc = ((s_part[el] + s_part[FIN_ELEMS + el]) + s_part[2 * FIN_ELEMS + el]) + s_part[3 * FIN_ELEMS + el];
+    e.g = acc * L.inv_norm;
+  }
+  if (q != 0) e.ok = false;
+  __syncthreads();
   return e;
 }
 
 // pass 1: reduce split-K partials, G or G - T, per-block (sum of squares, max abs)
 __global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize1_kernel(const __grid_constant__ GramParams p) {
   __shared__ float scratch[GRAM_FIN_THREADS / 32];
+  __shared__ float s_part[GRAM_FIN_THREADS];
   const int l = gram_find_layer_by_finblk(p, blockIdx.x);
   const GramLayer& L = p.L[l];
-  FinElem e = gram_fin_elem(p, L, blockIdx.x - L.fin_blk0);
+  FinElem e = gram_fin_elem(p, L, blockIdx.x - L.fin_blk0, s_part);
   float sq = 0.f, mx = 0.f;
   if (e.ok) {
     float d = e.g;
@@ -254,7 +272,8 @@ __global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize2_kernel(const 
   if (L.dh == nullptr) return;
   const float inv = mx > 0.f ? 1.f / mx : 0.f;
   const int tile = 128 * L.bn;
-  const int id = (blockIdx.x - L.fin_blk0) * GRAM_FIN_THREADS + threadIdx.x;
+  if (threadIdx.x >= FIN_ELEMS) return;
+  const int id = (blockIdx.x - L.fin_blk0) * FIN_ELEMS + threadIdx.x;
   if (id >= L.pairs * tile) return;
   const int pair = id / tile;
   const int rem = id - pair * tile;
@@ -310,7 +329,7 @@ size_t gram_plan(GramParams& p, int target_ctas) {
     L.item0 = item;
     item += L.pairs * L.splits;
     L.fin_blk0 = fin;
-    L.fin_blocks = (L.pairs * 128 * L.bn + GRAM_FIN_THREADS - 1) / GRAM_FIN_THREADS;
+    L.fin_blocks = (L.pairs * 128 * L.bn + FIN_ELEMS - 1) / FIN_ELEMS;
     fin += L.fin_blocks;
     L.ws_off = ws;
     ws += static_cast<size_t>(L.pairs) * L.splits * 128 * L.bn;

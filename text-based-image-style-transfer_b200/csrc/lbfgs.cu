@@ -30,6 +30,26 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   return acc;
 }
 
+// Reduces 4 per-lane values across the warp with 6 shuffles; on return lane 8*k (k = 0..3) holds value k in a[0].
+__device__ __forceinline__ void warp_reduce4(float (&a)[4], int lane) {
+  const bool up16 = (lane & 16) != 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = up16 ? a[k] : a[k + 2];
+    const float keep = up16 ? a[k + 2] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  const bool up8 = (lane & 8) != 0;
+  {
+    const float send = up8 ? a[0] : a[1];
+    const float keep = up8 ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 4);
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
 // Reduces 8 per-lane values across the warp with 9 shuffles (recursive halving);
 // on return lane 4*k (k = 0..7) holds the warp-wide sum of value k in a[0].
 __device__ __forceinline__ void warp_reduce8(float (&a)[8], int lane) {
@@ -66,7 +86,7 @@ __global__ void lbfgs_step_begin_kernel(NstLbfgsCtl* ctl) {
 // pass 1
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuffers b) {
-  __shared__ float wpart[LB_THREADS / 32][NST_LBFGS_SLOTS][6];
+  __shared__ float wpart[LB_THREADS / 32][NST_LBFGS_SLOTS][NST_LBFGS_NDOT];
   __shared__ float wscal[LB_THREADS / 32][NST_LBFGS_NSCAL];
   const NstLbfgsCtl* ctl = b.ctl;
   if (ctl->stop != NST_RUN) return;
@@ -128,37 +148,36 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
       a4[k] = ok[k] ? ld4_stream(Sp + off[k]) : z;
       c4[k] = ok[k] ? ld4_stream(Yp + off[k]) : z;
     }
-    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // S_p.y  S_p.g  Y_p.y  Y_p.g : all the recursion needs (lbfgs_ctl.h)
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      r[0] = dot4(a4[k], s4[k], r[0]);
-      r[1] = dot4(a4[k], y4[k], r[1]);
-      r[2] = dot4(a4[k], g4[k], r[2]);
-      r[3] = dot4(c4[k], s4[k], r[3]);
-      r[4] = dot4(c4[k], y4[k], r[4]);
-      r[5] = dot4(c4[k], g4[k], r[5]);
+      r[0] = dot4(a4[k], y4[k], r[0]);
+      r[1] = dot4(a4[k], g4[k], r[1]);
+      r[2] = dot4(c4[k], y4[k], r[2]);
+      r[3] = dot4(c4[k], g4[k], r[3]);
     }
-    warp_reduce8(r, lane);
-    if ((lane & 3) == 0 && (lane >> 2) < 6) wpart[warp][p][lane >> 2] = r[0];
+    warp_reduce4(r, lane);
+    if ((lane & 7) == 0) wpart[warp][p][lane >> 3] = r[0];
   }
   __syncthreads();
   // cross-warp sums in a fixed order -> per-block partials
   float* out = b.part + static_cast<size_t>(blockIdx.x) * LB_PART_STRIDE;
-  for (int idx = threadIdx.x; idx < len * 6; idx += LB_THREADS) {
-    const int i = idx / 6, q = idx - 6 * i;
+  for (int idx = threadIdx.x; idx < len * NST_LBFGS_NDOT; idx += LB_THREADS) {
+    const int i = idx / NST_LBFGS_NDOT, q = idx - NST_LBFGS_NDOT * i;
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < LB_THREADS / 32; ++w) acc += wpart[w][p][q];
-    out[p * 6 + q] = acc;
+    out[p * NST_LBFGS_NDOT + q] = acc;
   }
   if (threadIdx.x < NST_LBFGS_NSCAL) {
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < LB_THREADS / 32; ++w)
       acc = threadIdx.x == 6 ? fmaxf(acc, wscal[w][threadIdx.x]) : acc + wscal[w][threadIdx.x];
-    out[NST_LBFGS_SLOTS * 6 + threadIdx.x] = acc;
+    out[NST_LBFGS_SLOTS * NST_LBFGS_NDOT + threadIdx.x] = acc;
   }
 }
 
@@ -169,15 +188,15 @@ __global__ void __launch_bounds__(256) lbfgs_pass1_reduce_kernel(const LbfgsBuff
   const int lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= LB_PART_STRIDE) return;
-  const bool is_scal = o >= NST_LBFGS_SLOTS * 6;
+  const bool is_scal = o >= NST_LBFGS_SLOTS * NST_LBFGS_NDOT;
   if (!is_scal) {
     // skip slots that hold no stored pair
-    const int p = o / 6;
+    const int p = o / NST_LBFGS_NDOT;
     int rel = p - ctl->hist_head;
     if (rel < 0) rel += NST_LBFGS_SLOTS;
     if (rel >= ctl->hist_len) return;
   }
-  const bool is_max = o == NST_LBFGS_SLOTS * 6 + 6;
+  const bool is_max = o == NST_LBFGS_SLOTS * NST_LBFGS_NDOT + 6;
   double acc = 0.0;
   for (int blk = lane; blk < b.nblocks; blk += 32) {
     const double val = static_cast<double>(b.part[static_cast<size_t>(blk) * LB_PART_STRIDE + o]);
@@ -189,14 +208,38 @@ __global__ void __launch_bounds__(256) lbfgs_pass1_reduce_kernel(const LbfgsBuff
     acc = is_max ? fmax(acc, other) : acc + other;
   }
   if (lane == 0) {
-    if (is_scal) b.scal[o - NST_LBFGS_SLOTS * 6] = acc;
+    if (is_scal) b.scal[o - NST_LBFGS_SLOTS * NST_LBFGS_NDOT] = acc;
     else b.dots[o] = acc;
   }
 }
 
-__global__ void __launch_bounds__(32) lbfgs_control_kernel(const LbfgsBuffers b, int mode) {
-  __shared__ double cf[NST_LBFGS_NB + 1];
-  nst_lbfgs_control(b.ctl, b.M, b.v, cf, b.dots, b.scal, *b.eval_loss, b.td_part, b.nblocks, mode, 0);
+__global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const LbfgsBuffers b, int mode) {
+  extern __shared__ double ctl_smem[];
+  NstCtlWork w;
+  w.R = ctl_smem;
+  w.YY = w.R + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+  w.Sg = w.YY + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+  w.Yg = w.Sg + NST_LBFGS_SLOTS;
+  w.al = w.Yg + NST_LBFGS_SLOTS;
+  w.c = w.al + NST_LBFGS_SLOTS;
+  w.yq = w.c + NST_LBFGS_SLOTS;
+  w.red = w.yq + NST_LBFGS_SLOTS;
+  if (b.ctl->stop == NST_RUN && b.ctl->n_iter > 0) {
+    // stage the persistent dot-product matrices in shared memory (163 KB, L2 resident)
+    const double2* src_r = reinterpret_cast<const double2*>(b.R);
+    const double2* src_y = reinterpret_cast<const double2*>(b.YY);
+    constexpr int N2 = (NST_LBFGS_SLOTS * NST_LBFGS_SLOTS) / 2;
+    for (int i = threadIdx.x; i < N2; i += LB_CTL_THREADS) {
+      reinterpret_cast<double2*>(w.R)[i] = src_r[i];
+      reinterpret_cast<double2*>(w.YY)[i] = src_y[i];
+    }
+    if (threadIdx.x == 0) {
+      w.R[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1] = b.R[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1];
+      w.YY[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1] = b.YY[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1];
+    }
+  }
+  __syncthreads();
+  nst_lbfgs_control(b.ctl, w, b.R, b.YY, b.dots, b.scal, *b.eval_loss, b.td_part, b.nblocks, mode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -309,8 +352,11 @@ cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s) {
   lbfgs_pass1_reduce_kernel<<<(LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s>>>(b);
   return cudaGetLastError();
 }
+cudaError_t lbfgs_init() {
+  return cudaFuncSetAttribute(lbfgs_control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_CTL_SMEM);
+}
 cudaError_t launch_lbfgs_control(const LbfgsBuffers& b, int mode, cudaStream_t s) {
-  lbfgs_control_kernel<<<1, 32, 0, s>>>(b, mode);
+  lbfgs_control_kernel<<<1, LB_CTL_THREADS, LB_CTL_SMEM, s>>>(b, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s) {

@@ -9,7 +9,9 @@ namespace nst {
 static constexpr int LB_THREADS = 256;
 static constexpr int LB_VEC_PER_THREAD = 4;                        // float4 per thread per vector
 static constexpr int LB_MAX_VEC_PER_BLOCK = LB_THREADS * LB_VEC_PER_THREAD;
-static constexpr int LB_PART_STRIDE = NST_LBFGS_SLOTS * 6 + NST_LBFGS_NSCAL;  // floats per block in pass-1 partials
+static constexpr int LB_PART_STRIDE = NST_LBFGS_SLOTS * NST_LBFGS_NDOT + NST_LBFGS_NSCAL;  // floats per block in pass-1 partials
+static constexpr int LB_CTL_THREADS = 512;
+static constexpr int LB_CTL_SMEM = NST_CTL_WORK_DOUBLES * 8;
 
 struct LbfgsBuffers {
   int n_pad;        // vector length, multiple of 4; elements >= n are zero everywhere
@@ -23,16 +25,18 @@ struct LbfgsBuffers {
   float* Y;         // [SLOTS][n_pad] grad diffs (torch old_dirs)
   float* part;      // [nblocks][LB_PART_STRIDE] pass-1 per-block partial dots
   float* td_part;   // [nblocks] pass-2 per-block max|t d|
-  double* dots;     // [SLOTS*6] reduced
+  double* dots;     // [SLOTS*NDOT] reduced
   double* scal;     // [NSCAL] reduced
-  double* M;        // [2*SLOTS][2*SLOTS]
-  double* v;        // [2*SLOTS]
+  double* R;        // [SLOTS][SLOTS] s_i . y_j (upper triangle in age order)
+  double* YY;       // [SLOTS][SLOTS] y_i . y_j
   NstLbfgsCtl* ctl;
   const float* eval_loss;  // device scalar written by the evaluation (total loss)
 };
 
 // picks nblocks / vec_per_blk for a vector of n_pad floats
 void lbfgs_plan(LbfgsBuffers& b, int num_sms);
+// sets the controller kernel's opt-in shared memory; call once per process
+cudaError_t lbfgs_init();
 // clears ctl.stop at step() entry
 cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s);
 // the four launches of one iteration, individually (timing) ...

@@ -21,11 +21,23 @@ NstLbfgsCtl* nst_ctl_new(void) {
 }
 void nst_ctl_free(NstLbfgsCtl* c) { free(c); }
 
-// M: [2*SLOTS][2*SLOTS] doubles, v: [2*SLOTS] doubles (caller-owned, zero-initialised)
-void nst_ctl_run(NstLbfgsCtl* c, double* M, double* v, const double* dots, const double* scal, float eval_loss,
+int nst_ctl_ndot(void) { return NST_LBFGS_NDOT; }
+int nst_ctl_work_doubles(void) { return NST_CTL_WORK_DOUBLES; }
+
+// work: NST_CTL_WORK_DOUBLES doubles, zero-initialised and kept by the caller between calls (its R / YY parts are the
+// persistent dot-product matrices)
+void nst_ctl_run(NstLbfgsCtl* c, double* work, const double* dots, const double* scal, float eval_loss,
                  const float* td_part, int n_td, int mode) {
-  double cf[NST_LBFGS_NB + 1];
-  nst_lbfgs_control(c, M, v, cf, dots, scal, eval_loss, td_part, n_td, mode, 0);
+  NstCtlWork w;
+  w.R = work;
+  w.YY = w.R + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+  w.Sg = w.YY + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+  w.Yg = w.Sg + NST_LBFGS_SLOTS;
+  w.al = w.Yg + NST_LBFGS_SLOTS;
+  w.c = w.al + NST_LBFGS_SLOTS;
+  w.yq = w.c + NST_LBFGS_SLOTS;
+  w.red = w.yq + NST_LBFGS_SLOTS;
+  nst_lbfgs_control(c, w, w.R, w.YY, dots, scal, eval_loss, td_part, n_td, mode);
 }
 
 void nst_ctl_begin_step(NstLbfgsCtl* c) {

@@ -231,10 +231,11 @@ class Plan:
             n = check(self.lib.nst_plan_eval_timed(self.handle, _ptr(x), _ptr(grad), buf, 128, _stream_ptr(self.device)))
         return [(_lib.KIND_NAMES.get(buf[i].kind, str(buf[i].kind)), buf[i].layer, buf[i].ms) for i in range(n)]
 
-    def lbfgs_iteration_timed(self):
-        buf = (_lib.NstLaunchTime * 8)()
+    def lbfgs_step_timed(self):
+        """One whole optimizer.step() with a CUDA event after every launch -> list of (kind name, conv index, ms)."""
+        buf = (_lib.NstLaunchTime * 1200)()
         with torch.cuda.device(self.device):
-            n = check(self.lib.nst_lbfgs_iteration_timed(self.handle, buf, 8, _stream_ptr(self.device)))
+            n = check(self.lib.nst_lbfgs_step_timed(self.handle, buf, 1200, _stream_ptr(self.device)))
         return [(_lib.KIND_NAMES.get(buf[i].kind, str(buf[i].kind)), buf[i].layer, buf[i].ms) for i in range(n)]
 
     def launches_per_step(self) -> int:
