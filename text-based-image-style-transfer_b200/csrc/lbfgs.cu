@@ -226,16 +226,10 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
   w.red = w.yq + NST_LBFGS_SLOTS;
   if (b.ctl->stop == NST_RUN && b.ctl->n_iter > 0) {
     // stage the persistent dot-product matrices in shared memory (163 KB, L2 resident)
-    const double2* src_r = reinterpret_cast<const double2*>(b.R);
-    const double2* src_y = reinterpret_cast<const double2*>(b.YY);
-    constexpr int N2 = (NST_LBFGS_SLOTS * NST_LBFGS_SLOTS) / 2;
-    for (int i = threadIdx.x; i < N2; i += LB_CTL_THREADS) {
-      reinterpret_cast<double2*>(w.R)[i] = src_r[i];
-      reinterpret_cast<double2*>(w.YY)[i] = src_y[i];
-    }
-    if (threadIdx.x == 0) {
-      w.R[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1] = b.R[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1];
-      w.YY[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1] = b.YY[NST_LBFGS_SLOTS * NST_LBFGS_SLOTS - 1];
+    constexpr int N = NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+    for (int i = threadIdx.x; i < N; i += LB_CTL_THREADS) {
+      w.R[i] = b.R[i];
+      w.YY[i] = b.YY[i];
     }
   }
   __syncthreads();
