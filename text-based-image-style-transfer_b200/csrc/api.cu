@@ -113,6 +113,10 @@ extern "C" int nst_net_create(nst_net** out, const float* const* weights, const 
     if (e == cudaSuccess) e = cudaMalloc(&net->b32[i], kCout[i] * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpyAsync(net->w32[i], weights[i], nw * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(net->b32[i], biases[i], kCout[i] * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && i == 0) {
+      e = cudaMalloc(&net->wb[0], static_cast<size_t>(9) * 16 * 64 * sizeof(__nv_bfloat16));
+      if (e == cudaSuccess) e = launch_pack_weights_conv1_bwd(net->w32[0], net->wb[0], s);
+    }
     if (e == cudaSuccess && i >= 1) {
       e = cudaMalloc(&net->wf[i], nw * sizeof(__half));
       if (e == cudaSuccess) e = cudaMalloc(&net->wb[i], nw * sizeof(__nv_bfloat16));
@@ -255,7 +259,7 @@ static int build_conv_params(nst_plan* p) {
     f.K = kCin[i];
     f.N = kCout[i];
     f.taps = 9;
-    if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
+    if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
     f.block_n = conv_block_n(kCout[i], H, W, g_num_sms);
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
@@ -274,7 +278,7 @@ static int build_conv_params(nst_plan* p) {
     d.K = kCout[i];
     d.N = kCin[i];
     d.taps = 9;
-    if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
+    if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
     d.block_n = conv_block_n(kCin[i], H, W, g_num_sms);
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
@@ -291,6 +295,22 @@ static int build_conv_params(nst_plan* p) {
     conv_finalize_params(d, CONV_DGRAD);
   }
   if (!p->with_grad) return NST_OK;
+  {
+    // ---- conv1_1's data gradient on tensor cores: N = 16 (3 image channels + zero padding), K = 9 x 64
+    ConvParams& d = p->dgrad[0];
+    memset(&d, 0, sizeof(d));
+    d.H = p->H;
+    d.W = p->W;
+    d.K = 64;
+    d.N = 16;
+    d.taps = 9;
+    d.block_n = 16;
+    if (make_tmap_act(&d.tmA, p->gpre[0], p->H, p->W, 64, 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad 0)");
+    if (make_tmap_wgt(&d.tmB, net->wb[0], 9, 16, 64, 16) != 0) return fail(NST_ERR_CUDA, "tensor map (weights^T 0)");
+    d.grad_pix = p->grad_pix;
+    d.out_pix = nullptr;  // set per call
+    conv_finalize_params(d, CONV_DGRAD_PIX);
+  }
   // ---- Gram backward as a 1x1 convolution: seed[l] = alpha_l * F_l * (G_l - T_l)/max|.|
   for (int l = 0; l < p->n_style; ++l) {
     const int i = p->style_conv[l];
@@ -303,7 +323,7 @@ static int build_conv_params(nst_plan* p) {
     c.K = C;
     c.N = C;
     c.taps = 1;
-    if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, 16, 8) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
+    if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
     c.block_n = conv_block_n(C, c.H, c.W, g_num_sms);
     if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
     c.alpha = p->alpha + l;
@@ -479,8 +499,7 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.g, b.n_pad, true));
     PA(plan_alloc_t(p, &b.g_prev, b.n_pad, true));
     PA(plan_alloc_t(p, &b.d, b.n_pad, true));
-    PA(plan_alloc_t(p, &b.S, static_cast<size_t>(NST_LBFGS_SLOTS) * b.n_pad, true));
-    PA(plan_alloc_t(p, &b.Y, static_cast<size_t>(NST_LBFGS_SLOTS) * b.n_pad, true));
+    PA(plan_alloc_t(p, &b.hist, lbfgs_hist_floats(b), true));
     PA(plan_alloc_t(p, &b.part, static_cast<size_t>(b.nblocks) * LB_PART_STRIDE, true));
     PA(plan_alloc_t(p, &b.td_part, b.nblocks, true));
     PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * NST_LBFGS_NDOT, true));
@@ -907,7 +926,17 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
         TM(NST_K_CONV_DGRAD, i);
       }
       if (conc) CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
-      CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
+      {
+        static const bool cuda_core_conv1 = getenv("NST_CONV1_CUDA_CORES") != nullptr;
+        if (cuda_core_conv1) {
+          CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
+        } else {
+          ConvParams d = p->dgrad[0];
+          d.out_pix = grad;
+          for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
+          CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
+        }
+      }
       ++nl;
       TM(NST_K_CONV1_DGRAD, 0);
     } else {

@@ -4,12 +4,19 @@
 //   multi_style_transfer/helper_functions.py:94-101 (Vgg19.forward: nn.Conv2d + ReLU + MaxPool2d)
 // and their autograd data-gradients (run_style_transfer.py:140, loss.backward()).
 //
-// Tiling: one CTA tile = 8 x 16 output pixels (M = 128) x BLOCK_N output channels.  For every
-// filter tap and every 64-channel slice of the input, TMA loads the shifted 8x16x64 activation patch
-// (out-of-bounds -> zero = padding) and the [BLOCK_N x 64] weight slice into 128B-swizzled shared
-// memory; one elected thread issues four tcgen05.mma (K = 16 each) accumulating in TMEM.  The kernel
-// is persistent with two TMEM accumulator stages, so the epilogue of tile i overlaps the main loop
-// of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+// Tiling: one CTA tile = 16 x 8 output pixels (M = 128) x BLOCK_N output channels.  For every 64-channel slice of
+// the input, TMA loads ONE 18 x 10 x 64 halo patch (out-of-bounds -> zero = padding) into 128B-swizzled shared memory;
+// the nine filter taps are nine views of that patch: the A-operand descriptor starts (dr * 10 + ds) rows further and
+// steps 10 rows between 8-row groups (SBO = 1280 B).  tcgen05.mma applies the 128B swizzle to absolute shared-memory
+// addresses, so a descriptor may start on any 128-byte row (measured: profiles/r01_umma_descriptor_probe.log).
+// Only the [BLOCK_N x 64] weight slice is streamed per tap.  One elected thread issues four tcgen05.mma (K = 16
+// each) per (slice, tap), accumulating in TMEM.  The kernel is persistent with two TMEM accumulator stages, so the
+// epilogue of tile i overlaps the main loop of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer,
+// 2 = TMEM allocator, 4..7 = epilogue.
+//
+// Why the halo matters: the main loop is bound by shared-memory bandwidth (128 B/clk per SM, shared by the TMA
+// writes and the tensor core's operand reads).  Re-loading the patch per tap costs 16 KB of writes per 4 MMAs;
+// the halo costs 23 KB per 36.
 #include "conv_tc.cuh"
 #include "common.cuh"
 
@@ -18,22 +25,27 @@
 
 namespace nst {
 
-static constexpr int TILE_H = 8;
-static constexpr int TILE_W = 16;
+static constexpr int TILE_H = 16;
+static constexpr int TILE_W = 8;
 static constexpr int BLOCK_M = TILE_H * TILE_W;  // 128
 static constexpr int BLOCK_K = 64;               // 64 x 16-bit = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+static constexpr int HALO_ROWS = (TILE_H + 2) * (TILE_W + 2);     // 180 pixels
+static constexpr int HALO_TX_BYTES = HALO_ROWS * BLOCK_K * 2;     // 23040
+static constexpr int HALO_STAGE_BYTES = 23 * 1024;                // keeps the next stage 1024-byte aligned
+static constexpr int HALO_STAGES = 2;
+static constexpr int FLAT_TX_BYTES = BLOCK_M * BLOCK_K * 2;       // 1x1 convolution: no halo
 static constexpr int NUM_THREADS = 256;
 static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 
 template <int BLOCK_N>
 struct ConvCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int B_STAGES_FIT = (SMEM_BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
+  static constexpr int B_STAGES = B_STAGES_FIT > 8 ? 8 : B_STAGES_FIT;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
+  static constexpr int OPERAND_BYTES = HALO_STAGES * HALO_STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -93,17 +105,17 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
     if (p.out_act != nullptr && valid) store_h32(p.out_act + pix * p.N + n, v);
     return;
   }
-  // 2x2 max-pool across the four lanes {lane, lane^1, lane^16, lane^17}: tile rows are 16 pixels
-  // wide and a warp owns two consecutive rows.  The window position is folded into the two low
+  // 2x2 max-pool across the four lanes {lane, lane^1, lane^8, lane^9}: tile rows are 8 pixels
+  // wide and a warp owns four consecutive rows.  The window position is folded into the two low
   // mantissa bits so that one integer max gives both the value and PyTorch's first-max arg-max.
-  const uint32_t pos = ((lane >> 4) & 1) * 2 + (lane & 1);
+  const uint32_t pos = ((lane >> 3) & 1) * 2 + (lane & 1);
   float pooled[32];
   uint32_t win[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     uint32_t key = (__float_as_uint(v[j]) & ~3u) | (3u - pos);
     key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
-    key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
     pooled[j] = __uint_as_float(key & ~3u);
     win[j] = pooled[j] > 0.f ? 3u - (key & 3u) : 4u;
   }
@@ -201,15 +213,17 @@ template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle needs 1024-byte aligned tiles
+  // 128B swizzle needs 1024-byte aligned stages
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + Cfg::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::STAGES;
-  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint8_t* sB = smem + HALO_STAGES * HALO_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OPERAND_BYTES);
+  uint64_t* afull_bar = bars;
+  uint64_t* aempty_bar = afull_bar + HALO_STAGES;
+  uint64_t* bfull_bar = aempty_bar + HALO_STAGES;
+  uint64_t* bempty_bar = bfull_bar + Cfg::B_STAGES;
+  uint64_t* tfull_bar = bempty_bar + Cfg::B_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -221,9 +235,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < HALO_STAGES; ++s) {
+      mbar_init(&afull_bar[s], 1);
+      mbar_init(&aempty_bar[s], 1);
+    }
+    for (int s = 0; s < Cfg::B_STAGES; ++s) {
+      mbar_init(&bfull_bar[s], 1);
+      mbar_init(&bempty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -241,33 +259,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   const int k_slices = p.K / BLOCK_K;
-  const int num_k = p.taps * k_slices;
   const int pad = p.taps == 9 ? 1 : 0;
+  const int halo_w = TILE_W + 2 * pad;                     // pixels per patch row
+  const uint32_t a_tx = p.taps == 9 ? HALO_TX_BYTES : FLAT_TX_BYTES;
   const int sp_tiles = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aphase = 0, bphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile / sp_tiles;
         const int sp = tile - nt * sp_tiles;
         const int th = sp / p.tiles_w;
         const int tw = sp - th * p.tiles_w;
         const int h0 = th * TILE_H, w0 = tw * TILE_W, n0 = nt * BLOCK_N;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dr = p.taps == 9 ? tap / 3 : 0;
-          const int ds = p.taps == 9 ? tap - 3 * dr : 0;
-          for (int ks = 0; ks < k_slices; ++ks) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_3d(sA + stage * A_STAGE_BYTES, &p.tmA, &full_bar[stage], ks * BLOCK_K, w0 + ds - pad,
-                        h0 + dr - pad);
-            tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, &p.tmB, &full_bar[stage], ks * BLOCK_K, n0, tap);
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1u;
+        for (int ks = 0; ks < k_slices; ++ks) {
+          mbar_wait(&aempty_bar[as], aphase ^ 1u);
+          mbar_arrive_expect_tx(&afull_bar[as], a_tx);
+          tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA, &afull_bar[as], ks * BLOCK_K, w0 - pad, h0 - pad);
+          if (++as == HALO_STAGES) {
+            as = 0;
+            aphase ^= 1u;
+          }
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(&bempty_bar[bs], bphase ^ 1u);
+            mbar_arrive_expect_tx(&bfull_bar[bs], Cfg::B_STAGE_BYTES);
+            tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], ks * BLOCK_K, n0, tap);
+            if (++bs == Cfg::B_STAGES) {
+              bs = 0;
+              bphase ^= 1u;
             }
           }
         }
@@ -275,38 +297,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t aphase = 0;
+    int as = 0, bs = 0, ts = 0;
+    uint32_t aphase = 0, bphase = 0, tphase = 0;
+    const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;  // bytes between 8-pixel groups of the A operand
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      mbar_wait(&tempty_bar[ts], tphase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
+      for (int ks = 0; ks < k_slices; ++ks) {
+        mbar_wait(&afull_bar[as], aphase);
+        const uint32_t a_base = smem_u32(sA + as * HALO_STAGE_BYTES);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          mbar_wait(&bfull_bar[bs], bphase);
+          tc_fence_after();
+          if (elect_one()) {
+            const int dr = p.taps == 9 ? tap / 3 : 0;
+            const int ds = p.taps == 9 ? tap - 3 * dr : 0;
+            const uint32_t a_addr = a_base + static_cast<uint32_t>(dr * halo_w + ds) * 128u;
+            const uint32_t b_addr = smem_u32(sB + bs * Cfg::B_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-            umma_f16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, sbo);
+              const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+              umma_f16(d_tmem, da, db, p.idesc, (ks | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&bempty_bar[bs]);                                   // frees the weight slot when the MMAs retire
+            if (tap == p.taps - 1) umma_commit(&aempty_bar[as]);            // ... and the patch after its last tap
+            if (tap == p.taps - 1 && ks == k_slices - 1) umma_commit(&tfull_bar[ts]);  // accumulator complete
           }
-          umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
-          if (kb == num_k - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+          __syncwarp();
+          if (++bs == Cfg::B_STAGES) {
+            bs = 0;
+            bphase ^= 1u;
+          }
         }
-        __syncwarp();
-        if (++stage == Cfg::STAGES) {
-          stage = 0;
-          phase ^= 1u;
+        if (++as == HALO_STAGES) {
+          as = 0;
+          aphase ^= 1u;
         }
       }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1u;
+      if (++ts == 2) {
+        ts = 0;
+        tphase ^= 1u;
       }
     }
   } else if (warp >= 4) {
@@ -314,8 +346,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int t = q * 32 + lane;
     const int hl = t / TILE_W, wl = t % TILE_W;
-    int as = 0;
-    uint32_t aphase = 0;
+    int ts = 0;
+    uint32_t tphase = 0;
     float alpha = 0.f;
     if (MODE == CONV_SCALE) alpha = __ldg(p.alpha);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -325,9 +357,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const int tw = sp - th * p.tiles_w;
       const int h = th * TILE_H + hl, w = tw * TILE_W + wl, n0 = nt * BLOCK_N;
       const bool valid = h < p.H && w < p.W;
-      mbar_wait(&tfull_bar[as], aphase);
+      mbar_wait(&tfull_bar[ts], tphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * BLOCK_N);
+      if constexpr (MODE == CONV_DGRAD_PIX) {
+        // conv1_1: 3 of the 16 accumulator columns are image channels
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        if (valid) {
+          const size_t HW = static_cast<size_t>(p.H) * p.W;
+          const size_t o = static_cast<size_t>(h) * p.W + w;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float g = __uint_as_float(r[c]) * p.inv_std[c];
+            if (p.grad_pix != nullptr) g += p.grad_pix[c * HW + o];
+            p.out_pix[c * HW + o] = g;
+          }
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
@@ -343,10 +391,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1u;
+      if (lane == 0) mbar_arrive(&tempty_bar[ts]);
+      if (++ts == 2) {
+        ts = 0;
+        tphase ^= 1u;
       }
     }
   }
@@ -402,15 +450,16 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, in
 }
 
 // Picks the N tile that minimises (waves over the SMs) x (time per tile).  The per-tile time model is the shared-memory
-// traffic of one K=16 MMA step (operand reads + the TMA writes that refill them, 128 B/clk): 192 / 128 / 96 cycles
-// for N = 256 / 128 / 64 - wide tiles are cheaper per FLOP, narrow tiles fill the 148 SMs when the image is small.
+// traffic of one K=16 MMA step at 128 B/clk: operand reads (4 KB of A + N x 32 B of B) plus the TMA writes that refill
+// them (N x 32 B of weights + 1/36 of a halo patch): 161 / 99 / 68 cycles for N = 256 / 128 / 64 against 128 / 64 / 32
+// cycles of tensor-core time - wide tiles are cheaper per FLOP, narrow tiles fill the 148 SMs when the image is small.
 int conv_block_n(int N, int H, int W, int num_sms) {
   const int sp = ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
   if (num_sms < 1) num_sms = 148;
   int best = 64;
   long best_cost = -1;
   const int cand[3] = {256, 128, 64};
-  const int cyc[3] = {192, 128, 96};
+  const int cyc[3] = {161, 99, 68};
   for (int i = 0; i < 3; ++i) {
     if (cand[i] > N || N % cand[i] != 0) continue;
     const long tiles = static_cast<long>(sp) * (N / cand[i]);
@@ -430,7 +479,7 @@ void conv_finalize_params(ConvParams& p, int mode) {
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_n = p.N / bn;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  p.idesc = umma_idesc_f16(BLOCK_M, bn, mode == CONV_DGRAD ? 1 : 0, 0, 0);
+  p.idesc = umma_idesc_f16(BLOCK_M, bn, (mode == CONV_DGRAD || mode == CONV_DGRAD_PIX) ? 1 : 0, 0, 0);
 }
 
 template <int BLOCK_N, int MODE>
@@ -457,6 +506,7 @@ cudaError_t conv_tc_init() {
   cudaError_t e = init_mode<CONV_FWD>();
   if (e == cudaSuccess) e = init_mode<CONV_DGRAD>();
   if (e == cudaSuccess) e = init_mode<CONV_SCALE>();
+  if (e == cudaSuccess) e = init_one<16, CONV_DGRAD_PIX>();
   return e;
 }
 
@@ -470,6 +520,10 @@ static cudaError_t launch_mode(const ConvParams& p, int num_sms, cudaStream_t st
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p, int mode, int num_sms, cudaStream_t stream) {
+  if (mode == CONV_DGRAD_PIX) {
+    if (p.K % BLOCK_K != 0 || p.N != 16 || p.block_n != 16 || p.num_tiles <= 0) return cudaErrorInvalidValue;
+    return launch_one<16, CONV_DGRAD_PIX>(p, num_sms, stream);
+  }
   if (p.K % BLOCK_K != 0 || p.N % 64 != 0 || p.num_tiles <= 0) return cudaErrorInvalidValue;
   switch (mode) {
     case CONV_FWD: return launch_mode<CONV_FWD>(p, num_sms, stream);

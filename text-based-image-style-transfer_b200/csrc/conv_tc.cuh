@@ -8,10 +8,15 @@
 
 namespace nst {
 
+// output-pixel tile of one CTA (M = 128): activation tensor maps use a (64, W+2, H+2) box for 3x3, (64, W, H) for 1x1
+static constexpr int CONV_TILE_H = 16;
+static constexpr int CONV_TILE_W = 8;
+
 enum ConvMode : int {
   CONV_FWD = 0,    // fp16 operands; epilogue: +bias, optional pre-ReLU tap store, ReLU, optional 2x2 max-pool
   CONV_DGRAD = 1,  // bf16 operands; epilogue: ReLU mask or max-pool routing of the previous layer, + tap gradient
   CONV_SCALE = 2,  // fp16 operands; epilogue: out = alpha * acc as bf16 (Gram backward as a 1x1 convolution)
+  CONV_DGRAD_PIX = 3,  // bf16 operands, N = 16 (3 used): conv1_1's data gradient; epilogue: / std + pixel-term gradient -> fp32 [3,H,W]
 };
 
 // One launch = one convolution layer as an implicit GEMM:
@@ -41,6 +46,10 @@ struct ConvParams {
   int Hup, Wup;
   // ---- CONV_SCALE
   const float* alpha;  // device scalar
+  // ---- CONV_DGRAD_PIX
+  const float* grad_pix;  // [3,H,W] gradient of the TV + edge terms, or nullptr
+  float* out_pix;         // [3,H,W] fp32 gradient w.r.t. the raw image
+  float inv_std[3];       // d normalize / d x
 };
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)

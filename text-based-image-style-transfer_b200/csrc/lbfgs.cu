@@ -99,17 +99,22 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   const int nv = b.n_pad >> 2;
   const int v0 = blockIdx.x * b.vec_per_blk;
   const int v1 = min(nv, v0 + b.vec_per_blk);
+  const size_t row = static_cast<size_t>(b.vec_per_blk) * 4;  // floats per (slot, s|y) row of this block's region
+  float* hblk = b.hist + static_cast<size_t>(blockIdx.x) * (2 * NST_LBFGS_SLOTS) * row;
 
   float4 s4[LB_VEC_PER_THREAD], y4[LB_VEC_PER_THREAD], g4[LB_VEC_PER_THREAD];
-  size_t off[LB_VEC_PER_THREAD];
+  size_t off[LB_VEC_PER_THREAD];   // offset in the flat vectors (x, g, d, ...)
+  int hoff[LB_VEC_PER_THREAD];     // offset inside a history row
   bool ok[LB_VEC_PER_THREAD];
   float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float gmax = 0.f;
 #pragma unroll
   for (int i = 0; i < LB_VEC_PER_THREAD; ++i) {
-    const int vi = v0 + i * LB_THREADS + threadIdx.x;
+    const int lv = i * LB_THREADS + threadIdx.x;
+    const int vi = v0 + lv;
     ok[i] = vi < v1;
     off[i] = static_cast<size_t>(ok[i] ? vi : v0) * 4;
+    hoff[i] = (ok[i] ? lv : 0) * 4;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     g4[i] = ok[i] ? ld4(b.g + off[i]) : z;
     s4[i] = z;
@@ -119,8 +124,8 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
       const float4 dd = ld4(b.d + off[i]);
       y4[i] = make_float4(g4[i].x - gp.x, g4[i].y - gp.y, g4[i].z - gp.z, g4[i].w - gp.w);  // lbfgs.py:404
       s4[i] = make_float4(dd.x * t, dd.y * t, dd.z * t, dd.w * t);                          // lbfgs.py:405
-      st4(b.S + static_cast<size_t>(pn) * b.n_pad + off[i], s4[i]);
-      st4(b.Y + static_cast<size_t>(pn) * b.n_pad + off[i], y4[i]);
+      st4(hblk + (2 * pn) * row + hoff[i], s4[i]);
+      st4(hblk + (2 * pn + 1) * row + hoff[i], y4[i]);
     }
     sc[0] = dot4(s4[i], s4[i], sc[0]);
     sc[1] = dot4(s4[i], y4[i], sc[1]);
@@ -139,14 +144,14 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   for (int i = 0; i < len; ++i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
-    const float* Sp = b.S + static_cast<size_t>(p) * b.n_pad;
-    const float* Yp = b.Y + static_cast<size_t>(p) * b.n_pad;
+    const float* Sp = hblk + (2 * p) * row;
+    const float* Yp = Sp + row;
     float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      a4[k] = ok[k] ? ld4_stream(Sp + off[k]) : z;
-      c4[k] = ok[k] ? ld4_stream(Yp + off[k]) : z;
+      a4[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z;
+      c4[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z;
     }
     // S_p.y  S_p.g  Y_p.y  Y_p.g : all the recursion needs (lbfgs_ctl.h)
     float r[4] = {0.f, 0.f, 0.f, 0.f};
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
   w.al = w.Yg + NST_LBFGS_SLOTS;
   w.c = w.al + NST_LBFGS_SLOTS;
   w.yq = w.c + NST_LBFGS_SLOTS;
-  w.red = w.yq + NST_LBFGS_SLOTS;
+  w.ro = w.yq + NST_LBFGS_SLOTS;
+  w.red = w.ro + NST_LBFGS_SLOTS;
   if (b.ctl->stop == NST_RUN && b.ctl->n_iter > 0) {
     // stage the persistent dot-product matrices in shared memory (163 KB, L2 resident)
     constexpr int N = NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
@@ -253,16 +259,21 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
   const int nv = b.n_pad >> 2;
   const int v0 = blockIdx.x * b.vec_per_blk;
   const int v1 = min(nv, v0 + b.vec_per_blk);
+  const size_t row = static_cast<size_t>(b.vec_per_blk) * 4;
+  const float* hblk = b.hist + static_cast<size_t>(blockIdx.x) * (2 * NST_LBFGS_SLOTS) * row;
 
   float4 acc[LB_VEC_PER_THREAD];
   size_t off[LB_VEC_PER_THREAD];
+  int hoff[LB_VEC_PER_THREAD];
   bool ok[LB_VEC_PER_THREAD];
   const float cg = coef[NST_LBFGS_G];
 #pragma unroll
   for (int i = 0; i < LB_VEC_PER_THREAD; ++i) {
-    const int vi = v0 + i * LB_THREADS + threadIdx.x;
+    const int lv = i * LB_THREADS + threadIdx.x;
+    const int vi = v0 + lv;
     ok[i] = vi < v1;
     off[i] = static_cast<size_t>(ok[i] ? vi : v0) * 4;
+    hoff[i] = (ok[i] ? lv : 0) * 4;
     acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok[i]) {
       const float4 g = ld4(b.g + off[i]);
@@ -275,14 +286,14 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
     const float cs = coef[p], cy = coef[NST_LBFGS_SLOTS + p];
-    const float* Sp = b.S + static_cast<size_t>(p) * b.n_pad;
-    const float* Yp = b.Y + static_cast<size_t>(p) * b.n_pad;
+    const float* Sp = hblk + (2 * p) * row;
+    const float* Yp = Sp + row;
     float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      a4[k] = ok[k] ? ld4_stream(Sp + off[k]) : z;
-      c4[k] = ok[k] ? ld4_stream(Yp + off[k]) : z;
+      a4[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z;
+      c4[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z;
     }
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
@@ -330,6 +341,10 @@ void lbfgs_plan(LbfgsBuffers& b, int num_sms) {
   if (nblocks > nv) nblocks = nv > 0 ? nv : 1;
   b.nblocks = nblocks;
   b.vec_per_blk = (nv + nblocks - 1) / nblocks;
+}
+
+size_t lbfgs_hist_floats(const LbfgsBuffers& b) {
+  return static_cast<size_t>(b.nblocks) * (2 * NST_LBFGS_SLOTS) * static_cast<size_t>(b.vec_per_blk) * 4;
 }
 
 cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s) {

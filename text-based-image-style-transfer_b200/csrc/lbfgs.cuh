@@ -21,8 +21,10 @@ struct LbfgsBuffers {
   float* g;         // [n_pad] gradient of the latest evaluation
   float* g_prev;    // [n_pad]
   float* d;         // [n_pad] direction
-  float* S;         // [SLOTS][n_pad] steps      (torch old_stps)
-  float* Y;         // [SLOTS][n_pad] grad diffs (torch old_dirs)
+  // stored pairs, chunk-major: [nblocks][SLOTS][2 (s, y)][vec_per_blk * 4].  A block streams ONE contiguous region
+  // (~1 MB) instead of touching 2 x 101 vectors that are megabytes apart: the 0.64 GB history otherwise thrashes the
+  // TLB once more than ~60 pairs are stored (measured: pass 1 took 381 us at m = 100 against 75 us at m = 57).
+  float* hist;      // s = torch old_stps, y = torch old_dirs
   float* part;      // [nblocks][LB_PART_STRIDE] pass-1 per-block partial dots
   float* td_part;   // [nblocks] pass-2 per-block max|t d|
   double* dots;     // [SLOTS*NDOT] reduced
@@ -35,6 +37,8 @@ struct LbfgsBuffers {
 
 // picks nblocks / vec_per_blk for a vector of n_pad floats
 void lbfgs_plan(LbfgsBuffers& b, int num_sms);
+// floats in LbfgsBuffers::hist
+size_t lbfgs_hist_floats(const LbfgsBuffers& b);
 // sets the controller kernel's opt-in shared memory; call once per process
 cudaError_t lbfgs_init();
 // clears ctl.stop at step() entry

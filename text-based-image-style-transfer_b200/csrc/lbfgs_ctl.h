@@ -80,9 +80,10 @@ struct NstCtlWork {
   double* al;  // [SLOTS]
   double* c;   // [SLOTS] coefficient of s_i in d
   double* yq;  // [SLOTS] y_i . q
+  double* ro;  // [SLOTS] 1 / (y_i . s_i)
   double* red; // [4] broadcast scratch
 };
-#define NST_CTL_WORK_DOUBLES (2 * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS + 5 * NST_LBFGS_SLOTS + 4)
+#define NST_CTL_WORK_DOUBLES (2 * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS + 6 * NST_LBFGS_SLOTS + 4)
 
 #if defined(__CUDA_ARCH__)
 #define NST_HD __device__
@@ -217,24 +218,28 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
       c->yy = yy;
     }
     NST_BLOCK_SYNC();
-    // lbfgs.py:432-435: for i newest..oldest: al_i = ro_i (s_i . q); q -= al_i y_i        [warp 0, sequential]
+    for (int i = tid; i < len; i += nt) {
+      const int p = nst_ctl_slot(head, i);
+      w.ro[p] = c->ro[p];
+      w.c[p] = -w.Sg[p];  // running value of s_i . q
+    }
+    NST_BLOCK_SYNC();
+    // lbfgs.py:432-435: for k newest..oldest: al_k = ro_k (s_k . q); q -= al_k y_k.  Column oriented: once al_k is
+    // known every older row i subtracts al_k (s_i . y_k) from its running s_i . q - no reduction on the dependent chain.
     if (tid < NST_CTL_NL) {
-      for (int i = len - 1; i >= 0; --i) {
-        const int p = nst_ctl_slot(head, i);
-        double acc = 0.0;
-        for (int j = i + 1 + tid; j < len; j += NST_CTL_NL) {
-          const int pj = nst_ctl_slot(head, j);
-          acc += w.al[pj] * w.R[p * TOT + pj];
+      for (int k = len - 1; k >= 0; --k) {
+        const int pk = nst_ctl_slot(head, k);
+        const double al = w.ro[pk] * w.c[pk];
+        for (int i = tid; i < k; i += NST_CTL_NL) {
+          const int p = nst_ctl_slot(head, i);
+          w.c[p] -= al * w.R[p * TOT + pk];
         }
-        acc = nst_ctl_sum(acc);
-        const double al = c->ro[p] * (-w.Sg[p] - acc);
-        NST_WARP_SYNC();
-        if (tid == 0) w.al[p] = al;
+        if (tid == 0) w.al[pk] = al;
         NST_WARP_SYNC();
       }
     }
     NST_BLOCK_SYNC();
-    // y_i . q = -(y_i . g) - sum_j al_j (y_i . y_j)                                        [block parallel]
+    // y_i . r at the start of loop 2: H (y_i . q) = H (-(y_i . g) - sum_j al_j (y_i . y_j))          [block parallel]
     for (int i = tid; i < len; i += nt) {
       const int p = nst_ctl_slot(head, i);
       double acc = 0.0;
@@ -242,22 +247,20 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         const int pj = nst_ctl_slot(head, j);
         acc += w.al[pj] * w.YY[p * TOT + pj];
       }
-      w.yq[p] = -w.Yg[p] - acc;
+      w.yq[p] = H_diag * (-w.Yg[p] - acc);
     }
     NST_BLOCK_SYNC();
-    // lbfgs.py:439-442: r = H q; for i oldest..newest: be_i = ro_i (y_i . r); r += (al_i - be_i) s_i   [warp 0]
+    // lbfgs.py:439-442: r = H q; for k oldest..newest: be_k = ro_k (y_k . r); r += (al_k - be_k) s_k.  Once c_k is known
+    // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
     if (tid < NST_CTL_NL) {
-      for (int i = 0; i < len; ++i) {
-        const int p = nst_ctl_slot(head, i);
-        double acc = 0.0;
-        for (int j = tid; j < i; j += NST_CTL_NL) {
-          const int pj = nst_ctl_slot(head, j);
-          acc += w.c[pj] * w.R[pj * TOT + p];
+      for (int k = 0; k < len; ++k) {
+        const int pk = nst_ctl_slot(head, k);
+        const double ck = w.al[pk] - w.ro[pk] * w.yq[pk];
+        for (int i = k + 1 + tid; i < len; i += NST_CTL_NL) {
+          const int p = nst_ctl_slot(head, i);
+          w.yq[p] += ck * w.R[pk * TOT + p];
         }
-        acc = nst_ctl_sum(acc);
-        const double be = c->ro[p] * (H_diag * w.yq[p] + acc);
-        NST_WARP_SYNC();
-        if (tid == 0) w.c[p] = w.al[p] - be;
+        if (tid == 0) w.c[pk] = ck;
         NST_WARP_SYNC();
       }
     }

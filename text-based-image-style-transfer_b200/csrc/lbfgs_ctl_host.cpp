@@ -36,7 +36,8 @@ void nst_ctl_run(NstLbfgsCtl* c, double* work, const double* dots, const double*
   w.al = w.Yg + NST_LBFGS_SLOTS;
   w.c = w.al + NST_LBFGS_SLOTS;
   w.yq = w.c + NST_LBFGS_SLOTS;
-  w.red = w.yq + NST_LBFGS_SLOTS;
+  w.ro = w.yq + NST_LBFGS_SLOTS;
+  w.red = w.ro + NST_LBFGS_SLOTS;
   nst_lbfgs_control(c, w, w.R, w.YY, dots, scal, eval_loss, td_part, n_td, mode);
 }
 

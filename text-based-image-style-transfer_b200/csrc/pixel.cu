@@ -586,6 +586,20 @@ cudaError_t launch_pack_weights(const float* w, __half* w_fwd, __nv_bfloat16* w_
   return cudaGetLastError();
 }
 
+__global__ void pack_weights_conv1_bwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb) {
+  // wb[tap'][c][n] = w[n][c][2-r'][2-s'] for c < 3, zero for the 13 padding channels
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * 16 * 64; i += gridDim.x * blockDim.x) {
+    const int n = i % 64, c = (i / 64) % 16, tap = i / (64 * 16);
+    float v = 0.f;
+    if (c < 3) v = w[(n * 3 + c) * 9 + (8 - tap)];
+    wb[i] = __float2bfloat16_rn(v);
+  }
+}
+cudaError_t launch_pack_weights_conv1_bwd(const float* w, __nv_bfloat16* w_bwd, cudaStream_t s) {
+  pack_weights_conv1_bwd_kernel<<<36, 256, 0, s>>>(w, w_bwd);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // content target and channel attention
 // ------------------------------------------------------------------------------------------------

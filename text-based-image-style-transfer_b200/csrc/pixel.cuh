@@ -82,6 +82,9 @@ cudaError_t launch_nchw_float_to_nhwc_bf16(const float* in, __nv_bfloat16* out, 
 // data-gradient operand [9][Cin][Cout] bf16 (taps flipped)
 cudaError_t launch_pack_weights(const float* w, __half* w_fwd, __nv_bfloat16* w_bwd, int Cout, int Cin, cudaStream_t s);
 
+// conv1_1 data-gradient operand: torch [64,3,3,3] fp32 -> [9][16][64] bf16 (taps flipped, image channels padded 3 -> 16)
+cudaError_t launch_pack_weights_conv1_bwd(const float* w, __nv_bfloat16* w_bwd, cudaStream_t s);
+
 // content target: yc = float(y) * gate[c] (gate == nullptr -> 1)   (run_style_transfer.py:13-25, 94-96)
 cudaError_t launch_make_content_target(const __half* y, const float* gate, float* yc, size_t pixels, int C,
                                        cudaStream_t s);
