@@ -184,6 +184,9 @@ int nst_plan_eval_timed(nst_plan* plan, const float* x, float* grad, nst_launch_
  * Returns the number of rows written (about 900). */
 int nst_lbfgs_step_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
 
+/* phase timestamps (SM clock) of CTA 0 of one convolution launch: tuning aid, see tools/conv_phases.py */
+int nst_plan_conv_phases(nst_plan* plan, int conv, int mode, long long* out7, void* stream);
+
 /* ---- host-buffer convenience (the e2e path: copies inside) ---------------------------------------
  * content_u8: [H,W,3] uint8 host; out_u8: [H,W,3] uint8 host (truncating, like ToPILImage).
  * Requires style / content / edge targets to be refreshed from the content image, which this call

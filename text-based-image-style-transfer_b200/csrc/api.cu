@@ -1010,6 +1010,26 @@ extern "C" int nst_lbfgs_step_timed(nst_plan* p, nst_launch_time* out, int max_o
   return timer_collect(tm, out, max_out, s);
 }
 
+// Debug / tuning aid: runs one convolution launch of the plan (mode 0 forward, 1 data gradient) with phase
+// timestamps of CTA 0 -> out[7] (SM clock): 0 start, 1 setup done, 2 first operands landed, 3 last MMA issued,
+// 4 accumulator complete, 5 epilogue done, 6 exit.
+extern "C" int nst_plan_conv_phases(nst_plan* p, int conv, int mode, long long* out7, void* stream) {
+  if (!p || conv < 1 || conv >= p->n_layers || !out7) return fail(NST_ERR_ARG, "nst_plan_conv_phases: bad arguments");
+  if (mode == 1 && !p->with_grad) return fail(NST_ERR_STATE, "plan has no gradient buffers");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long* d = nullptr;
+  CK(cudaMalloc(&d, 8 * sizeof(long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, 8 * sizeof(long long), s);
+  ConvParams c = mode == 0 ? p->fwd[conv] : p->dgrad[conv];
+  c.dbg = d;
+  if (e == cudaSuccess) e = launch_conv_tc(c, mode == 0 ? CONV_FWD : CONV_DGRAD, g_num_sms, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, 7 * sizeof(long long), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_plan_conv_phases: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // function-level mirrors
 // ------------------------------------------------------------------------------------------------

@@ -229,6 +229,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+#define NST_STAMP(slot, cond)                                        \
+  do {                                                               \
+    if (dbg && (cond)) p.dbg[slot] = clock64();                      \
+  } while (0)
+  NST_STAMP(0, threadIdx.x == 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -257,6 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  NST_STAMP(1, threadIdx.x == 0);
 
   const int k_slices = p.K / BLOCK_K;
   const int pad = p.taps == 9 ? 1 : 0;
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
       for (int ks = 0; ks < k_slices; ++ks) {
         mbar_wait(&afull_bar[as], aphase);
+        NST_STAMP(2, lane == 0 && ks == 0 && tile == blockIdx.x);
         const uint32_t a_base = smem_u32(sA + as * HALO_STAGE_BYTES);
         for (int tap = 0; tap < p.taps; ++tap) {
           mbar_wait(&bfull_bar[bs], bphase);
@@ -336,6 +344,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           aphase ^= 1u;
         }
       }
+      NST_STAMP(3, lane == 0 && tile == blockIdx.x);
       if (++ts == 2) {
         ts = 0;
         tphase ^= 1u;
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const bool valid = h < p.H && w < p.W;
       mbar_wait(&tfull_bar[ts], tphase);
       tc_fence_after();
+      NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * BLOCK_N);
       if constexpr (MODE == CONV_DGRAD_PIX) {
         // conv1_1: 3 of the 16 accumulator columns are image channels
@@ -391,6 +401,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
       tc_fence_before();
       __syncwarp();
+      NST_STAMP(5, threadIdx.x == 128 && tile == blockIdx.x);
       if (lane == 0) mbar_arrive(&tempty_bar[ts]);
       if (++ts == 2) {
         ts = 0;
@@ -405,6 +416,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  NST_STAMP(6, threadIdx.x == 64);
+#undef NST_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------

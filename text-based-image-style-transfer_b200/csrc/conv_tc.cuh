@@ -50,6 +50,8 @@ struct ConvParams {
   const float* grad_pix;  // [3,H,W] gradient of the TV + edge terms, or nullptr
   float* out_pix;         // [3,H,W] fp32 gradient w.r.t. the raw image
   float inv_std[3];       // d normalize / d x
+  // ---- phase timestamps of CTA 0 (debug; nullptr in production): see tools/conv_phases.py
+  long long* dbg;
 };
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)

@@ -175,11 +175,11 @@ struct FinElem {
   bool ok, offdiag;
   float g;
 };
-static constexpr int FIN_ELEMS = GRAM_FIN_THREADS / 4;
-
 __device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const GramLayer& L, int blk_in_layer, float* s_part) {
   FinElem e;
   const int tile = 128 * L.bn;
+  const int QL = L.fin_q;                       // 1 or 4
+  const int FIN_ELEMS = GRAM_FIN_THREADS / QL;  // elements per block
   const int el = threadIdx.x % FIN_ELEMS, q = threadIdx.x / FIN_ELEMS;
   const int id = blk_in_layer * FIN_ELEMS + el;
   e.ok = id < L.pairs * tile;
@@ -203,11 +203,15 @@ __device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const Gram
   if (e.ok) {
     const float* src = p.ws + L.ws_off + (static_cast<size_t>(pair) * L.splits * 128 + li) * L.bn + lj;
     int s = q;
-    for (; s + 4 < L.splits; s += 8) {
+    for (; s + QL < L.splits; s += 2 * QL) {
       a0 += src[static_cast<size_t>(s) * tile];
-      a1 += src[static_cast<size_t>(s + 4) * tile];
+      a1 += src[static_cast<size_t>(s + QL) * tile];
     }
     if (s < L.splits) a0 += src[static_cast<size_t>(s) * tile];
+  }
+  if (QL == 1) {
+    e.g = (a0 + a1) * L.inv_norm;
+    return e;
   }
   s_part[q * FIN_ELEMS + el] = a0 + a1;
   __syncthreads();
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize2_kernel(const 
   if (L.dh == nullptr) return;
   const float inv = mx > 0.f ? 1.f / mx : 0.f;
   const int tile = 128 * L.bn;
+  const int FIN_ELEMS = GRAM_FIN_THREADS / L.fin_q;
   if (threadIdx.x >= FIN_ELEMS) return;
   const int id = (blockIdx.x - L.fin_blk0) * FIN_ELEMS + threadIdx.x;
   if (id >= L.pairs * tile) return;
@@ -329,7 +334,9 @@ size_t gram_plan(GramParams& p, int target_ctas) {
     L.item0 = item;
     item += L.pairs * L.splits;
     L.fin_blk0 = fin;
-    L.fin_blocks = (L.pairs * 128 * L.bn + FIN_ELEMS - 1) / FIN_ELEMS;
+    L.fin_q = L.splits >= 16 ? 4 : 1;
+    const int fin_elems = GRAM_FIN_THREADS / L.fin_q;
+    L.fin_blocks = (L.pairs * 128 * L.bn + fin_elems - 1) / fin_elems;
     fin += L.fin_blocks;
     L.ws_off = ws;
     ws += static_cast<size_t>(L.pairs) * L.splits * 128 * L.bn;

@@ -23,6 +23,7 @@ struct GramLayer {
   int item0;      // first work item of this layer
   int fin_blk0;   // first finalize block of this layer
   int fin_blocks; // finalize blocks of this layer
+  int fin_q;      // threads that share the split-K sum of one element in finalize1: 4 when there are many splits, else 1
   size_t ws_off;  // float offset of this layer's partial tiles in the workspace
   // finalize inputs / outputs
   const float* target;  // [C,C] target Gram or nullptr (then `gram_out` receives G itself)

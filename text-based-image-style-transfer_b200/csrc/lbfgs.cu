@@ -14,13 +14,10 @@
 namespace nst {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 ld4_stream(const float* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p));
-  return r;
-}
+// streaming 128-bit load (evict-first).  Deliberately NOT `asm volatile`: the compiler must be free to hoist the loads
+// of the next stored pair above the shuffle reduction of the current one (the volatile version serialised
+// load -> reduce -> load and ran pass 1 at a quarter of the HBM bandwidth).
+__device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc);
@@ -140,19 +137,31 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   warp_reduce8(sc, lane);
   if ((lane & 3) == 0) wscal[warp][lane >> 2] = (lane >> 2) == 6 ? gmax : sc[0];
 
-#pragma unroll 2
-  for (int i = 0; i < len; ++i) {
+  // software pipeline over the stored pairs: the loads of pair i+1 are in flight while pair i is reduced
+  float4 na[LB_VEC_PER_THREAD], nc[LB_VEC_PER_THREAD];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_pair = [&](int i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
     const float* Sp = hblk + (2 * p) * row;
     const float* Yp = Sp + row;
-    float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      a4[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z;
-      c4[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z;
+      na[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z4;
+      nc[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z4;
     }
+  };
+  if (len > 0) load_pair(0);
+  for (int i = 0; i < len; ++i) {
+    int p = head + i;
+    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
+      a4[k] = na[k];
+      c4[k] = nc[k];
+    }
+    if (i + 1 < len) load_pair(i + 1);
     // S_p.y  S_p.g  Y_p.y  Y_p.g : all the recursion needs (lbfgs_ctl.h)
     float r[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
       acc[i] = make_float4(cg * g.x, cg * g.y, cg * g.z, cg * g.w);
     }
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int i = 0; i < len; ++i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
@@ -336,8 +345,7 @@ void lbfgs_plan(LbfgsBuffers& b, int num_sms) {
   const int nv = b.n_pad >> 2;
   int r = (nv + LB_MAX_VEC_PER_BLOCK * num_sms - 1) / (LB_MAX_VEC_PER_BLOCK * num_sms);
   if (r < 1) r = 1;
-  // two resident blocks per SM keep more loads in flight at small sizes
-  int nblocks = num_sms * r * 2;
+  int nblocks = num_sms * r;
   if (nblocks > nv) nblocks = nv > 0 ? nv : 1;
   b.nblocks = nblocks;
   b.vec_per_blk = (nv + nblocks - 1) / nblocks;
