@@ -33,19 +33,21 @@ static constexpr int UMMA_K = 16;
 static constexpr int HALO_ROWS = (TILE_H + 2) * (TILE_W + 2);     // 180 pixels
 static constexpr int HALO_TX_BYTES = HALO_ROWS * BLOCK_K * 2;     // 23040
 static constexpr int HALO_STAGE_BYTES = 23 * 1024;                // keeps the next stage 1024-byte aligned
-static constexpr int HALO_STAGES = 2;
 static constexpr int FLAT_TX_BYTES = BLOCK_M * BLOCK_K * 2;       // 1x1 convolution: no halo
 static constexpr int NUM_THREADS = 256;
 static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 
 template <int BLOCK_N>
 struct ConvCfg {
+  // a patch feeds 36 MMAs; with narrow N those take less time than a TMA round trip, so more patches must be in flight
+  static constexpr int HALO_STAGES = BLOCK_N >= 256 ? 2 : 4;
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int B_STAGES_FIT = (SMEM_BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
   static constexpr int B_STAGES = B_STAGES_FIT > 8 ? 8 : B_STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
   static constexpr int OPERAND_BYTES = HALO_STAGES * HALO_STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
-  static constexpr int SMEM_BYTES = OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one bias slice per accumulator stage
+  static constexpr int SMEM_BYTES = OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -86,12 +88,12 @@ __device__ __forceinline__ void store_bf32(__nv_bfloat16* dst, const float (&v)[
 
 // forward epilogue for 32 channels of one pixel
 __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
-                                             int lane) {
-  // bias (same address across the warp -> broadcast load)
-  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+                                             int lane, const float* sbias /* 32 values of this chunk, shared memory */) {
+  // bias (same address across the warp -> broadcast read); staged in shared memory while the main loop ran
+  const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    float4 b = __ldg(b4 + q);
+    float4 b = b4[q];
     v[4 * q + 0] += b.x;
     v[4 * q + 1] += b.y;
     v[4 * q + 2] += b.z;
@@ -142,17 +144,42 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
   }
 }
 
+// Operands of the data-gradient epilogue for 32 channels of one pixel (mask + tap seed, or pool routing bytes).
+// They do not depend on the accumulator, so they are fetched one chunk ahead - the first one before the
+// accumulator is even complete - instead of serialising eight global-memory latencies per tile.
+struct DgradAux {
+  uint4 m[4];  // post-ReLU activation (fp16) whose sign masks the gradient   | m[0..1]: routing bytes
+  uint4 a[4];  // tap seed (bf16) added to the gradient
+};
+__device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x, int h, int w, int n, bool valid) {
+  if (!valid) return;
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  if (p.route == nullptr) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x.m[q] = __ldg(m4 + q);
+    if (p.addend != nullptr) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x.a[q] = __ldg(a4 + q);
+    }
+  } else {
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.route + pix * p.N + n);
+    x.m[0] = __ldg(r4);
+    x.m[1] = __ldg(r4 + 1);
+  }
+}
+
 // data-gradient epilogue for 32 channels of one pixel
-__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid) {
+__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
+                                               const DgradAux& x) {
   if (!valid) return;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
     // ReLU mask from the stored post-ReLU activation (PyTorch: grad * (result > 0))
-    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      uint4 m = __ldg(m4 + q);
-      const __half2* hh = reinterpret_cast<const __half2*>(&m);
+      const __half2* hh = reinterpret_cast<const __half2*>(&x.m[q]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float2 f = __half22float2(hh[e]);
@@ -161,11 +188,9 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[3
       }
     }
     if (p.addend != nullptr) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 a = __ldg(a4 + q);
-        const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&x.a[q]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 f = __bfloat1622float2(bb[e]);
@@ -179,10 +204,8 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[3
     // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
     // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
     uint32_t r[8];
-    const uint4* r4 = reinterpret_cast<const uint4*>(p.route + pix * p.N + n);
-    uint4 ra = __ldg(r4), rb = __ldg(r4 + 1);
-    r[0] = ra.x; r[1] = ra.y; r[2] = ra.z; r[3] = ra.w;
-    r[4] = rb.x; r[5] = rb.y; r[6] = rb.z; r[7] = rb.w;
+    r[0] = x.m[0].x; r[1] = x.m[0].y; r[2] = x.m[0].z; r[3] = x.m[0].w;
+    r[4] = x.m[1].x; r[5] = x.m[1].y; r[6] = x.m[1].z; r[7] = x.m[1].w;
 #pragma unroll
     for (int pos = 0; pos < 4; ++pos) {
       float o[32];
@@ -217,15 +240,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + HALO_STAGES * HALO_STAGE_BYTES;
+  uint8_t* sB = smem + Cfg::HALO_STAGES * HALO_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OPERAND_BYTES);
   uint64_t* afull_bar = bars;
-  uint64_t* aempty_bar = afull_bar + HALO_STAGES;
-  uint64_t* bfull_bar = aempty_bar + HALO_STAGES;
+  uint64_t* aempty_bar = afull_bar + Cfg::HALO_STAGES;
+  uint64_t* bfull_bar = aempty_bar + Cfg::HALO_STAGES;
   uint64_t* bempty_bar = bfull_bar + Cfg::B_STAGES;
   uint64_t* tfull_bar = bempty_bar + Cfg::B_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::OPERAND_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,7 +265,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < HALO_STAGES; ++s) {
+    for (int s = 0; s < Cfg::HALO_STAGES; ++s) {
       mbar_init(&afull_bar[s], 1);
       mbar_init(&aempty_bar[s], 1);
     }
@@ -286,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           mbar_wait(&aempty_bar[as], aphase ^ 1u);
           mbar_arrive_expect_tx(&afull_bar[as], a_tx);
           tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA, &afull_bar[as], ks * BLOCK_K, w0 - pad, h0 - pad);
-          if (++as == HALO_STAGES) {
+          if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
           }
@@ -339,7 +363,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             bphase ^= 1u;
           }
         }
-        if (++as == HALO_STAGES) {
+        if (++as == Cfg::HALO_STAGES) {
           as = 0;
           aphase ^= 1u;
         }
@@ -366,6 +390,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const int tw = sp - th * p.tiles_w;
       const int h = th * TILE_H + hl, w = tw * TILE_W + wl, n0 = nt * BLOCK_N;
       const bool valid = h < p.H && w < p.W;
+      // everything that does not depend on the accumulator is fetched while the main loop still runs
+      DgradAux aux_cur, aux_nxt;
+      if constexpr (MODE == CONV_FWD) {
+        for (int j = t; j < BLOCK_N; j += 128) sbias[ts * BLOCK_N + j] = __ldg(p.bias + n0 + j);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      }
+      if constexpr (MODE == CONV_DGRAD) dgrad_aux_load(p, aux_cur, h, w, n0, valid);
       mbar_wait(&tfull_bar[ts], tphase);
       tc_fence_after();
       NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
@@ -388,6 +419,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
+        if constexpr (MODE == CONV_DGRAD) {
+          if (c + 1 < BLOCK_N / 32) dgrad_aux_load(p, aux_nxt, h, w, n0 + (c + 1) * 32, valid);
+        }
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -395,9 +429,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const int n = n0 + c * 32;
-        if (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane);
-        if (MODE == CONV_DGRAD) epilogue_dgrad(p, v, h, w, n, valid);
-        if (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
+        if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + c * 32);
+        if constexpr (MODE == CONV_DGRAD) {
+          epilogue_dgrad(p, v, h, w, n, valid, aux_cur);
+          aux_cur = aux_nxt;
+        }
+        if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
       }
       tc_fence_before();
       __syncwarp();

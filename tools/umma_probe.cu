@@ -89,7 +89,80 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ X
   if (tid < 32) tmem_dealloc(tmem, 64);
 }
 
+// ---- issue-rate microbenchmark: back-to-back tcgen05.mma (M = 128, K = 16) from shared-memory operands, no TMA traffic
+__global__ void __launch_bounds__(128) rate_kernel(int N, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* sA = smem;               // 128 x 128 B
+  uint8_t* sB = smem + 16384;       // up to 256 x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (16384 + 32768) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (tid < 32) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, N, 0, 0, 0);
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+        const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+        umma_f16(tmem, da, db, idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 256);
+}
+
+static void rate_bench() {
+  long long* d;
+  long long h[2];
+  cudaMalloc(&d, 2 * sizeof(long long));
+  const int smem = 16384 + 32768 + 1024 + 64;
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int iters = 2000;
+  const int Ns[] = {16, 64, 128, 256};
+  for (int N : Ns) {
+    for (int ctas : {1, 148}) {
+      rate_kernel<<<ctas, 128, smem>>>(N, iters, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        printf("rate N=%d: %s\n", N, cudaGetErrorString(e));
+        return;
+      }
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("MMA rate M=128 N=%3d K=16, %3d CTAs: issue %.1f cycles/MMA, complete %.1f cycles/MMA (tensor floor %d)\n", N, ctas,
+             (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), 128 * N / 256);
+    }
+  }
+  cudaFree(d);
+}
+
 int main() {
+  rate_bench();
   __half* hX = (__half*)malloc(ROWS * 64 * sizeof(__half));
   __half* dX;
   float* dD;
