@@ -337,6 +337,62 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_video(args, rank, world, local_rank):
+    """BASELINE configs[4]: synthetic 720p frames, one shared style, frame-sharded over the ranks (video.py).  Reports
+    frames/s; every frame is a full run_multi_style_transfer on host uint8 buffers (H2D, targets, loop, D2H) and the
+    finished frames are all-gathered in order.  Not the default workload (a frame at the reference's num_steps=400
+    costs seconds); run with --workload video."""
+    import torch
+    import nst_b200
+    from nst_b200 import synth, video
+    from importlib import import_module
+    hf = import_module("text-based-image-style-transfer_b200.multi_style_transfer.helper_functions")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    H, W = 720, 1280
+    ws, bs = synth.vgg19_random_weights(1234, 13)
+    hf.set_vgg_weight_provider(lambda: (ws, bs))
+    style = torch.from_numpy(synth.synth_image(512, 512, 1)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
+    n_frames = args.frames
+    # a slowly drifting field: frame k = blend of two fixed 1/f^2 fields (independence of the frames is what matters)
+    f0 = torch.from_numpy(synth.synth_image(H, W, 100)).float()
+    f1 = torch.from_numpy(synth.synth_image(H, W, 101)).float()
+    frames = torch.stack([((1 - k / max(n_frames - 1, 1)) * f0 + (k / max(n_frames - 1, 1)) * f1).round().to(torch.uint8)
+                          for k in range(n_frames)])
+    styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=args.video_steps, device=dev,
+                               **synth.APP_WEIGHTS)
+    styler(0, frames[0])                                   # warm-up: graph capture, allocator
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = video.run_sharded(frames, styler, dev)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    evals = 20 * (args.video_steps // 20 + 1)
+    if rank == 0:
+        line = dict(metric="video style transfer frames/s (720p, frame-sharded)", value=n_frames / dt, unit="frames/s", n_gpus=world,
+                    steps=n_frames, warmup=1, ms_per_step=1e3 * dt / n_frames, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="f16", data="synthetic",
+                    config=dict(workload="%d synthetic 1280x720 frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), "
+                                         "contiguous frame blocks per rank, NCCL broadcast of the style Gram targets + all-gather of the "
+                                         "finished frames (BASELINE configs[4], reduced frame count / steps)" % (n_frames, args.video_steps, evals)),
+                    evals_per_s=n_frames * evals / dt, checksum=int(out.to(torch.int64).sum()))
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,12 +403,18 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-launch timing table (CSV) here")
+    ap.add_argument("--workload", default="pair512", choices=["pair512", "video"])
+    ap.add_argument("--frames", type=int, default=16, help="--workload video: number of 720p frames (all ranks together)")
+    ap.add_argument("--video-steps", type=int, default=100, help="--workload video: num_steps per frame (the reference UI uses 400)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "video":
+        run_video(args, rank, world, local_rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         sys.stderr.write("bench.py: --gpus %d needs torchrun (one rank per GPU); running rank 0 alone as N=1\n" % args.gpus)

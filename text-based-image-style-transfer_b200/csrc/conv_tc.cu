@@ -40,10 +40,15 @@ static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 template <int BLOCK_N>
 struct ConvCfg {
   // a patch feeds 36 MMAs; with narrow N those take less time than a TMA round trip, so more patches must be in flight
-  static constexpr int HALO_STAGES = BLOCK_N >= 256 ? 2 : 4;
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int HALO_STAGES = 2;
+  // Filter taps per weight stage.  One pipeline iteration (barrier wait, fence, commit) costs a few hundred cycles of
+  // the issuing thread and every tcgen05.mma about 45 (profiles/r01_mma_issue_rate.log); with one tap (4 MMAs) per
+  // iteration the main loop was issue-bound at ~480 cycles per tap for every N <= 128.  Three taps per stage amortise it.
+  static constexpr int TPS = BLOCK_N >= 256 ? 1 : (BLOCK_N >= 64 ? 3 : 9);
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // one tap
+  static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
   static constexpr int B_STAGES_FIT = (SMEM_BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
-  static constexpr int B_STAGES = B_STAGES_FIT > 8 ? 8 : B_STAGES_FIT;
+  static constexpr int B_STAGES = B_STAGES_FIT > 6 ? 6 : B_STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
   static constexpr int OPERAND_BYTES = HALO_STAGES * HALO_STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one bias slice per accumulator stage
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const int halo_w = TILE_W + 2 * pad;                     // pixels per patch row
   const uint32_t a_tx = p.taps == 9 ? HALO_TX_BYTES : FLAT_TX_BYTES;
   const int sp_tiles = p.tiles_w * p.tiles_h;
+  const int tps = p.taps == 9 ? Cfg::TPS : 1;              // taps per weight stage (the weight tensor map's box depth)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -314,9 +320,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             as = 0;
             aphase ^= 1u;
           }
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tap = 0; tap < p.taps; tap += tps) {
             mbar_wait(&bempty_bar[bs], bphase ^ 1u);
-            mbar_arrive_expect_tx(&bfull_bar[bs], Cfg::B_STAGE_BYTES);
+            mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
             tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], ks * BLOCK_K, n0, tap);
             if (++bs == Cfg::B_STAGES) {
               bs = 0;
@@ -326,49 +332,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
     int as = 0, bs = 0, ts = 0;
     uint32_t aphase = 0, bphase = 0, tphase = 0;
     const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;  // bytes between 8-pixel groups of the A operand
+    const uint32_t idesc = p.idesc;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[ts], tphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
+      uint32_t accumulate = 0;
       for (int ks = 0; ks < k_slices; ++ks) {
         mbar_wait(&afull_bar[as], aphase);
-        NST_STAMP(2, lane == 0 && ks == 0 && tile == blockIdx.x);
+        NST_STAMP(2, ks == 0 && tile == blockIdx.x);
         const uint32_t a_base = smem_u32(sA + as * HALO_STAGE_BYTES);
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int tap0 = 0; tap0 < p.taps; tap0 += tps) {
           mbar_wait(&bfull_bar[bs], bphase);
           tc_fence_after();
-          if (elect_one()) {
+          const uint32_t b_base = smem_u32(sB + bs * Cfg::B_STAGE_BYTES);
+          for (int tt = 0; tt < tps; ++tt) {
+            const int tap = tap0 + tt;
             const int dr = p.taps == 9 ? tap / 3 : 0;
             const int ds = p.taps == 9 ? tap - 3 * dr : 0;
             const uint32_t a_addr = a_base + static_cast<uint32_t>(dr * halo_w + ds) * 128u;
-            const uint32_t b_addr = smem_u32(sB + bs * Cfg::B_STAGE_BYTES);
+            const uint32_t b_addr = b_base + static_cast<uint32_t>(tt) * Cfg::B_TILE_BYTES;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, sbo);
               const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-              umma_f16(d_tmem, da, db, p.idesc, (ks | tap | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, da, db, idesc, accumulate);
+              accumulate = 1u;
             }
-            umma_commit(&bempty_bar[bs]);                                   // frees the weight slot when the MMAs retire
-            if (tap == p.taps - 1) umma_commit(&aempty_bar[as]);            // ... and the patch after its last tap
-            if (tap == p.taps - 1 && ks == k_slices - 1) umma_commit(&tfull_bar[ts]);  // accumulator complete
           }
-          __syncwarp();
+          umma_commit(&bempty_bar[bs]);  // frees the weight stage when its MMAs retire
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;
           }
         }
+        umma_commit(&aempty_bar[as]);  // ... and the patch after its last tap
         if (++as == Cfg::HALO_STAGES) {
           as = 0;
           aphase ^= 1u;
         }
       }
-      NST_STAMP(3, lane == 0 && tile == blockIdx.x);
+      umma_commit(&tfull_bar[ts]);  // accumulator complete
+      NST_STAMP(3, tile == blockIdx.x);
       if (++ts == 2) {
         ts = 0;
         tphase ^= 1u;
@@ -486,12 +496,18 @@ int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int b
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
+int conv_taps_per_stage(int block_n, int taps) {
+  if (taps != 9) return 1;
+  return block_n >= 256 ? ConvCfg<256>::TPS : (block_n >= 128 ? ConvCfg<128>::TPS : (block_n >= 64 ? ConvCfg<64>::TPS : ConvCfg<16>::TPS));
+}
+
 int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n) {
   auto fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(taps)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(N) * K * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_n), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_n),
+                       static_cast<cuuint32_t>(conv_taps_per_stage(box_n, taps))};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -499,17 +515,17 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, in
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-// Picks the N tile that minimises (waves over the SMs) x (time per tile).  The per-tile time model is the shared-memory
-// traffic of one K=16 MMA step at 128 B/clk: operand reads (4 KB of A + N x 32 B of B) plus the TMA writes that refill
-// them (N x 32 B of weights + 1/36 of a halo patch): 161 / 99 / 68 cycles for N = 256 / 128 / 64 against 128 / 64 / 32
-// cycles of tensor-core time - wide tiles are cheaper per FLOP, narrow tiles fill the 148 SMs when the image is small.
+// Picks the N tile that minimises (waves over the SMs) x (time per tile).  Time per K=16 step, measured
+// (profiles/r01_mma_issue_rate.log, r01_conv_phases_*.log): the tensor core needs 128 / 64 / 32 cycles for
+// N = 256 / 128 / 64 but a tcgen05.mma cannot be issued faster than every ~45-48 cycles, plus pipeline overhead per
+// stage: about 136 / 84 / 68 cycles.  Wide tiles are cheaper per FLOP, narrow tiles fill the 148 SMs on small images.
 int conv_block_n(int N, int H, int W, int num_sms) {
   const int sp = ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
   if (num_sms < 1) num_sms = 148;
   int best = 64;
   long best_cost = -1;
   const int cand[3] = {256, 128, 64};
-  const int cyc[3] = {161, 99, 68};
+  const int cyc[3] = {136, 84, 68};
   for (int i = 0; i < 3; ++i) {
     if (cand[i] > N || N % cand[i] != 0) continue;
     const long tiles = static_cast<long>(sp) * (N / cand[i]);

@@ -57,6 +57,8 @@ struct ConvParams {
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
 int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n);
+// filter taps the kernel loads per weight stage for this N tile (the depth of the weight tensor map's box)
+int conv_taps_per_stage(int block_n, int taps);
 
 // picks the N tile for a layer of N output channels on an H x W pixel grid
 int conv_block_n(int N, int H, int W, int num_sms);
