@@ -334,10 +334,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer (one thread) =====================
+    // The issue rate of tcgen05.mma is set by the scalar instructions this thread executes between two of them
+    // (measured: 45 cycles per MMA with constant descriptors, 76 with a few extra index operations,
+    // profiles/r01_mma_issue_rate.log), so the 64-bit descriptors are not rebuilt per MMA: their upper halves are
+    // loop constants and the lower halves (address >> 4) advance by compile-time immediates.
     int as = 0, bs = 0, ts = 0;
     uint32_t aphase = 0, bphase = 0, tphase = 0;
     const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;  // bytes between 8-pixel groups of the A operand
     const uint32_t idesc = p.idesc;
+    const uint32_t a_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, sbo) >> 32);
+    const uint32_t b_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, 1024) >> 32);
+    const uint32_t lbo_lo = static_cast<uint32_t>(umma_desc_sw128(0, 16, 0) & 0xffffffffu);  // LBO field, address 0
+    const bool conv3x3 = p.taps == 9;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[ts], tphase ^ 1u);
       tc_fence_after();
@@ -346,26 +354,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       for (int ks = 0; ks < k_slices; ++ks) {
         mbar_wait(&afull_bar[as], aphase);
         NST_STAMP(2, ks == 0 && tile == blockIdx.x);
-        const uint32_t a_base = smem_u32(sA + as * HALO_STAGE_BYTES);
-        for (int tap0 = 0; tap0 < p.taps; tap0 += tps) {
-          mbar_wait(&bfull_bar[bs], bphase);
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(sB + bs * Cfg::B_STAGE_BYTES);
-          for (int tt = 0; tt < tps; ++tt) {
-            const int tap = tap0 + tt;
-            const int dr = p.taps == 9 ? tap / 3 : 0;
-            const int ds = p.taps == 9 ? tap - 3 * dr : 0;
-            const uint32_t a_addr = a_base + static_cast<uint32_t>(dr * halo_w + ds) * 128u;
-            const uint32_t b_addr = b_base + static_cast<uint32_t>(tt) * Cfg::B_TILE_BYTES;
+        const uint32_t a_lo0 = lbo_lo | (smem_u32(sA + as * HALO_STAGE_BYTES) >> 4);
+        if (conv3x3) {
+          // nine taps = nine row shifts of the patch: (dr * 10 + ds) rows of 128 B = (dr * 10 + ds) * 8 descriptor units
+#pragma unroll 1
+          for (int g = 0; g < 9 / Cfg::TPS; ++g) {
+            mbar_wait(&bfull_bar[bs], bphase);
+            tc_fence_after();
+            const uint32_t b_lo0 = lbo_lo | (smem_u32(sB + bs * Cfg::B_STAGE_BYTES) >> 4);
+            // TPS = 1: tap g;  TPS = 3: taps 3g .. 3g+2 (one filter row);  TPS = 9: all taps
+            const uint32_t a_lo_g = Cfg::TPS == 1 ? a_lo0 + static_cast<uint32_t>((g / 3) * (TILE_W + 2) + g % 3) * 8u
+                                                  : a_lo0 + static_cast<uint32_t>(g) * ((TILE_W + 2) * 8u);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, sbo);
-              const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-              umma_f16(d_tmem, da, db, idesc, accumulate);
-              accumulate = 1u;
+            for (int tt = 0; tt < Cfg::TPS; ++tt) {
+              const uint32_t a_tap = Cfg::TPS == 9 ? static_cast<uint32_t>(((tt / 3) * (TILE_W + 2) + tt % 3) * 8)
+                                                   : static_cast<uint32_t>(tt * 8);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_lo_g + a_tap + static_cast<uint32_t>(k * 2));
+                const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) |
+                                    (b_lo0 + static_cast<uint32_t>(tt * (Cfg::B_TILE_BYTES / 16) + k * 2));
+                umma_f16(d_tmem, da, db, idesc, accumulate);
+                accumulate = 1u;
+              }
+            }
+            umma_commit(&bempty_bar[bs]);  // frees the weight stage when its MMAs retire
+            if (++bs == Cfg::B_STAGES) {
+              bs = 0;
+              bphase ^= 1u;
             }
           }
-          umma_commit(&bempty_bar[bs]);  // frees the weight stage when its MMAs retire
+        } else {
+          // 1x1 convolution: one weight tile per 64-channel slice, no shift
+          mbar_wait(&bfull_bar[bs], bphase);
+          tc_fence_after();
+          const uint32_t b_lo0 = lbo_lo | (smem_u32(sB + bs * Cfg::B_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + static_cast<uint32_t>(k * 2));
+            const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + static_cast<uint32_t>(k * 2));
+            umma_f16(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1u;
+          }
+          umma_commit(&bempty_bar[bs]);
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;

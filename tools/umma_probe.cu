@@ -90,16 +90,16 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ X
 }
 
 // ---- issue-rate microbenchmark: back-to-back tcgen05.mma (M = 128, K = 16) from shared-memory operands, no TMA traffic
-__global__ void __launch_bounds__(128) rate_kernel(int N, int iters, long long* out) {
+__global__ void __launch_bounds__(128) rate_kernel(int N, int iters, long long* out, int shift_rows, int sbo, int vary) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint8_t* sA = smem;               // 128 x 128 B
-  uint8_t* sB = smem + 16384;       // up to 256 x 128 B
+  uint8_t* sA = smem;               // 192 x 128 B (room for a shifted / strided operand)
+  uint8_t* sB = smem + 24576;       // up to 256 x 128 B
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32768);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x;
-  for (int i = tid; i < (16384 + 32768) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (24576 + 32768) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -115,12 +115,15 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int iters, long long* 
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) {
     const uint32_t idesc = umma_idesc_f16(128, N, 0, 0, 0);
-    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    const uint32_t a_addr0 = smem_u32(sA) + shift_rows * 128, b_addr = smem_u32(sB);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      // vary: walk the start row like the nine filter taps do (0,1,2,10,11,12,20,21,22)
+      const int tap = vary ? it % 9 : 0;
+      const uint32_t a_addr = a_addr0 + ((tap / 3) * 10 + tap % 3) * 128;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+        const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, sbo);
         const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
         umma_f16(tmem, da, db, idesc, 1u);
       }
@@ -141,21 +144,22 @@ static void rate_bench() {
   long long* d;
   long long h[2];
   cudaMalloc(&d, 2 * sizeof(long long));
-  const int smem = 16384 + 32768 + 1024 + 64;
+  const int smem = 24576 + 32768 + 1024 + 64;
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 2000;
   const int Ns[] = {16, 64, 128, 256};
   for (int N : Ns) {
-    for (int ctas : {1, 148}) {
-      rate_kernel<<<ctas, 128, smem>>>(N, iters, d);
+    const int variants[5][3] = {{0, 1024, 0}, {0, 1280, 0}, {1, 1024, 0}, {11, 1280, 0}, {0, 1280, 1}};
+    for (int v = 0; v < 5; ++v) {
+      rate_kernel<<<148, 128, smem>>>(N, iters, d, variants[v][0], variants[v][1], variants[v][2]);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("rate N=%d: %s\n", N, cudaGetErrorString(e));
         return;
       }
       cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-      printf("MMA rate M=128 N=%3d K=16, %3d CTAs: issue %.1f cycles/MMA, complete %.1f cycles/MMA (tensor floor %d)\n", N, ctas,
-             (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), 128 * N / 256);
+      printf("MMA rate M=128 N=%3d K=16 A: start row %2d, group stride %4d B, tap walk %d: issue %.1f, complete %.1f cycles/MMA (tensor floor %d)\n",
+             N, variants[v][0], variants[v][1], variants[v][2], (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), 128 * N / 256);
     }
   }
   cudaFree(d);
