@@ -260,7 +260,7 @@ static int build_conv_params(nst_plan* p) {
     f.N = kCout[i];
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
-    f.block_n = conv_block_n(kCout[i], H, W, g_num_sms);
+    f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
@@ -279,7 +279,7 @@ static int build_conv_params(nst_plan* p) {
     d.N = kCin[i];
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
-    d.block_n = conv_block_n(kCin[i], H, W, g_num_sms);
+    d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
@@ -324,7 +324,7 @@ static int build_conv_params(nst_plan* p) {
     c.N = C;
     c.taps = 1;
     if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
-    c.block_n = conv_block_n(C, c.H, c.W, g_num_sms);
+    c.block_n = conv_block_n(C, c.H, c.W, C, g_num_sms);
     if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
     c.alpha = p->alpha + l;
     c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
@@ -504,8 +504,8 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.td_part, b.nblocks, true));
     PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * NST_LBFGS_NDOT, true));
     PA(plan_alloc_t(p, &b.scal, NST_LBFGS_NSCAL, true));
-    PA(plan_alloc_t(p, &b.R, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS, true));
-    PA(plan_alloc_t(p, &b.YY, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS, true));
+    PA(plan_alloc_t(p, &b.R, NST_CTL_MAT_DOUBLES, true));
+    PA(plan_alloc_t(p, &b.YY, NST_CTL_MAT_DOUBLES, true));
     PA(plan_alloc_t(p, &b.ctl, 1, true));
     b.eval_loss = p->losses;
   }
@@ -1140,8 +1140,8 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
   h.trace_cap = p->trace_cap;
   CK(cudaMemcpyAsync(b.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));  // `h` lives on this stack frame
-  CK(cudaMemsetAsync(b.R, 0, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS * sizeof(double), s));
-  CK(cudaMemsetAsync(b.YY, 0, static_cast<size_t>(NST_LBFGS_SLOTS) * NST_LBFGS_SLOTS * sizeof(double), s));
+  CK(cudaMemsetAsync(b.R, 0, NST_CTL_MAT_DOUBLES * sizeof(double), s));
+  CK(cudaMemsetAsync(b.YY, 0, NST_CTL_MAT_DOUBLES * sizeof(double), s));
   CK(cudaMemsetAsync(b.x, 0, b.n_pad * sizeof(float), s));
   CK(cudaMemsetAsync(b.g, 0, b.n_pad * sizeof(float), s));
   CK(cudaMemsetAsync(b.g_prev, 0, b.n_pad * sizeof(float), s));

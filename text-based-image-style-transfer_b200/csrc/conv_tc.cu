@@ -34,11 +34,15 @@ static constexpr int HALO_ROWS = (TILE_H + 2) * (TILE_W + 2);     // 180 pixels
 static constexpr int HALO_TX_BYTES = HALO_ROWS * BLOCK_K * 2;     // 23040
 static constexpr int HALO_STAGE_BYTES = 23 * 1024;                // keeps the next stage 1024-byte aligned
 static constexpr int FLAT_TX_BYTES = BLOCK_M * BLOCK_K * 2;       // 1x1 convolution: no halo
-static constexpr int NUM_THREADS = 256;
 static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 
 template <int BLOCK_N>
 struct ConvCfg {
+  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, spare; then the epilogue warps.  Eight of them (two per TMEM
+  // lane quarter, each taking half of the accumulator columns): the epilogue is a latency chain (tcgen05.ld -> math ->
+  // scattered 16-byte stores) and one warp per scheduler cannot hide it.
+  static constexpr int EPI_WARPS = BLOCK_N >= 64 ? 8 : 4;
+  static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
   // a patch feeds 36 MMAs; with narrow N those take less time than a TMA round trip, so more patches must be in flight
   static constexpr int HALO_STAGES = 2;
   // Filter taps per weight stage.  One pipeline iteration (barrier wait, fence, commit) costs a few hundred cycles of
@@ -78,10 +82,11 @@ __device__ __forceinline__ void store_h32(__half* dst, const float (&v)[32]) {
     d[q] = u;
   }
 }
-__device__ __forceinline__ void store_bf32(__nv_bfloat16* dst, const float (&v)[32]) {
+template <int CH>
+__device__ __forceinline__ void store_bf(__nv_bfloat16* dst, const float (&v)[CH]) {
   uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < CH / 8; ++q) {
     uint4 u;
     u.x = pack_bf2(v[8 * q + 0], v[8 * q + 1]);
     u.y = pack_bf2(v[8 * q + 2], v[8 * q + 3]);
@@ -149,41 +154,40 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
   }
 }
 
-// Operands of the data-gradient epilogue for 32 channels of one pixel (mask + tap seed, or pool routing bytes).
+// Operands of the data-gradient epilogue for DG_CH channels of one pixel (mask + tap seed, or pool routing bytes).
 // They do not depend on the accumulator, so they are fetched one chunk ahead - the first one before the
-// accumulator is even complete - instead of serialising eight global-memory latencies per tile.
+// accumulator is even complete - instead of serialising global-memory latencies on the critical path of a tile.
+static constexpr int DG_CH = 16;
 struct DgradAux {
-  uint4 m[4];  // post-ReLU activation (fp16) whose sign masks the gradient   | m[0..1]: routing bytes
-  uint4 a[4];  // tap seed (bf16) added to the gradient
+  uint4 m[2];  // post-ReLU activation (fp16) whose sign masks the gradient   | m[0]: routing bytes
+  uint4 a[2];  // tap seed (bf16) added to the gradient
 };
 __device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x, int h, int w, int n, bool valid) {
   if (!valid) return;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
     const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) x.m[q] = __ldg(m4 + q);
+    x.m[0] = __ldg(m4);
+    x.m[1] = __ldg(m4 + 1);
     if (p.addend != nullptr) {
       const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) x.a[q] = __ldg(a4 + q);
+      x.a[0] = __ldg(a4);
+      x.a[1] = __ldg(a4 + 1);
     }
   } else {
-    const uint4* r4 = reinterpret_cast<const uint4*>(p.route + pix * p.N + n);
-    x.m[0] = __ldg(r4);
-    x.m[1] = __ldg(r4 + 1);
+    x.m[0] = __ldg(reinterpret_cast<const uint4*>(p.route + pix * p.N + n));
   }
 }
 
-// data-gradient epilogue for 32 channels of one pixel
-__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
+// data-gradient epilogue for DG_CH channels of one pixel
+__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[DG_CH], int h, int w, int n, bool valid,
                                                const DgradAux& x) {
   if (!valid) return;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
     // ReLU mask from the stored post-ReLU activation (PyTorch: grad * (result > 0))
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       const __half2* hh = reinterpret_cast<const __half2*>(&x.m[q]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -194,7 +198,7 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[3
     }
     if (p.addend != nullptr) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&x.a[q]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -204,23 +208,22 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[3
         }
       }
     }
-    store_bf32(p.out_grad + pix * p.N + n, v);
+    store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
   } else {
     // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
     // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
-    uint32_t r[8];
+    uint32_t r[4];
     r[0] = x.m[0].x; r[1] = x.m[0].y; r[2] = x.m[0].z; r[3] = x.m[0].w;
-    r[4] = x.m[1].x; r[5] = x.m[1].y; r[6] = x.m[1].z; r[7] = x.m[1].w;
 #pragma unroll
     for (int pos = 0; pos < 4; ++pos) {
-      float o[32];
+      float o[DG_CH];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < DG_CH; ++j) {
         const uint32_t rj = (r[j >> 2] >> (8 * (j & 3))) & 0xffu;
         o[j] = rj == static_cast<uint32_t>(pos) ? v[j] : 0.f;
       }
       const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
-      store_bf32(p.out_grad + upix * p.N + n, o);
+      store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
     }
   }
 }
@@ -231,14 +234,14 @@ __device__ __forceinline__ void epilogue_scale(const ConvParams& p, float (&v)[3
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= alpha;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
-  store_bf32(p.out_grad + pix * p.N + n, v);
+  store_bf<32>(p.out_grad + pix * p.N + n, v);
 }
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stages
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[s], Cfg::EPI_WARPS);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -417,9 +420,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;       // which half of the accumulator columns (0 when there are four epilogue warps)
+    constexpr int COLS = BLOCK_N / (Cfg::EPI_WARPS / 4);  // columns per warp
+    const int col0 = half * COLS;
     const int t = q * 32 + lane;
     const int hl = t / TILE_W, wl = t % TILE_W;
+    const int et = threadIdx.x - 128;       // index among the epilogue threads
     int ts = 0;
     uint32_t tphase = 0;
     float alpha = 0.f;
@@ -434,14 +441,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       // everything that does not depend on the accumulator is fetched while the main loop still runs
       DgradAux aux_cur, aux_nxt;
       if constexpr (MODE == CONV_FWD) {
-        for (int j = t; j < BLOCK_N; j += 128) sbias[ts * BLOCK_N + j] = __ldg(p.bias + n0 + j);
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        for (int j = et; j < BLOCK_N; j += Cfg::EPI_WARPS * 32) sbias[ts * BLOCK_N + j] = __ldg(p.bias + n0 + j);
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
       }
-      if constexpr (MODE == CONV_DGRAD) dgrad_aux_load(p, aux_cur, h, w, n0, valid);
+      if constexpr (MODE == CONV_DGRAD) dgrad_aux_load(p, aux_cur, h, w, n0 + col0, valid);
       mbar_wait(&tfull_bar[ts], tphase);
       tc_fence_after();
       NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * BLOCK_N);
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * BLOCK_N + col0);
       if constexpr (MODE == CONV_DGRAD_PIX) {
         // conv1_1: 3 of the 16 accumulator columns are image channels
         uint32_t r[16];
@@ -457,25 +465,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             p.out_pix[c * HW + o] = g;
           }
         }
-      }
+      } else if constexpr (MODE == CONV_DGRAD) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        if constexpr (MODE == CONV_DGRAD) {
-          if (c + 1 < BLOCK_N / 32) dgrad_aux_load(p, aux_nxt, h, w, n0 + (c + 1) * 32, valid);
-        }
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
+        for (int c = 0; c < COLS / DG_CH; ++c) {
+          if (c + 1 < COLS / DG_CH) dgrad_aux_load(p, aux_nxt, h, w, n0 + col0 + (c + 1) * DG_CH, valid);
+          uint32_t r[DG_CH];
+          tmem_ld16(taddr + c * DG_CH, r);
+          tmem_ld_wait();
+          float v[DG_CH];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int n = n0 + c * 32;
-        if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + c * 32);
-        if constexpr (MODE == CONV_DGRAD) {
-          epilogue_dgrad(p, v, h, w, n, valid, aux_cur);
+          for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux_cur);
           aux_cur = aux_nxt;
         }
-        if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < COLS / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int n = n0 + col0 + c * 32;
+          if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + col0 + c * 32);
+          if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -546,22 +561,24 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, in
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-// Picks the N tile that minimises (waves over the SMs) x (time per tile).  Time per K=16 step, measured
-// (profiles/r01_mma_issue_rate.log, r01_conv_phases_*.log): the tensor core needs 128 / 64 / 32 cycles for
-// N = 256 / 128 / 64 but a tcgen05.mma cannot be issued faster than every ~45-48 cycles, plus pipeline overhead per
-// stage: about 136 / 84 / 68 cycles.  Wide tiles are cheaper per FLOP, narrow tiles fill the 148 SMs on small images.
-int conv_block_n(int N, int H, int W, int num_sms) {
+// Picks the N tile that minimises the modelled kernel time: (tiles per CTA) x (main loop of one tile) + the epilogue of
+// the last tile (earlier epilogues overlap the next tile's main loop).  Measured constants (profiles/r01_mma_issue_rate.log,
+// r01_conv_phases_v3_issue_loop.log): a K=16 step costs max(tensor floor 128 N / 256, ~48 issue cycles); the epilogue of a
+// 128 x N tile about 20 cycles per output column.  Wide tiles are cheaper per FLOP; narrow tiles fill the 148 SMs on small
+// images and let the epilogue of the first half of a pixel tile hide behind the main loop of the second half.
+int conv_block_n(int N, int H, int W, int k_total, int num_sms) {
   const int sp = ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
   if (num_sms < 1) num_sms = 148;
+  const int ksteps = k_total / UMMA_K;
   int best = 64;
   long best_cost = -1;
   const int cand[3] = {256, 128, 64};
-  const int cyc[3] = {136, 84, 68};
   for (int i = 0; i < 3; ++i) {
     if (cand[i] > N || N % cand[i] != 0) continue;
     const long tiles = static_cast<long>(sp) * (N / cand[i]);
-    const long waves = (tiles + num_sms - 1) / num_sms;
-    const long cost = waves * cyc[i];
+    const long per_cta = (tiles + num_sms - 1) / num_sms;
+    const long step = cand[i] / 2 > 48 ? cand[i] / 2 : 48;
+    const long cost = per_cta * ksteps * step + 20L * cand[i];
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = cand[i];
@@ -583,7 +600,7 @@ template <int BLOCK_N, int MODE>
 static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  conv_tc_kernel<BLOCK_N, MODE><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  conv_tc_kernel<BLOCK_N, MODE><<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
 

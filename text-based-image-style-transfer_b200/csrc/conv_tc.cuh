@@ -60,8 +60,8 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, in
 // filter taps the kernel loads per weight stage for this N tile (the depth of the weight tensor map's box)
 int conv_taps_per_stage(int block_n, int taps);
 
-// picks the N tile for a layer of N output channels on an H x W pixel grid
-int conv_block_n(int N, int H, int W, int num_sms);
+// picks the N tile for a layer of N output channels on an H x W pixel grid contracting k_total = taps * K values
+int conv_block_n(int N, int H, int W, int k_total, int num_sms);
 // fills tiles_* / idesc from H, W, K, N, taps and mode
 void conv_finalize_params(ConvParams& p, int mode);
 // sets the kernel attributes (opt-in shared memory) of every instantiation; call once per process

@@ -231,22 +231,32 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
   extern __shared__ double ctl_smem[];
   NstCtlWork w;
   w.R = ctl_smem;
-  w.YY = w.R + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
-  w.Sg = w.YY + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+  w.YY = w.R + NST_CTL_MAT_DOUBLES;
+  w.Sg = w.YY + NST_CTL_MAT_DOUBLES;
   w.Yg = w.Sg + NST_LBFGS_SLOTS;
   w.al = w.Yg + NST_LBFGS_SLOTS;
   w.c = w.al + NST_LBFGS_SLOTS;
   w.yq = w.c + NST_LBFGS_SLOTS;
   w.ro = w.yq + NST_LBFGS_SLOTS;
   w.red = w.ro + NST_LBFGS_SLOTS;
-  if (b.ctl->stop == NST_RUN && b.ctl->n_iter > 0) {
-    // stage the persistent dot-product matrices in shared memory (163 KB, L2 resident)
-    constexpr int N = NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
-    for (int i = threadIdx.x; i < N; i += LB_CTL_THREADS) {
-      w.R[i] = b.R[i];
-      w.YY[i] = b.YY[i];
-    }
+  uint64_t* bar = reinterpret_cast<uint64_t*>(w.red + 2);
+  const bool stage = b.ctl->stop == NST_RUN && b.ctl->n_iter > 0;
+  if (stage && threadIdx.x == 0) {
+    // stage the persistent dot-product matrices in shared memory with two bulk copies (2 x 80 KB, L2 resident):
+    // the recurrences below touch every element once, on a dependent chain - it must not see global-memory latency
+    constexpr uint32_t BYTES = NST_CTL_MAT_DOUBLES * 8;
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar, 2 * BYTES);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(w.R)),
+                 "l"(b.R), "r"(BYTES), "r"(smem_u32(bar))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(w.YY)),
+                 "l"(b.YY), "r"(BYTES), "r"(smem_u32(bar))
+                 : "memory");
   }
+  __syncthreads();
+  if (stage) mbar_wait(bar, 0);
   __syncthreads();
   nst_lbfgs_control(b.ctl, w, b.R, b.YY, b.dots, b.scal, *b.eval_loss, b.td_part, b.nblocks, mode);
 }

@@ -83,7 +83,9 @@ struct NstCtlWork {
   double* ro;  // [SLOTS] 1 / (y_i . s_i)
   double* red; // [4] broadcast scratch
 };
-#define NST_CTL_WORK_DOUBLES (2 * NST_LBFGS_SLOTS * NST_LBFGS_SLOTS + 6 * NST_LBFGS_SLOTS + 4)
+// doubles per dot-product matrix: SLOTS^2 rounded up to a multiple of 2 (16-byte granules for bulk copies)
+#define NST_CTL_MAT_DOUBLES ((NST_LBFGS_SLOTS * NST_LBFGS_SLOTS + 1) / 2 * 2)
+#define NST_CTL_WORK_DOUBLES (2 * NST_CTL_MAT_DOUBLES + 6 * NST_LBFGS_SLOTS + 4)
 
 #if defined(__CUDA_ARCH__)
 #define NST_HD __device__

@@ -30,8 +30,8 @@ void nst_ctl_run(NstLbfgsCtl* c, double* work, const double* dots, const double*
                  const float* td_part, int n_td, int mode) {
   NstCtlWork w;
   w.R = work;
-  w.YY = w.R + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
-  w.Sg = w.YY + NST_LBFGS_SLOTS * NST_LBFGS_SLOTS;
+  w.YY = w.R + NST_CTL_MAT_DOUBLES;
+  w.Sg = w.YY + NST_CTL_MAT_DOUBLES;
   w.Yg = w.Sg + NST_LBFGS_SLOTS;
   w.al = w.Yg + NST_LBFGS_SLOTS;
   w.c = w.al + NST_LBFGS_SLOTS;
