@@ -22,6 +22,7 @@
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace nst {
 
@@ -267,6 +268,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     if (dbg && (cond)) p.dbg[slot] = clock64();                      \
   } while (0)
   NST_STAMP(0, threadIdx.x == 0);
+  // Programmatic dependent launch: let the next kernel in the stream get scheduled as soon as CTAs of this grid retire
+  // (its CTAs run their own setup, then block in griddepcontrol.wait until this grid has completed and flushed).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -295,6 +299,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only kernel parameters and on-chip state; from here on this grid reads and writes tensors
+  // produced by earlier kernels: wait for the grid(s) it depends on (no-op without the launch attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   NST_STAMP(1, threadIdx.x == 0);
 
   const int k_slices = p.K / BLOCK_K;
@@ -600,8 +607,18 @@ template <int BLOCK_N, int MODE>
 static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  conv_tc_kernel<BLOCK_N, MODE><<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
-  return cudaGetLastError();
+  static const bool pdl = getenv("NST_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE>, p);
 }
 
 template <int BLOCK_N, int MODE>
