@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -320,7 +320,7 @@ def run_b200(args, rank, world, local_rank):
                             history_pairs_at_end=hist_len, final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S)),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
                 ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if args.kernel_table:
         with open(args.kernel_table, "w") as f:
             f.write("kind,conv,ms,gflop,tflops\n")
@@ -366,6 +366,7 @@ def run_video(args, rank, world, local_rank):
     styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=args.video_steps, device=dev,
                                **synth.APP_WEIGHTS)
     styler(0, frames[0])                                   # warm-up: graph capture, allocator
+    video.gather_frames(frames[:1].clone(), world, dev)    # ... and the NCCL communicator of the all-gather
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -388,12 +389,31 @@ def run_video(args, rank, world, local_rank):
                                          "contiguous frame blocks per rank, NCCL broadcast of the style Gram targets + all-gather of the "
                                          "finished frames (BASELINE configs[4], reduced frame count / steps)" % (n_frames, args.video_steps, evals)),
                     evals_per_s=n_frames * evals / dt, checksum=int(out.to(torch.int64).sum()))
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL's version banner, torchrun's OMP notice) print to stdout; the contract is one JSON line there:
+    # everything except that line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=320, help="closure evaluations to time (num_steps=300 runs 320)")

@@ -312,3 +312,97 @@ def test_full_size_512_properties(nst, rst, oracle):
     assert float(ev.min()) > -1e-6 * float(ev.max())                       # Gram matrices are positive semi-definite
     assert torch.isfinite(g_flat).all()
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs
+def test_config1_256_against_oracle(nst, rst, oracle, vgg_weights):
+    """BASELINE configs[0]: 256x256 pair, the reference's own CPU-runnable case.  One optimizer.step() (20 evaluations)
+    of the oracle takes seconds; loss curve and iterate are compared with the north_star tolerances."""
+    O = oracle
+    ws, bs = vgg_weights
+    content, style = O.synth_image(256, 256, 0), O.synth_image(256, 256, 1)
+    ref = O.run_oracle(ws, bs, content, [style], 0, **O.APP_WEIGHTS)
+    s, c = session(rst, O, content, [style])
+    s.prepare(c, trace_capacity=64)
+    with torch.cuda.stream(s.stream):
+        losses, _ = s.plan.eval(c)
+    assert float(losses[0]) == pytest.approx(ref.losses[0][0], rel=LOSS_TOL)
+    assert s.run(0) == ref.evals == 20
+    tr = s.trace()[:, 0].double().numpy()
+    rl = np.array([l[0] for l in ref.losses])
+    assert np.all(np.abs(tr - rl) <= CURVE_TOL * np.abs(rl))
+    assert O.psnr(s.result().cpu(), ref.image) >= PSNR_MIN
+    s.close()
+
+
+def test_config3_two_styles_channel_attention_512(nst, rst, oracle, vgg_weights):
+    """BASELINE configs[2]: StyleMixer two-style blending + channel attention at 512x512.  Step-0 terms against the
+    oracle (one evaluation at 512^2 is affordable), then the run's size-independent properties."""
+    O = oracle
+    ws, bs = vgg_weights
+    content = O.synth_image(512, 512, 0)
+    styles = [O.synth_image(512, 512, 1), O.synth_image(384, 640, 2)]
+    s, c = session(rst, O, content, styles, mix_w=0.5)
+    torch.manual_seed(101)
+    s.prepare(c, channel_attention=True, trace_capacity=128)
+    torch.manual_seed(101)
+    co = O.ClosureOracle(ws, bs, c.cpu(), [O.to_tensor_u8(x) for x in styles], style_img_weight=0.5,
+                         channel_attention_on=True, **O.APP_WEIGHTS)
+    ref = co.evaluate(c.cpu(), need_grad=False)
+    with torch.cuda.stream(s.stream):
+        losses, _ = s.plan.eval(c)
+    l = losses.cpu().tolist()
+    for idx, term in ((0, "total"), (1, "content"), (2, "style"), (3, "tv"), (4, "edge")):
+        assert l[idx] == pytest.approx(ref[term], rel=LOSS_TOL, abs=1e-7), term
+    for i in range(5):
+        assert l[5 + i] == pytest.approx(ref["gram_mse"][i], rel=LOSS_TOL)
+    # mixed target of conv1_1 lives at (512 + 384 // 2) x (512 + 640 // 2) feature resolution (StyleMixer.py:31-32)
+    for name in O.STYLE_LAYERS:
+        assert rel(s.style_targets[name], co.style_t[name]) < GRAM_TOL, name
+    assert s.run(60) == 80
+    tr = s.trace()[:, 0].double().numpy()
+    assert np.isfinite(tr).all() and tr[-1] < tr[0] and (np.diff(tr) < 0).mean() > 0.9
+    s.close()
+
+
+def test_config4_1024_high_resolution(nst, rst, oracle):
+    """BASELINE configs[3]: 1024x1024 (memory / tiling stress: 2.5 GB of L-BFGS history, 1.2 GB of activations).
+    Properties only: evaluation count, decreasing loss, bounded iterate, symmetric Grams, bit-reproducible evaluation."""
+    O = oracle
+    content, style = O.synth_image(1024, 1024, 0), O.synth_image(1024, 1024, 1)
+    s, c = session(rst, O, content, [style])
+    assert s.plan.bytes() > 3e9
+    s.prepare(c, trace_capacity=128)
+    with torch.cuda.stream(s.stream):
+        l1, g1 = s.plan.eval(c)
+        l2, g2 = s.plan.eval(c)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2) and torch.isfinite(g1).all()
+    assert s.run(40) == 60
+    tr = s.trace()[:, 0].double().numpy()
+    assert tr.shape[0] == 60 and np.isfinite(tr).all() and tr[-1] < tr[0] and (np.diff(tr) < 0).mean() > 0.9
+    x = s.result()
+    assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+    with torch.cuda.stream(s.stream):
+        g = s.plan.tap_gram("conv2_1")
+    assert torch.equal(g, g.transpose(1, 2))
+    s.close()
+
+
+def test_config5_video_frames_match_single_image_runs(nst, rst, oracle):
+    """BASELINE configs[4] in miniature: a stream of frames through FrameStyler (host uint8 in, host uint8 out, style
+    targets hoisted) equals run_multi_style_transfer on each frame on its own - frames are independent."""
+    from PIL import Image
+    video = importlib.import_module("text-based-image-style-transfer_b200.video")
+    O = oracle
+    style = O.synth_image(64, 64, 1)
+    frames = torch.stack([torch.from_numpy(O.synth_image(72, 96, 100 + k)) for k in range(3)])
+    styler = video.FrameStyler(O.VGG_MEAN, O.VGG_STD, (72, 96), [O.to_tensor_u8(style).cuda()], num_steps=20, device="cuda",
+                               **O.APP_WEIGHTS)
+    out = video.run_sharded(frames, styler, "cuda")
+    styler.close()
+    assert out.shape == frames.shape and out.dtype == torch.uint8
+    for k in range(3):
+        with contextlib.redirect_stdout(io.StringIO()):
+            single = nst.run_multi_style_transfer(torch.tensor(O.VGG_MEAN), torch.tensor(O.VGG_STD), Image.fromarray(frames[k].numpy()),
+                                                  20, False, style_img1=Image.fromarray(style), device="cuda", **O.APP_WEIGHTS)
+        assert np.array_equal(np.asarray(single), out[k].cpu().numpy())

@@ -300,20 +300,33 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
       acc[i] = make_float4(cg * g.x, cg * g.y, cg * g.z, cg * g.w);
     }
   }
-#pragma unroll 4
+  // software pipeline over the stored pairs (as in pass 1): the loads of pair i+1 are in flight while pair i is consumed
+  float4 na[LB_VEC_PER_THREAD], nc[LB_VEC_PER_THREAD];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_pair = [&](int i) {
+    int p = head + i;
+    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    const float* Sp = hblk + (2 * p) * row;
+    const float* Yp = Sp + row;
+#pragma unroll
+    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
+      na[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z4;
+      nc[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z4;
+    }
+  };
+  if (len > 0) load_pair(0);
+#pragma unroll 2
   for (int i = 0; i < len; ++i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
     const float cs = coef[p], cy = coef[NST_LBFGS_SLOTS + p];
-    const float* Sp = hblk + (2 * p) * row;
-    const float* Yp = Sp + row;
     float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      a4[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z;
-      c4[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z;
+      a4[k] = na[k];
+      c4[k] = nc[k];
     }
+    if (i + 1 < len) load_pair(i + 1);
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
       acc[k].x = fmaf(cs, a4[k].x, fmaf(cy, c4[k].x, acc[k].x));
