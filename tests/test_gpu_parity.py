@@ -359,9 +359,19 @@ def test_config3_two_styles_channel_attention_512(nst, rst, oracle, vgg_weights)
     # mixed target of conv1_1 lives at (512 + 384 // 2) x (512 + 640 // 2) feature resolution (StyleMixer.py:31-32)
     for name in O.STYLE_LAYERS:
         assert rel(s.style_targets[name], co.style_t[name]) < GRAM_TOL, name
+    # On this input the reference's own trajectory is NOT monotone: unit-step L-BFGS (no line search) overshoots at the
+    # sixth evaluation (oracle, CPU fp32: 0.6717 0.6716 0.6714 0.6699 0.6298 3.90 1.40 5.01 ... 92.9 ... 2.9) and is
+    # chaotic from there on.  The evaluations before the overshoot are compared with the oracle;
+    # the overshoot itself must be reproduced, not "fixed".
+    ref_run = O.run_oracle(ws, bs, content, styles, 10 ** 9, style_img_weight=0.5, channel_attention_on=True, max_evals=7,
+                           **O.APP_WEIGHTS)
+    rl = np.array([v[0] for v in ref_run.losses])
     assert s.run(60) == 80
     tr = s.trace()[:, 0].double().numpy()
-    assert np.isfinite(tr).all() and tr[-1] < tr[0] and (np.diff(tr) < 0).mean() > 0.9
+    assert np.isfinite(tr).all()
+    assert np.all(np.abs(tr[:5] - rl[:5]) <= CURVE_TOL * np.abs(rl[:5]))
+    assert tr[5] > 3.0 * tr[4] and rl[5] > 3.0 * rl[4]
+    assert abs(tr[5] - rl[5]) <= 0.1 * rl[5]
     s.close()
 
 
