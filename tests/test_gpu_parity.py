@@ -8,6 +8,8 @@ gradients); pixel-space terms and the optimizer are fp32."""
 import importlib
 import io
 import contextlib
+import json
+import os
 
 import numpy as np
 import pytest
@@ -21,6 +23,7 @@ GRAM_TOL = 1e-3
 LOSS_TOL = 1e-3
 CURVE_TOL = 1e-2
 PSNR_MIN = 40.0
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def rel(a, b):
@@ -377,7 +380,9 @@ def test_config3_two_styles_channel_attention_512(nst, rst, oracle, vgg_weights)
 
 def test_config4_1024_high_resolution(nst, rst, oracle):
     """BASELINE configs[3]: 1024x1024 (memory / tiling stress: 2.5 GB of L-BFGS history, 1.2 GB of activations).
-    Properties only: evaluation count, decreasing loss, bounded iterate, symmetric Grams, bit-reproducible evaluation."""
+    The first evaluations are compared with the oracle's committed loss trace (tests/golden/config4_1024_losses.json,
+    made by tests/golden/make_config4_1024.py); then properties: evaluation count, bounded iterate, symmetric Grams,
+    bit-reproducible evaluation."""
     O = oracle
     content, style = O.synth_image(1024, 1024, 0), O.synth_image(1024, 1024, 1)
     s, c = session(rst, O, content, [style])
@@ -389,7 +394,14 @@ def test_config4_1024_high_resolution(nst, rst, oracle):
     assert torch.equal(l1, l2) and torch.equal(g1, g2) and torch.isfinite(g1).all()
     assert s.run(40) == 60
     tr = s.trace()[:, 0].double().numpy()
-    assert tr.shape[0] == 60 and np.isfinite(tr).all() and tr[-1] < tr[0] and (np.diff(tr) < 0).mean() > 0.9
+    assert tr.shape[0] == 60 and np.isfinite(tr).all()
+    # As at 512^2 with two styles, the reference's trajectory on this input is not monotone: unit-step L-BFGS overshoots
+    # at the seventh evaluation (oracle: ... 0.3648 0.3481 14.40 3.60 18.8) and is chaotic afterwards.
+    # Before the overshoot the curve must match to CURVE_TOL; the overshoot itself must be reproduced.
+    with open(os.path.join(GOLDEN_DIR, "config4_1024_losses.json")) as f:
+        rl = np.array(json.load(f)["total_loss"])
+    assert np.all(np.abs(tr[:6] - rl[:6]) <= CURVE_TOL * np.abs(rl[:6]))
+    assert tr[6] > 3.0 * tr[5] and abs(tr[6] - rl[6]) <= 0.1 * rl[6]
     x = s.result()
     assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
     with torch.cuda.stream(s.stream):

@@ -342,8 +342,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer (one thread) =====================
+    // The thread is chosen with elect.sync in a warp-uniform branch (not `lane == 0`): only then does the compiler know that
+    // a single lane runs the uniform-datapath UTCHMMA / UTCBAR instructions and emits them back to back; with a divergent
+    // predicate every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY serialisation loop (~45 cycles per MMA).
     // The issue rate of tcgen05.mma is set by the scalar instructions this thread executes between two of them
     // (measured: 45 cycles per MMA with constant descriptors, 76 with a few extra index operations,
     // profiles/r01_mma_issue_rate.log), so the 64-bit descriptors are not rebuilt per MMA: their upper halves are

@@ -228,6 +228,35 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     NST_BLOCK_SYNC();
     // lbfgs.py:432-435: for k newest..oldest: al_k = ro_k (s_k . q); q -= al_k y_k.  Column oriented: once al_k is
     // known every older row i subtracts al_k (s_i . y_k) from its running s_i . q - no reduction on the dependent chain.
+#if defined(__CUDA_ARCH__)
+    // device: lane l keeps the running values of rows l, l+32, l+64, l+96 in registers; al_k is broadcast from its
+    // owner with one 64-bit shuffle, so a step costs a shuffle + a multiply instead of a shared-memory round trip
+    if (tid < 32) {
+      double run[4], rok[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = tid + 32 * r;
+        const int p = nst_ctl_slot(head, i < len ? i : 0);
+        run[r] = i < len ? w.c[p] : 0.0;
+        rok[r] = i < len ? w.ro[p] : 0.0;
+      }
+#pragma unroll
+      for (int rb = 3; rb >= 0; --rb) {
+        for (int kk = 31; kk >= 0; --kk) {
+          const int k = rb * 32 + kk;
+          if (k >= len) continue;
+          const int pk = nst_ctl_slot(head, k);
+          const double al = __shfl_sync(0xffffffffu, rok[rb] * run[rb], kk);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = tid + 32 * r;
+            if (r <= rb && i < k) run[r] -= al * w.R[nst_ctl_slot(head, i) * TOT + pk];
+          }
+          if (tid == kk) w.al[pk] = al;
+        }
+      }
+    }
+#else
     if (tid < NST_CTL_NL) {
       for (int k = len - 1; k >= 0; --k) {
         const int pk = nst_ctl_slot(head, k);
@@ -240,6 +269,7 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         NST_WARP_SYNC();
       }
     }
+#endif
     NST_BLOCK_SYNC();
     // y_i . r at the start of loop 2: H (y_i . q) = H (-(y_i . g) - sum_j al_j (y_i . y_j))          [block parallel]
     for (int i = tid; i < len; i += nt) {
@@ -254,6 +284,34 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     NST_BLOCK_SYNC();
     // lbfgs.py:439-442: r = H q; for k oldest..newest: be_k = ro_k (y_k . r); r += (al_k - be_k) s_k.  Once c_k is known
     // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
+#if defined(__CUDA_ARCH__)
+    if (tid < 32) {
+      double run[4], rok[4], alk[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = tid + 32 * r;
+        const int p = nst_ctl_slot(head, i < len ? i : 0);
+        run[r] = i < len ? w.yq[p] : 0.0;
+        rok[r] = i < len ? w.ro[p] : 0.0;
+        alk[r] = i < len ? w.al[p] : 0.0;
+      }
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) {
+        for (int kk = 0; kk < 32; ++kk) {
+          const int k = rb * 32 + kk;
+          if (k >= len) break;
+          const int pk = nst_ctl_slot(head, k);
+          const double ck = __shfl_sync(0xffffffffu, alk[rb] - rok[rb] * run[rb], kk);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = tid + 32 * r;
+            if (r >= rb && i > k && i < len) run[r] += ck * w.R[pk * TOT + nst_ctl_slot(head, i)];
+          }
+          if (tid == kk) w.c[pk] = ck;
+        }
+      }
+    }
+#else
     if (tid < NST_CTL_NL) {
       for (int k = 0; k < len; ++k) {
         const int pk = nst_ctl_slot(head, k);
@@ -266,6 +324,7 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         NST_WARP_SYNC();
       }
     }
+#endif
     NST_BLOCK_SYNC();
     for (int i = tid; i < len; i += nt) {
       const int p = nst_ctl_slot(head, i);

@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int iters, long long* 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
+  // the issuing thread is chosen with elect.sync inside a warp-uniform branch: the compiler then knows that exactly one
+  // lane executes the uniform-datapath UTCHMMA and does not wrap each one in an ELECT / BRA.U.ANY serialisation loop
+  if (tid < 32 && elect_one()) {
     const uint32_t idesc = umma_idesc_f16(128, N, 0, 0, 0);
     const uint32_t a_addr0 = smem_u32(sA) + shift_rows * 128, b_addr = smem_u32(sB);
     const long long t0 = clock64();
