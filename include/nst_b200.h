@@ -184,8 +184,21 @@ int nst_plan_eval_timed(nst_plan* plan, const float* x, float* grad, nst_launch_
  * Returns the number of rows written (about 900). */
 int nst_lbfgs_step_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
 
-/* phase timestamps (SM clock) of CTA 0 of one convolution launch: tuning aid, see tools/conv_phases.py */
-int nst_plan_conv_phases(nst_plan* plan, int conv, int mode, long long* out7, void* stream);
+/* phase timestamps (SM clock) of CTA 0 of one convolution launch (mode 0 forward, 1 data gradient; conv 0 = conv1_1's
+   data gradient) -> out[0..6], and the SM cycles its roles spent waiting -> out[8..13] (slots: csrc/conv_tc.cu); out holds
+   14 values: tuning aid, see tools/conv_phases.py */
+int nst_plan_conv_phases(nst_plan* plan, int conv, int mode, long long* out14, void* stream);
+/* launch spans {earliest CTA start, latest CTA end} (%globaltimer ns) of the convolution launches inside the captured
+   step: slot = conv (forward), 16 + conv (data gradient), 32 + conv (Gram backward); enable re-captures the step with
+   the slots armed, out96 (2 x 48 values, may be NULL) reads them back and re-arms: tuning aid, tools/conv_timeline.py */
+int nst_plan_timeline(nst_plan* plan, int enable, unsigned long long* out96, void* stream);
+/* SM clock at the phase boundaries of the most recent L-BFGS controller launch (slots: csrc/lbfgs_ctl.h), 8 values:
+   tuning aid, tools/ctl_phases.py */
+int nst_lbfgs_ctl_clocks(nst_plan* plan, long long* out8, void* stream);
+/* runs the forward (which = 0) or backward (1) chained convolution launch once on the plan's current buffers with wait
+   accounting: out[16 * cta + slot] SM cycles (slots: csrc/conv_chain.cu), then 4 counters per chain layer from
+   out[16 * n_ctas]; out holds 16 * max_ctas + 256 values; returns the number of CTAs: tools/chain_waits.py */
+int nst_plan_chain_waits(nst_plan* plan, int which, long long* out, int max_ctas, void* stream);
 
 /* ---- host-buffer convenience (the e2e path: copies inside) ---------------------------------------
  * content_u8: [H,W,3] uint8 host; out_u8: [H,W,3] uint8 host (truncating, like ToPILImage).

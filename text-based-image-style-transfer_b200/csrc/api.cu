@@ -13,12 +13,14 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <vector>
 
+#include "conv_chain.cuh"
 #include "conv_tc.cuh"
 #include "gram.cuh"
 #include "lbfgs.cuh"
@@ -65,6 +67,7 @@ extern "C" int nst_device_check(void) {
                 prop.major, prop.minor);
   if (g_num_sms == 0) {
     e = conv_tc_init();
+    if (e == cudaSuccess) e = conv_chain_init();
     if (e == cudaSuccess) e = gram_init();
     if (e == cudaSuccess) e = lbfgs_init();
     if (e != cudaSuccess) return fail(NST_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(e));
@@ -197,6 +200,14 @@ struct nst_plan {
   float* img_dev = nullptr;
   float* gate_dev = nullptr;
   float* pooled_dev = nullptr;
+  // chained convolution launches (conv_chain.cu): [0] forward conv1_2.., [1] Gram backward + data gradients
+  bool chain = false;
+  ChainLayer* chain_dev[2] = {};
+  int chain_layers[2] = {}, chain_items[2] = {};
+  int* chain_done = nullptr;
+  size_t chain_done_bytes = 0;
+  unsigned long long* timeline = nullptr;  // [48][2] launch spans of the conv kernels (debug, nst_plan_timeline)
+  bool timeline_on = false;
 };
 
 static int plan_alloc(nst_plan* p, void** ptr, size_t bytes, bool zero) {
@@ -260,7 +271,7 @@ static int build_conv_params(nst_plan* p) {
     f.N = kCout[i];
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
-    f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
+    f.block_n = p->chain ? chain_block_n(kCout[i]) : conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
@@ -279,7 +290,7 @@ static int build_conv_params(nst_plan* p) {
     d.N = kCin[i];
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
-    d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
+    d.block_n = p->chain ? chain_block_n(kCin[i]) : conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
@@ -324,7 +335,7 @@ static int build_conv_params(nst_plan* p) {
     c.N = C;
     c.taps = 1;
     if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
-    c.block_n = conv_block_n(C, c.H, c.W, C, g_num_sms);
+    c.block_n = p->chain ? chain_block_n(C) : conv_block_n(C, c.H, c.W, C, g_num_sms);
     if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
     c.alpha = p->alpha + l;
     c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
@@ -359,6 +370,74 @@ static int build_gram_params(nst_plan* p) {
   }
   return NST_OK;
 }
+
+// Work lists of the two chained launches (conv_chain.cu).  Forward: conv1_2 .. the deepest conv.  Backward: the Gram
+// backward (1x1) layers of every style layer first - they depend on nothing inside the launch - then the data gradients
+// from the deepest conv down to conv1_2 (conv1_1's data gradient, N = 3, stays a launch of its own).
+static int build_chains(nst_plan* p) {
+  if (!p->chain) return NST_OK;
+  const int last = p->n_layers - 1;
+  std::vector<ChainLayer> lists[2];
+  std::vector<size_t> done_off[2];
+  size_t n_done = 0;
+  auto push = [&](int which, const ConvParams& c, int mode) -> int {
+    ChainLayer L;
+    memset(&L, 0, sizeof(L));
+    L.c = c;
+    L.c.dbg = nullptr;
+    L.c.tl = nullptr;
+    L.mode = mode;
+    L.dep_layer[0] = L.dep_layer[1] = -1;
+    L.item_base = lists[which].empty() ? 0 : lists[which].back().item_base + lists[which].back().c.num_tiles;
+    done_off[which].push_back(n_done);
+    n_done += static_cast<size_t>(c.tiles_h) * c.tiles_w;
+    lists[which].push_back(L);
+    return static_cast<int>(lists[which].size()) - 1;
+  };
+  auto dep = [&](ChainLayer& L, int k, int layer, int rpt, int cpt, int halo) {
+    L.dep_layer[k] = layer;
+    L.dep_rpt[k] = rpt;
+    L.dep_cpt[k] = cpt;
+    L.dep_halo[k] = halo;
+  };
+  for (int i = 1; i <= last; ++i) {
+    const int e = push(0, p->fwd[i], CONV_FWD);
+    // conv i reads the (pooled) output of conv i-1; conv1_1 is an earlier launch
+    if (i >= 2) dep(lists[0][e], 0, e - 1, kPoolAfter[i - 1] ? 8 : 16, kPoolAfter[i - 1] ? 4 : 8, 1);
+  }
+  if (p->with_grad) {
+    int scale_entry[NST_MAX_CONV];
+    for (int i = 0; i < NST_MAX_CONV; ++i) scale_entry[i] = -1;
+    for (int l = p->n_style - 1; l >= 0; --l) scale_entry[p->style_conv[l]] = push(1, p->scale[p->style_conv[l]], CONV_SCALE);
+    int prev = -1;
+    for (int i = last; i >= 1; --i) {
+      const int e = push(1, p->dgrad[i], CONV_DGRAD);
+      ChainLayer& L = lists[1][e];
+      // A operand = gpre[i]: written by the data gradient of conv i+1 (through the pool routing if conv i is pooled),
+      // or, for the deepest conv, by its Gram-backward layer (a content-only seed comes from an earlier launch)
+      if (i == last) {
+        if (scale_entry[last] >= 0) dep(L, 0, scale_entry[last], 16, 8, 1);
+      } else {
+        dep(L, 0, prev, kPoolAfter[i] ? 32 : 16, kPoolAfter[i] ? 16 : 8, 1);
+      }
+      // the epilogue adds the tap seed of conv i-1 (gadd[i-1]) when that is a style layer
+      if (L.c.addend != nullptr && scale_entry[i - 1] >= 0) dep(L, 1, scale_entry[i - 1], 16, 8, 0);
+      prev = e;
+    }
+  }
+  CKI(plan_alloc_t(p, &p->chain_done, n_done > 0 ? n_done : 1, true));
+  p->chain_done_bytes = n_done * sizeof(int);
+  for (int w = 0; w < 2; ++w) {
+    if (lists[w].empty()) continue;
+    for (size_t k = 0; k < lists[w].size(); ++k) lists[w][k].done = p->chain_done + done_off[w][k];
+    CKI(plan_alloc_t(p, &p->chain_dev[w], lists[w].size()));
+    CK(cudaMemcpy(p->chain_dev[w], lists[w].data(), lists[w].size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
+    p->chain_layers[w] = static_cast<int>(lists[w].size());
+    p->chain_items[w] = lists[w].back().item_base + lists[w].back().c.num_tiles;
+  }
+  return NST_OK;
+}
+
 
 extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
                                uint32_t content_mask, int with_grad) {
@@ -509,7 +588,21 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.ctl, 1, true));
     b.eval_loss = p->losses;
   }
+  {
+    // Opt-in (NST_CHAIN=1): one persistent launch per chain with tile-level dataflow between layers (conv_chain.cu).
+    // Measured at 512^2 (profiles/r01_chain_waits_512.log) it does not beat the per-layer launches: CTAs advance in
+    // lockstep, so almost every tile consumes what the previous wave just produced and pays the producer -> consumer
+    // latency (epilogue + fence + poll + first TMA, ~4.5 us) that a kernel boundary pays once per layer, and the Gram
+    // kernels can no longer hide on the side stream.  Kept for batches of independent frames, where other frames' tiles
+    // fill those waits.  A conv that is both a style and a content layer needs the content seed accumulated after its
+    // Gram seed, which only the per-layer path orders.
+    const bool want_chain = getenv("NST_CHAIN") != nullptr && getenv("NST_CHAIN")[0] == '1';
+    bool both = false;
+    for (int l = 0; l < p->n_content; ++l) both = both || style_index(p, p->content_conv[l]) >= 0;
+    p->chain = want_chain && !both && n_layers >= 2;
+  }
   PA(build_conv_params(p));
+  PA(build_chains(p));
 #undef PA
   *out = p;
   return NST_OK;
@@ -547,7 +640,12 @@ extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content,
 // ------------------------------------------------------------------------------------------------
 static int forward_enqueue(nst_plan* p, const float* x, cudaStream_t s) {
   const nst_net* net = p->net;
+  if (p->chain) CK(cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s));
   CK(launch_conv1_fwd(x, net->w32[0], net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+  if (p->chain) {
+    CK(launch_conv_chain(p->chain_dev[0], p->chain_layers[0], p->chain_items[0], g_num_sms, s));
+    return NST_OK;
+  }
   for (int i = 1; i < p->n_layers; ++i) CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
   return NST_OK;
 }
@@ -754,6 +852,123 @@ struct LaunchTimer {
     if (tm && tm->mark((k), (l)) != 0) return fail(NST_ERR_CUDA, "event record failed"); \
   } while (0)
 
+// The same evaluation with the two chained launches (conv_chain.cu): main stream = conv1_1, forward chain, Gram of the
+// deepest style layer, backward chain (Gram backward + data gradients), conv1_1's data gradient; side stream = pixel
+// terms, Gram / style MSE of the shallower style layers, content loss, loss assembly.
+static int eval_enqueue_chain(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
+                              cudaStream_t s, LaunchTimer* tm) {
+  int nl = 0;
+  TM(NST_K_START, -1);
+  const bool conc = tm == nullptr && p->side != nullptr;
+  cudaStream_t s2 = conc ? p->side : s;
+  enum { EV_FORK = 0, EV_TAPS = 1, EV_SEEDS = 4, EV_GRAM = 5, EV_JOIN = 6 };
+  auto edge = [&](int ev, cudaStream_t from, cudaStream_t to) -> cudaError_t {
+    if (!conc) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(p->ev[ev], from);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(to, p->ev[ev], 0);
+    return e;
+  };
+  const int last = p->n_layers - 1;
+  const bool deep_style = p->n_style > 0 && p->style_conv[p->n_style - 1] == last;
+  auto content_launch = [&](int l, cudaStream_t st) -> cudaError_t {
+    const int i = p->content_conv[l];
+    const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+    __nv_bfloat16* seed = grad != nullptr ? (i == last ? p->gpre[i] : p->gadd[i]) : nullptr;
+    const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
+    return launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel, gcoef, 0, st);
+  };
+  // ---- side: pixel-space terms
+  CK(edge(EV_FORK, s, s2));
+  CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
+  ++nl;
+  TM(NST_K_PIXEL, -1);
+  // ---- main: VGG forward
+  CK(cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s));
+  CK(launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+  ++nl;
+  TM(NST_K_CONV1_FWD, 0);
+  CK(launch_conv_chain(p->chain_dev[0], p->chain_layers[0], p->chain_items[0], g_num_sms, s));
+  ++nl;
+  TM(NST_K_CONV_FWD, 100);
+  // ---- side: Gram, style MSE and backward operand of the shallower style layers; content loss (+ its seed)
+  CK(edge(EV_TAPS, s, s2));
+  if (p->gram_shallow.num_layers > 0) {
+    CK(launch_gram(p->gram_shallow, s2));
+    nl += 3;
+    TM(NST_K_GRAM, 0);
+  }
+  for (int l = 0; l < p->n_content; ++l) {
+    if (p->content_conv[l] == last) continue;
+    CK(content_launch(l, s2));
+    ++nl;
+    TM(NST_K_CONTENT, p->content_conv[l]);
+  }
+  if (grad != nullptr && conc) CK(cudaEventRecord(p->ev[EV_SEEDS], s2));
+  // ---- main: the deepest layer's targets
+  if (deep_style) {
+    CK(launch_gram(p->gram_deep, s));
+    nl += 3;
+    TM(NST_K_GRAM, last);
+  }
+  for (int l = 0; l < p->n_content; ++l) {
+    if (p->content_conv[l] != last) continue;
+    CK(content_launch(l, s));
+    ++nl;
+    TM(NST_K_CONTENT, last);
+  }
+  // ---- side: loss assembly
+  CK(edge(EV_GRAM, s, s2));
+  LossAssembleArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tv_part = p->tv_part;
+  a.n_tv = pixel_blocks(p->H, p->W);
+  a.edge_part = p->edge_part;
+  a.n_edge = pixel_blocks(p->H, p->W);
+  a.content_part = p->content_part;
+  a.n_content = p->content_part_off[p->n_content];
+  a.style_layer_loss = p->style_loss;
+  a.num_style = p->n_style;
+  a.w_style = p->w_style;
+  a.w_content = p->w_content;
+  a.w_tv = p->w_tv;
+  a.w_edge = p->w_edge;
+  a.tv_norm = 1.0 / (3.0 * p->H * p->W);
+  a.edge_norm = (p->H > 2 && p->W > 2) ? 1.0 / (static_cast<double>(p->H - 2) * (p->W - 2)) : 0.0;
+  if (p->n_content > 0) {
+    const int i = p->content_conv[0];
+    const double numel = static_cast<double>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
+    a.content_norm = 1.0 / (numel * p->n_content);
+  }
+  a.out = p->losses;
+  a.counter = counter;
+  a.stop_flag = stop_flag;
+  a.trace = p->trace;
+  a.trace_cap = p->trace_cap;
+  CK(launch_loss_assemble(a, s2));
+  ++nl;
+  TM(NST_K_ASSEMBLE, -1);
+  if (conc) CK(cudaEventRecord(p->ev[EV_JOIN], s2));
+  // ---- main: backward chain
+  if (grad != nullptr) {
+    if (conc) CK(cudaStreamWaitEvent(s, p->ev[EV_SEEDS], 0));
+    CK(launch_conv_chain(p->chain_dev[1], p->chain_layers[1], p->chain_items[1], g_num_sms, s));
+    ++nl;
+    TM(NST_K_CONV_DGRAD, 100);
+    if (conc) CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
+    ConvParams d = p->dgrad[0];
+    d.out_pix = grad;
+    for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
+    CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
+    ++nl;
+    TM(NST_K_CONV1_DGRAD, 0);
+  } else if (conc) {
+    CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
+  }
+  if (launches) *launches += nl;
+  return NST_OK;
+}
+
+
 // Enqueues one closure evaluation.  With a side stream (p->side, default) the evaluation is a small DAG: the
 // critical path conv forward -> Gram of the deepest style layer -> data gradients runs on `s`; everything that
 // only feeds it sideways (pixel-space losses, Gram + finalize + Gram-backward seeds of the shallower style layers,
@@ -762,9 +977,10 @@ struct LaunchTimer {
 static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
                         cudaStream_t s, LaunchTimer* tm = nullptr) {
   int nl = 0;
-  TM(NST_K_START, -1);
   const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
   if (grad != nullptr && !p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
+  if (p->chain && use_vgg) return eval_enqueue_chain(p, x, grad, counter, stop_flag, launches, s, tm);
+  TM(NST_K_START, -1);
   const bool conc = tm == nullptr && p->side != nullptr && use_vgg;
   cudaStream_t s2 = conc ? p->side : s;
   enum { EV_FORK = 0, EV_TAPS = 1, EV_CONTENT_IN = 2, EV_CONTENT = 3, EV_SEEDS = 4, EV_GRAM = 5, EV_JOIN = 6 };
@@ -995,6 +1211,7 @@ extern "C" int nst_plan_eval_timed(nst_plan* p, const float* x, float* grad, nst
 
 // forward declaration (defined with the L-BFGS loop below)
 static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm);
+static void timeline_arm(nst_plan* p, bool on);
 
 extern "C" int nst_lbfgs_step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
   if (!p || !out || max_out < 64) return fail(NST_ERR_ARG, "nst_lbfgs_step_timed: bad arguments");
@@ -1014,19 +1231,76 @@ extern "C" int nst_lbfgs_step_timed(nst_plan* p, nst_launch_time* out, int max_o
 // timestamps of CTA 0 -> out[7] (SM clock): 0 start, 1 setup done, 2 first operands landed, 3 last MMA issued,
 // 4 accumulator complete, 5 epilogue done, 6 exit.
 extern "C" int nst_plan_conv_phases(nst_plan* p, int conv, int mode, long long* out7, void* stream) {
-  if (!p || conv < 1 || conv >= p->n_layers || !out7) return fail(NST_ERR_ARG, "nst_plan_conv_phases: bad arguments");
+  if (!p || conv < (mode == 1 ? 0 : 1) || conv >= p->n_layers || !out7) return fail(NST_ERR_ARG, "nst_plan_conv_phases: bad arguments");
   if (mode == 1 && !p->with_grad) return fail(NST_ERR_STATE, "plan has no gradient buffers");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long* d = nullptr;
-  CK(cudaMalloc(&d, 8 * sizeof(long long)));
-  cudaError_t e = cudaMemsetAsync(d, 0, 8 * sizeof(long long), s);
+  CK(cudaMalloc(&d, 16 * sizeof(long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, 16 * sizeof(long long), s);
   ConvParams c = mode == 0 ? p->fwd[conv] : p->dgrad[conv];
   c.dbg = d;
-  if (e == cudaSuccess) e = launch_conv_tc(c, mode == 0 ? CONV_FWD : CONV_DGRAD, g_num_sms, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, 7 * sizeof(long long), cudaMemcpyDeviceToHost, s);
+  if (mode == 1 && conv == 0) {
+    c.out_pix = p->lb.g != nullptr ? p->lb.g : p->grad_pix;
+    for (int k = 0; k < 3; ++k) c.inv_std[k] = 1.f / p->pc.stdv[k];
+  }
+  if (e == cudaSuccess) e = launch_conv_tc(c, mode == 0 ? CONV_FWD : (conv == 0 ? CONV_DGRAD_PIX : CONV_DGRAD), g_num_sms, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, 14 * sizeof(long long), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(d);
   if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_plan_conv_phases: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
+// Debug / tuning aid: SM clock at the phase boundaries of the last L-BFGS controller launch (slots: lbfgs_ctl.h).
+extern "C" int nst_lbfgs_ctl_clocks(nst_plan* p, long long* out8, void* stream) {
+  if (!p || !out8 || !p->with_grad) return fail(NST_ERR_ARG, "nst_lbfgs_ctl_clocks: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(out8, reinterpret_cast<const char*>(p->lb.ctl) + offsetof(NstLbfgsCtl, clk), 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return NST_OK;
+}
+
+// Debug / tuning aid: runs the forward (which = 0) or backward (1) chained launch once on the plan's current buffers and
+// returns the wait accounting of every CTA (16 counters per CTA, SM cycles; slot meaning: conv_chain.cu) followed by 4
+// counters per layer of the chain (64 layers): out must hold 16 * max_ctas + 256 values.
+extern "C" int nst_plan_chain_waits(nst_plan* p, int which, long long* out, int max_ctas, void* stream) {
+  if (!p || !out || which < 0 || which > 1 || max_ctas < g_num_sms) return fail(NST_ERR_ARG, "nst_plan_chain_waits: bad arguments");
+  if (!p->chain || p->chain_layers[which] == 0) return fail(NST_ERR_STATE, "plan has no chained launch %d", which);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long* d = nullptr;
+  const size_t bytes = (static_cast<size_t>(16) * g_num_sms + 256) * sizeof(long long);
+  CK(cudaMalloc(&d, bytes));
+  cudaError_t e = cudaMemsetAsync(d, 0, bytes, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s);
+  if (e == cudaSuccess) e = launch_conv_chain(p->chain_dev[which], p->chain_layers[which], p->chain_items[which], g_num_sms, s, d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_plan_chain_waits: %s", cudaGetErrorString(e));
+  return g_num_sms;
+}
+
+// Debug / tuning aid: where do the convolution launches sit inside the captured step?  enable = 1 gives every conv launch
+// of the plan a slot {earliest CTA start, latest CTA end} in %globaltimer ns (slot = conv for forward, 16 + conv for data
+// gradients, 32 + conv for Gram backward) and drops the captured graph so that the next step re-captures with the slots;
+// out96 != nullptr reads the slots back (2 x 48 values) and re-arms them.
+extern "C" int nst_plan_timeline(nst_plan* p, int enable, unsigned long long* out96, void* stream) {
+  if (!p) return fail(NST_ERR_ARG, "nst_plan_timeline: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (enable && !p->timeline) CKI(plan_alloc_t(p, &p->timeline, 96));
+  unsigned long long init[96];
+  for (int i = 0; i < 48; ++i) {
+    init[2 * i] = ~0ull;
+    init[2 * i + 1] = 0ull;
+  }
+  if (out96 && p->timeline) {
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpy(out96, p->timeline, sizeof(init), cudaMemcpyDeviceToHost));
+  }
+  if (p->timeline) CK(cudaMemcpy(p->timeline, init, sizeof(init), cudaMemcpyHostToDevice));
+  p->timeline_on = enable != 0;
+  if (!p->timeline_on) timeline_arm(p, false);
+  drop_graph(p);
   return NST_OK;
 }
 
@@ -1154,6 +1428,15 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
 
 // One optimizer.step(closure).  max_evals < 20 truncates the step after that many evaluations (used to time an
 // exact number of evaluations; the optimizer state stays valid - it looks like a step that ended early).
+// arms (or disarms) the launch-span slots of every convolution launch of the plan; see nst_plan_timeline
+static void timeline_arm(nst_plan* p, bool on) {
+  for (int i = 0; i < p->n_layers; ++i) {
+    p->fwd[i].tl = on ? p->timeline + 2 * i : nullptr;
+    p->dgrad[i].tl = on ? p->timeline + 2 * (16 + i) : nullptr;
+    p->scale[i].tl = on ? p->timeline + 2 * (32 + i) : nullptr;
+  }
+}
+
 static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm) {
   LbfgsBuffers& b = p->lb;
   int nl = 0, evals = 0;
@@ -1179,6 +1462,7 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
     }
     nl += 4;
     if (k != max_iter) {
+      if (p->timeline_on) timeline_arm(p, evals == 10);  // the spans of ONE evaluation in the middle of the step
       CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s, tm));  // lbfgs.py:493-502
       ++evals;
     }

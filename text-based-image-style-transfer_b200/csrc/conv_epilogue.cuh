@@ -1,0 +1,188 @@
+// Epilogue building blocks of the tcgen05 convolution kernels (conv_tc.cu: one launch per layer; conv_chain.cu: a whole
+// chain of layers in one persistent launch).  One thread = one pixel of the 16 x 8 tile.
+#pragma once
+#include "conv_tc.cuh"
+#include "common.cuh"
+
+namespace nst {
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers (one thread = one pixel of the tile, 32 consecutive channels per call)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store_h32(__half* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_h2(v[8 * q + 0], v[8 * q + 1]);
+    u.y = pack_h2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_h2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack_h2(v[8 * q + 6], v[8 * q + 7]);
+    d[q] = u;
+  }
+}
+template <int CH>
+__device__ __forceinline__ void store_bf(__nv_bfloat16* dst, const float (&v)[CH]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < CH / 8; ++q) {
+    uint4 u;
+    u.x = pack_bf2(v[8 * q + 0], v[8 * q + 1]);
+    u.y = pack_bf2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack_bf2(v[8 * q + 6], v[8 * q + 7]);
+    d[q] = u;
+  }
+}
+
+// forward epilogue for 32 channels of one pixel
+__device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
+                                             int lane, const float* sbias /* 32 values of this chunk, shared memory */) {
+  // bias (same address across the warp -> broadcast read); staged in shared memory while the main loop ran
+  const float4* b4 = reinterpret_cast<const float4*>(sbias);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 b = b4[q];
+    v[4 * q + 0] += b.x;
+    v[4 * q + 1] += b.y;
+    v[4 * q + 2] += b.z;
+    v[4 * q + 3] += b.w;
+  }
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  if (p.out_tap != nullptr && valid) store_h32(p.out_tap + pix * p.N + n, v);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+  if (!p.pool) {
+    if (p.out_act != nullptr && valid) store_h32(p.out_act + pix * p.N + n, v);
+    return;
+  }
+  // 2x2 max-pool across the four lanes {lane, lane^1, lane^8, lane^9}: tile rows are 8 pixels
+  // wide and a warp owns four consecutive rows.  The window position is folded into the two low
+  // mantissa bits so that one integer max gives both the value and PyTorch's first-max arg-max.
+  const uint32_t pos = ((lane >> 3) & 1) * 2 + (lane & 1);
+  float pooled[32];
+  uint32_t win[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    uint32_t key = (__float_as_uint(v[j]) & ~3u) | (3u - pos);
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
+    pooled[j] = __uint_as_float(key & ~3u);
+    win[j] = pooled[j] > 0.f ? 3u - (key & 3u) : 4u;
+  }
+  const int Hp = p.H >> 1, Wp = p.W >> 1;
+  const int hp = h >> 1, wp = w >> 1;
+  if (hp < Hp && wp < Wp) {
+    const size_t ppix = static_cast<size_t>(hp) * Wp + wp;
+    // each of the four lanes of a window stores 8 of the 32 channels
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      if (pos == static_cast<uint32_t>(jj)) {
+        uint4 u;
+        u.x = pack_h2(pooled[8 * jj + 0], pooled[8 * jj + 1]);
+        u.y = pack_h2(pooled[8 * jj + 2], pooled[8 * jj + 3]);
+        u.z = pack_h2(pooled[8 * jj + 4], pooled[8 * jj + 5]);
+        u.w = pack_h2(pooled[8 * jj + 6], pooled[8 * jj + 7]);
+        *reinterpret_cast<uint4*>(p.out_act + ppix * p.N + n + 8 * jj) = u;
+        uint2 r;
+        r.x = win[8 * jj + 0] | (win[8 * jj + 1] << 8) | (win[8 * jj + 2] << 16) | (win[8 * jj + 3] << 24);
+        r.y = win[8 * jj + 4] | (win[8 * jj + 5] << 8) | (win[8 * jj + 6] << 16) | (win[8 * jj + 7] << 24);
+        *reinterpret_cast<uint2*>(p.out_route + ppix * p.N + n + 8 * jj) = r;
+      }
+    }
+  }
+}
+
+// Operands of the data-gradient epilogue for DG_CH channels of one pixel (mask + tap seed, or pool routing bytes).
+// They do not depend on the accumulator, so they are fetched one chunk ahead - the first one before the
+// accumulator is even complete - instead of serialising global-memory latencies on the critical path of a tile.
+static constexpr int DG_CH = 16;
+struct DgradAux {
+  uint4 m[2];  // post-ReLU activation (fp16) whose sign masks the gradient   | m[0]: routing bytes
+  uint4 a[2];  // tap seed (bf16) added to the gradient
+};
+__device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x, int h, int w, int n, bool valid) {
+  if (!valid) return;
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  if (p.route == nullptr) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
+    x.m[0] = __ldg(m4);
+    x.m[1] = __ldg(m4 + 1);
+    if (p.addend != nullptr) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
+      // L2-coherent loads: in the chained kernel the seed is written earlier in the same launch (by another SM)
+      x.a[0] = __ldcg(a4);
+      x.a[1] = __ldcg(a4 + 1);
+    }
+  } else {
+    x.m[0] = __ldg(reinterpret_cast<const uint4*>(p.route + pix * p.N + n));
+  }
+}
+
+// data-gradient epilogue for DG_CH channels of one pixel
+__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[DG_CH], int h, int w, int n, bool valid,
+                                               const DgradAux& x) {
+  if (!valid) return;
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  if (p.route == nullptr) {
+    // ReLU mask from the stored post-ReLU activation (PyTorch: grad * (result > 0))
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const __half2* hh = reinterpret_cast<const __half2*>(&x.m[q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(hh[e]);
+        if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
+        if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+      }
+    }
+    if (p.addend != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&x.a[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(bb[e]);
+          v[8 * q + 2 * e] += f.x;
+          v[8 * q + 2 * e + 1] += f.y;
+        }
+      }
+    }
+    store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
+  } else {
+    // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
+    // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
+    uint32_t r[4];
+    r[0] = x.m[0].x; r[1] = x.m[0].y; r[2] = x.m[0].z; r[3] = x.m[0].w;
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      float o[DG_CH];
+#pragma unroll
+      for (int j = 0; j < DG_CH; ++j) {
+        const uint32_t rj = (r[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        o[j] = rj == static_cast<uint32_t>(pos) ? v[j] : 0.f;
+      }
+      const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
+      store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_scale(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
+                                               float alpha) {
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= alpha;
+  const size_t pix = static_cast<size_t>(h) * p.W + w;
+  store_bf<32>(p.out_grad + pix * p.N + n, v);
+}
+
+}  // namespace nst

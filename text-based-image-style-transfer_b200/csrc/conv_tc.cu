@@ -19,6 +19,7 @@
 // the halo costs 23 KB per 36.
 #include "conv_tc.cuh"
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -60,182 +61,10 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
 };
 
-// ---------------------------------------------------------------------------------------------
-// epilogue helpers (one thread = one pixel of the tile, 32 consecutive channels per call)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void store_h32(__half* dst, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_h2(v[8 * q + 0], v[8 * q + 1]);
-    u.y = pack_h2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_h2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack_h2(v[8 * q + 6], v[8 * q + 7]);
-    d[q] = u;
-  }
-}
-template <int CH>
-__device__ __forceinline__ void store_bf(__nv_bfloat16* dst, const float (&v)[CH]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < CH / 8; ++q) {
-    uint4 u;
-    u.x = pack_bf2(v[8 * q + 0], v[8 * q + 1]);
-    u.y = pack_bf2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack_bf2(v[8 * q + 6], v[8 * q + 7]);
-    d[q] = u;
-  }
-}
-
-// forward epilogue for 32 channels of one pixel
-__device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
-                                             int lane, const float* sbias /* 32 values of this chunk, shared memory */) {
-  // bias (same address across the warp -> broadcast read); staged in shared memory while the main loop ran
-  const float4* b4 = reinterpret_cast<const float4*>(sbias);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4 b = b4[q];
-    v[4 * q + 0] += b.x;
-    v[4 * q + 1] += b.y;
-    v[4 * q + 2] += b.z;
-    v[4 * q + 3] += b.w;
-  }
-  const size_t pix = static_cast<size_t>(h) * p.W + w;
-  if (p.out_tap != nullptr && valid) store_h32(p.out_tap + pix * p.N + n, v);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
-  if (!p.pool) {
-    if (p.out_act != nullptr && valid) store_h32(p.out_act + pix * p.N + n, v);
-    return;
-  }
-  // 2x2 max-pool across the four lanes {lane, lane^1, lane^8, lane^9}: tile rows are 8 pixels
-  // wide and a warp owns four consecutive rows.  The window position is folded into the two low
-  // mantissa bits so that one integer max gives both the value and PyTorch's first-max arg-max.
-  const uint32_t pos = ((lane >> 3) & 1) * 2 + (lane & 1);
-  float pooled[32];
-  uint32_t win[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    uint32_t key = (__float_as_uint(v[j]) & ~3u) | (3u - pos);
-    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
-    key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
-    pooled[j] = __uint_as_float(key & ~3u);
-    win[j] = pooled[j] > 0.f ? 3u - (key & 3u) : 4u;
-  }
-  const int Hp = p.H >> 1, Wp = p.W >> 1;
-  const int hp = h >> 1, wp = w >> 1;
-  if (hp < Hp && wp < Wp) {
-    const size_t ppix = static_cast<size_t>(hp) * Wp + wp;
-    // each of the four lanes of a window stores 8 of the 32 channels
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      if (pos == static_cast<uint32_t>(jj)) {
-        uint4 u;
-        u.x = pack_h2(pooled[8 * jj + 0], pooled[8 * jj + 1]);
-        u.y = pack_h2(pooled[8 * jj + 2], pooled[8 * jj + 3]);
-        u.z = pack_h2(pooled[8 * jj + 4], pooled[8 * jj + 5]);
-        u.w = pack_h2(pooled[8 * jj + 6], pooled[8 * jj + 7]);
-        *reinterpret_cast<uint4*>(p.out_act + ppix * p.N + n + 8 * jj) = u;
-        uint2 r;
-        r.x = win[8 * jj + 0] | (win[8 * jj + 1] << 8) | (win[8 * jj + 2] << 16) | (win[8 * jj + 3] << 24);
-        r.y = win[8 * jj + 4] | (win[8 * jj + 5] << 8) | (win[8 * jj + 6] << 16) | (win[8 * jj + 7] << 24);
-        *reinterpret_cast<uint2*>(p.out_route + ppix * p.N + n + 8 * jj) = r;
-      }
-    }
-  }
-}
-
-// Operands of the data-gradient epilogue for DG_CH channels of one pixel (mask + tap seed, or pool routing bytes).
-// They do not depend on the accumulator, so they are fetched one chunk ahead - the first one before the
-// accumulator is even complete - instead of serialising global-memory latencies on the critical path of a tile.
-static constexpr int DG_CH = 16;
-struct DgradAux {
-  uint4 m[2];  // post-ReLU activation (fp16) whose sign masks the gradient   | m[0]: routing bytes
-  uint4 a[2];  // tap seed (bf16) added to the gradient
-};
-__device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x, int h, int w, int n, bool valid) {
-  if (!valid) return;
-  const size_t pix = static_cast<size_t>(h) * p.W + w;
-  if (p.route == nullptr) {
-    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
-    x.m[0] = __ldg(m4);
-    x.m[1] = __ldg(m4 + 1);
-    if (p.addend != nullptr) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
-      x.a[0] = __ldg(a4);
-      x.a[1] = __ldg(a4 + 1);
-    }
-  } else {
-    x.m[0] = __ldg(reinterpret_cast<const uint4*>(p.route + pix * p.N + n));
-  }
-}
-
-// data-gradient epilogue for DG_CH channels of one pixel
-__device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[DG_CH], int h, int w, int n, bool valid,
-                                               const DgradAux& x) {
-  if (!valid) return;
-  const size_t pix = static_cast<size_t>(h) * p.W + w;
-  if (p.route == nullptr) {
-    // ReLU mask from the stored post-ReLU activation (PyTorch: grad * (result > 0))
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const __half2* hh = reinterpret_cast<const __half2*>(&x.m[q]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(hh[e]);
-        if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
-        if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
-      }
-    }
-    if (p.addend != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&x.a[q]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 f = __bfloat1622float2(bb[e]);
-          v[8 * q + 2 * e] += f.x;
-          v[8 * q + 2 * e + 1] += f.y;
-        }
-      }
-    }
-    store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
-  } else {
-    // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
-    // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
-    uint32_t r[4];
-    r[0] = x.m[0].x; r[1] = x.m[0].y; r[2] = x.m[0].z; r[3] = x.m[0].w;
-#pragma unroll
-    for (int pos = 0; pos < 4; ++pos) {
-      float o[DG_CH];
-#pragma unroll
-      for (int j = 0; j < DG_CH; ++j) {
-        const uint32_t rj = (r[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        o[j] = rj == static_cast<uint32_t>(pos) ? v[j] : 0.f;
-      }
-      const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
-      store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
-    }
-  }
-}
-
-__device__ __forceinline__ void epilogue_scale(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
-                                               float alpha) {
-  if (!valid) return;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= alpha;
-  const size_t pix = static_cast<size_t>(h) * p.W + w;
-  store_bf<32>(p.out_grad + pix * p.N + n, v);
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,7 +96,21 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   do {                                                               \
     if (dbg && (cond)) p.dbg[slot] = clock64();                      \
   } while (0)
+  // wait accounting of CTA 0 (debug): slot 8 MMA waits for the patch, 9 for weights, 10 for a free accumulator stage,
+  // 11 epilogue (warp 4) waits for the accumulator, 12 producer waits for a free patch stage, 13 for a free weight stage
+  long long wacc0 = 0, wacc1 = 0, wacc2 = 0;
+#define NST_WAIT(acc, stmt)                   \
+  do {                                        \
+    if (dbg) {                                \
+      const long long w0__ = clock64();       \
+      stmt;                                   \
+      acc += clock64() - w0__;                \
+    } else {                                  \
+      stmt;                                   \
+    }                                         \
+  } while (0)
   NST_STAMP(0, threadIdx.x == 0);
+  if (p.tl != nullptr && threadIdx.x == 0) atomicMin(&p.tl[0], globaltimer_ns());
   // Programmatic dependent launch: let the next kernel in the stream get scheduled as soon as CTAs of this grid retire
   // (its CTAs run their own setup, then block in griddepcontrol.wait until this grid has completed and flushed).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -310,6 +153,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   const uint32_t a_tx = p.taps == 9 ? HALO_TX_BYTES : FLAT_TX_BYTES;
   const int sp_tiles = p.tiles_w * p.tiles_h;
   const int tps = p.taps == 9 ? Cfg::TPS : 1;              // taps per weight stage (the weight tensor map's box depth)
+  // A layer with 64 input channels has ONE 64-channel slice: its whole weight set (nine taps) fits the weight ring.  It
+  // is then loaded once per CTA and stays resident - re-streaming it for every tile (72 KB next to a 23 KB patch at
+  // N = 64) made the 64-channel layers L2-bandwidth bound (148 SMs x ~96 KB per microsecond).  All tiles of a launch
+  // must then use the same weights: one N tile only.
+  const bool b_resident = p.taps == 9 && k_slices == 1 && 9 / Cfg::TPS <= Cfg::B_STAGES && p.tiles_n == 1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -323,15 +171,16 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         const int tw = sp - th * p.tiles_w;
         const int h0 = th * TILE_H, w0 = tw * TILE_W, n0 = nt * BLOCK_N;
         for (int ks = 0; ks < k_slices; ++ks) {
-          mbar_wait(&aempty_bar[as], aphase ^ 1u);
+          NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
           mbar_arrive_expect_tx(&afull_bar[as], a_tx);
           tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA, &afull_bar[as], ks * BLOCK_K, w0 - pad, h0 - pad);
           if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
           }
+          if (b_resident && tile != static_cast<int>(blockIdx.x)) continue;
           for (int tap = 0; tap < p.taps; tap += tps) {
-            mbar_wait(&bempty_bar[bs], bphase ^ 1u);
+            NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
             mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
             tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], ks * BLOCK_K, n0, tap);
             if (++bs == Cfg::B_STAGES) {
@@ -340,6 +189,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             }
           }
         }
+      }
+      if (dbg) {
+        p.dbg[12] = wacc0;
+        p.dbg[13] = wacc1;
       }
     }
   } else if (warp == 1 && elect_one()) {
@@ -360,19 +213,21 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     const uint32_t lbo_lo = static_cast<uint32_t>(umma_desc_sw128(0, 16, 0) & 0xffffffffu);  // LBO field, address 0
     const bool conv3x3 = p.taps == 9;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[ts], tphase ^ 1u);
+      NST_WAIT(wacc2, mbar_wait(&tempty_bar[ts], tphase ^ 1u));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
       uint32_t accumulate = 0;
       for (int ks = 0; ks < k_slices; ++ks) {
-        mbar_wait(&afull_bar[as], aphase);
+        NST_WAIT(wacc0, mbar_wait(&afull_bar[as], aphase));
         NST_STAMP(2, ks == 0 && tile == blockIdx.x);
         const uint32_t a_lo0 = lbo_lo | (smem_u32(sA + as * HALO_STAGE_BYTES) >> 4);
         if (conv3x3) {
           // nine taps = nine row shifts of the patch: (dr * 10 + ds) rows of 128 B = (dr * 10 + ds) * 8 descriptor units
 #pragma unroll 1
           for (int g = 0; g < 9 / Cfg::TPS; ++g) {
-            mbar_wait(&bfull_bar[bs], bphase);
+            // resident weights: stage g holds filter row(s) g for the whole launch; only the first tile waits for them
+            if (b_resident) bs = g;
+            if (!b_resident || tile == static_cast<int>(blockIdx.x)) NST_WAIT(wacc1, mbar_wait(&bfull_bar[bs], bphase));
             tc_fence_after();
             const uint32_t b_lo0 = lbo_lo | (smem_u32(sB + bs * Cfg::B_STAGE_BYTES) >> 4);
             // TPS = 1: tap g;  TPS = 3: taps 3g .. 3g+2 (one filter row);  TPS = 9: all taps
@@ -391,6 +246,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
                 accumulate = 1u;
               }
             }
+            if (b_resident) continue;
             umma_commit(&bempty_bar[bs]);  // frees the weight stage when its MMAs retire
             if (++bs == Cfg::B_STAGES) {
               bs = 0;
@@ -428,6 +284,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         tphase ^= 1u;
       }
     }
+    if (dbg) {
+      p.dbg[8] = wacc0;
+      p.dbg[9] = wacc1;
+      p.dbg[10] = wacc2;
+    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -455,7 +316,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
       }
       if constexpr (MODE == CONV_DGRAD) dgrad_aux_load(p, aux_cur, h, w, n0 + col0, valid);
-      mbar_wait(&tfull_bar[ts], tphase);
+      NST_WAIT(wacc0, mbar_wait(&tfull_bar[ts], tphase));
       tc_fence_after();
       NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
       const uint32_t taddr =
@@ -513,6 +374,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     }
   }
 
+  if (dbg && threadIdx.x == 128) p.dbg[11] = wacc0;
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -520,7 +382,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   NST_STAMP(6, threadIdx.x == 64);
+  if (p.tl != nullptr && threadIdx.x == 64) atomicMax(&p.tl[1], globaltimer_ns());
 #undef NST_STAMP
+#undef NST_WAIT
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -52,6 +52,9 @@ struct ConvParams {
   float inv_std[3];       // d normalize / d x
   // ---- phase timestamps of CTA 0 (debug; nullptr in production): see tools/conv_phases.py
   long long* dbg;
+  // ---- launch span inside a captured step (debug; nullptr in production): tl[0] = earliest CTA start, tl[1] = latest CTA
+  // end, both %globaltimer ns (atomicMin / atomicMax by every CTA): tools/conv_timeline.py
+  unsigned long long* tl;
 };
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)

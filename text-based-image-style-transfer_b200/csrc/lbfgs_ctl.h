@@ -67,6 +67,9 @@ struct NstLbfgsCtl {
   double gtd, max_td, gmax, gl1, ys, yy;
   // ---- output of the recursion: d = sum_k coef[k] * basis_k  (S slots, Y slots, g)
   float coef[NST_LBFGS_NB + 3];
+  // ---- SM clock at the controller's phase boundaries (device only; tuning aid, tools/ctl_phases.py):
+  //  0 entry  1 matrices staged  2 pair accepted / rows initialised  3 loop 1 done  4 y.r initialised  5 loop 2 done  6 exit
+  long long clk[8];
 };
 
 // scalars produced by pass 1 (index into `scal`):  0 s.s  1 s.y  2 y.y  3 s.g  4 y.g  5 g.g  6 max|g|  7 sum|g|
@@ -88,6 +91,7 @@ struct NstCtlWork {
 #define NST_CTL_WORK_DOUBLES (2 * NST_CTL_MAT_DOUBLES + 6 * NST_LBFGS_SLOTS + 4)
 
 #if defined(__CUDA_ARCH__)
+#define NST_CLK(k) do { if (NST_TID == 0) c->clk[k] = clock64(); } while (0)
 #define NST_HD __device__
 #define NST_TID (static_cast<int>(threadIdx.x))
 #define NST_NT (static_cast<int>(blockDim.x))
@@ -105,6 +109,7 @@ __device__ __forceinline__ double nst_ctl_max(double v) {
   return v;
 }
 #else
+#define NST_CLK(k) ((void)0)
 #define NST_HD
 #define NST_TID 0
 #define NST_NT 1
@@ -175,6 +180,7 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
   }
   if (stop != NST_RUN) return;
 
+  NST_CLK(1);
   // ---- new iteration (lbfgs.py:388-442)
   for (int k = tid; k < NST_LBFGS_NB; k += nt) c->coef[k] = 0.f;
   NST_BLOCK_SYNC();
@@ -226,35 +232,52 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
       w.c[p] = -w.Sg[p];  // running value of s_i . q
     }
     NST_BLOCK_SYNC();
+    NST_CLK(2);
     // lbfgs.py:432-435: for k newest..oldest: al_k = ro_k (s_k . q); q -= al_k y_k.  Column oriented: once al_k is
     // known every older row i subtracts al_k (s_i . y_k) from its running s_i . q - no reduction on the dependent chain.
 #if defined(__CUDA_ARCH__)
-    // device: lane l keeps the running values of rows l, l+32, l+64, l+96 in registers; al_k is broadcast from its
-    // owner with one 64-bit shuffle, so a step costs a shuffle + a multiply instead of a shared-memory round trip
-    if (tid < 32) {
-      double run[4], rok[4];
+    // Device: blocked back-substitution.  The recurrence is a triangular solve; 32 pairs at a time, warp 0 runs the
+    // dependent chain with everything in registers (lane l owns one row, its 32 matrix entries of the diagonal block
+    // are preloaded, al_k travels by one 64-bit shuffle: a step is shuffle + multiply-add), then the whole block applies
+    // the 32 new al_k to all older rows in parallel.  Same arithmetic as the loop below up to the fp64 summation order.
+    for (int hi = len; hi > 0; hi -= 32) {
+      const int lo = hi > 32 ? hi - 32 : 0, nb = hi - lo;
+      if (tid < 32) {
+        const bool own = tid < nb;
+        const int pa = nst_ctl_slot(head, own ? lo + tid : lo);
+        double run = own ? w.c[pa] : 0.0;
+        const double rok = own ? w.ro[pa] : 0.0;
+        double rr[32];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = tid + 32 * r;
-        const int p = nst_ctl_slot(head, i < len ? i : 0);
-        run[r] = i < len ? w.c[p] : 0.0;
-        rok[r] = i < len ? w.ro[p] : 0.0;
-      }
+        for (int j = 0; j < 32; ++j) rr[j] = (own && j < nb) ? w.R[pa * TOT + nst_ctl_slot(head, lo + (j < nb ? j : 0))] : 0.0;
+        double mine = 0.0;
 #pragma unroll
-      for (int rb = 3; rb >= 0; --rb) {
         for (int kk = 31; kk >= 0; --kk) {
-          const int k = rb * 32 + kk;
-          if (k >= len) continue;
-          const int pk = nst_ctl_slot(head, k);
-          const double al = __shfl_sync(0xffffffffu, rok[rb] * run[rb], kk);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int i = tid + 32 * r;
-            if (r <= rb && i < k) run[r] -= al * w.R[nst_ctl_slot(head, i) * TOT + pk];
+          if (kk < nb) {
+            const double al = __shfl_sync(0xffffffffu, rok * run, kk);
+            if (tid < kk) run -= al * rr[kk];
+            if (tid == kk) mine = al;
           }
-          if (tid == kk) w.al[pk] = al;
         }
+        if (own) w.al[pa] = mine;
       }
+      NST_BLOCK_SYNC();
+      // rows older than the block: c_i -= sum_k al_k (s_i . y_k); four threads per row, eight columns each
+      {
+        const int row = tid >> 2, part = tid & 3;
+        double acc = 0.0;
+        const int pi = nst_ctl_slot(head, row < lo ? row : 0);
+        if (row < lo) {
+          for (int j = part; j < nb; j += 4) {
+            const int pk = nst_ctl_slot(head, lo + j);
+            acc += w.al[pk] * w.R[pi * TOT + pk];
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (row < lo && part == 0) w.c[pi] -= acc;
+      }
+      NST_BLOCK_SYNC();
     }
 #else
     if (tid < NST_CTL_NL) {
@@ -271,6 +294,7 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     }
 #endif
     NST_BLOCK_SYNC();
+    NST_CLK(3);
     // y_i . r at the start of loop 2: H (y_i . q) = H (-(y_i . g) - sum_j al_j (y_i . y_j))          [block parallel]
     for (int i = tid; i < len; i += nt) {
       const int p = nst_ctl_slot(head, i);
@@ -282,34 +306,49 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
       w.yq[p] = H_diag * (-w.Yg[p] - acc);
     }
     NST_BLOCK_SYNC();
+    NST_CLK(4);
     // lbfgs.py:439-442: r = H q; for k oldest..newest: be_k = ro_k (y_k . r); r += (al_k - be_k) s_k.  Once c_k is known
     // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
 #if defined(__CUDA_ARCH__)
-    if (tid < 32) {
-      double run[4], rok[4], alk[4];
+    // device: the same blocking, forward
+    for (int lo = 0; lo < len; lo += 32) {
+      const int hi = lo + 32 < len ? lo + 32 : len, nb = hi - lo;
+      if (tid < 32) {
+        const bool own = tid < nb;
+        const int pa = nst_ctl_slot(head, own ? lo + tid : lo);
+        double run = own ? w.yq[pa] : 0.0;
+        const double rok = own ? w.ro[pa] : 0.0, alk = own ? w.al[pa] : 0.0;
+        double rr[32];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = tid + 32 * r;
-        const int p = nst_ctl_slot(head, i < len ? i : 0);
-        run[r] = i < len ? w.yq[p] : 0.0;
-        rok[r] = i < len ? w.ro[p] : 0.0;
-        alk[r] = i < len ? w.al[p] : 0.0;
-      }
+        for (int j = 0; j < 32; ++j) rr[j] = (own && j < nb) ? w.R[nst_ctl_slot(head, lo + (j < nb ? j : 0)) * TOT + pa] : 0.0;
+        double mine = 0.0;
 #pragma unroll
-      for (int rb = 0; rb < 4; ++rb) {
         for (int kk = 0; kk < 32; ++kk) {
-          const int k = rb * 32 + kk;
-          if (k >= len) break;
-          const int pk = nst_ctl_slot(head, k);
-          const double ck = __shfl_sync(0xffffffffu, alk[rb] - rok[rb] * run[rb], kk);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int i = tid + 32 * r;
-            if (r >= rb && i > k && i < len) run[r] += ck * w.R[pk * TOT + nst_ctl_slot(head, i)];
+          if (kk < nb) {
+            const double ck = __shfl_sync(0xffffffffu, alk - rok * run, kk);
+            if (tid > kk) run += ck * rr[kk];
+            if (tid == kk) mine = ck;
           }
-          if (tid == kk) w.c[pk] = ck;
         }
+        if (own) w.c[pa] = mine;
       }
+      NST_BLOCK_SYNC();
+      // rows younger than the block: (y_i . r) += sum_k c_k (s_k . y_i)
+      {
+        const int row = hi + (tid >> 2), part = tid & 3;
+        double acc = 0.0;
+        const int pi = nst_ctl_slot(head, row < len ? row : 0);
+        if (row < len) {
+          for (int j = part; j < nb; j += 4) {
+            const int pk = nst_ctl_slot(head, lo + j);
+            acc += w.c[pk] * w.R[pk * TOT + pi];
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (row < len && part == 0) w.yq[pi] += acc;
+      }
+      NST_BLOCK_SYNC();
     }
 #else
     if (tid < NST_CTL_NL) {
@@ -326,6 +365,7 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     }
 #endif
     NST_BLOCK_SYNC();
+    NST_CLK(5);
     for (int i = tid; i < len; i += nt) {
       const int p = nst_ctl_slot(head, i);
       c->coef[p] = static_cast<float>(w.c[p]);
@@ -361,4 +401,5 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     }
   }
   NST_BLOCK_SYNC();
+  NST_CLK(6);
 }
