@@ -185,8 +185,8 @@ int nst_plan_eval_timed(nst_plan* plan, const float* x, float* grad, nst_launch_
 int nst_lbfgs_step_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
 
 /* phase timestamps (SM clock) of CTA 0 of one convolution launch (mode 0 forward, 1 data gradient; conv 0 = conv1_1's
-   data gradient) -> out[0..6], and the SM cycles its roles spent waiting -> out[8..13] (slots: csrc/conv_tc.cu); out holds
-   14 values: tuning aid, see tools/conv_phases.py */
+   data gradient) -> out[0..6], the SM cycles its roles spent waiting -> out[8..13] (slots: csrc/conv_tc.cu) and the
+   lifetime in SM cycles of every CTA -> out[16 + cta]; out holds 176 values: tuning aid, see tools/conv_phases.py */
 int nst_plan_conv_phases(nst_plan* plan, int conv, int mode, long long* out14, void* stream);
 /* launch spans {earliest CTA start, latest CTA end} (%globaltimer ns) of the convolution launches inside the captured
    step: slot = conv (forward), 16 + conv (data gradient), 32 + conv (Gram backward); enable re-captures the step with

@@ -1235,16 +1235,19 @@ extern "C" int nst_plan_conv_phases(nst_plan* p, int conv, int mode, long long* 
   if (mode == 1 && !p->with_grad) return fail(NST_ERR_STATE, "plan has no gradient buffers");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long* d = nullptr;
-  CK(cudaMalloc(&d, 16 * sizeof(long long)));
-  cudaError_t e = cudaMemsetAsync(d, 0, 16 * sizeof(long long), s);
+  CK(cudaMalloc(&d, (16 + 160) * sizeof(long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, (16 + 160) * sizeof(long long), s);
   ConvParams c = mode == 0 ? p->fwd[conv] : p->dgrad[conv];
   c.dbg = d;
+  c.tl = reinterpret_cast<unsigned long long*>(d + 14);  // out[14], out[15]: launch span in %globaltimer ns
+  const unsigned long long tl_init[2] = {~0ull, 0ull};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 14, tl_init, sizeof(tl_init), cudaMemcpyHostToDevice, s);
   if (mode == 1 && conv == 0) {
     c.out_pix = p->lb.g != nullptr ? p->lb.g : p->grad_pix;
     for (int k = 0; k < 3; ++k) c.inv_std[k] = 1.f / p->pc.stdv[k];
   }
   if (e == cudaSuccess) e = launch_conv_tc(c, mode == 0 ? CONV_FWD : (conv == 0 ? CONV_DGRAD_PIX : CONV_DGRAD), g_num_sms, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, 14 * sizeof(long long), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, (16 + 160) * sizeof(long long), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(d);
   if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_plan_conv_phases: %s", cudaGetErrorString(e));

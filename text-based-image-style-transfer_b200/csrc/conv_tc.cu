@@ -45,7 +45,8 @@ struct ConvCfg {
   // scattered 16-byte stores) and one warp per scheduler cannot hide it.
   static constexpr int EPI_WARPS = BLOCK_N >= 64 ? 8 : 4;
   static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
-  // a patch feeds 36 MMAs; with narrow N those take less time than a TMA round trip, so more patches must be in flight
+  // Patches in flight: two.  Deeper rings (5 at N = 64, 8 at N = 16) were measured inside the captured step and made the
+  // 64-channel data gradients slower (conv1_2: 39 -> 58 us), not faster: the operand stream is not what bounds them.
   static constexpr int HALO_STAGES = 2;
   // Filter taps per weight stage.  One pipeline iteration (barrier wait, fence, commit) costs a few hundred cycles of
   // the issuing thread and every tcgen05.mma about 45 (profiles/r01_mma_issue_rate.log); with one tap (4 MMAs) per
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  const long long life0 = p.dbg != nullptr ? clock64() : 0;
 #define NST_STAMP(slot, cond)                                        \
   do {                                                               \
     if (dbg && (cond)) p.dbg[slot] = clock64();                      \
@@ -302,20 +304,61 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     uint32_t tphase = 0;
     float alpha = 0.f;
     if (MODE == CONV_SCALE) alpha = __ldg(p.alpha);
+    // Data-gradient epilogue operands (ReLU mask + tap seed, or pool routing bytes; for conv1_1 the pixel-term gradient)
+    // do not depend on the accumulator.  All chunks of a tile are requested together when they fit in registers
+    // (<= 4 chunks), and for narrow tiles (<= 2 chunks, and conv1_1) the NEXT tile's operands are requested before the
+    // current tile is processed: with ~1 us of tensor work per tile a global-memory latency per tile (cold: inside the
+    // step these operands were written by earlier launches, they are not L2-warm as in a re-run) is the whole epilogue.
+    constexpr int DG_CHUNKS = COLS / DG_CH;
+    constexpr int DG_PRE = DG_CHUNKS <= 4 ? DG_CHUNKS : 1;
+    constexpr bool XT = MODE == CONV_DGRAD_PIX || (MODE == CONV_DGRAD && DG_PRE == DG_CHUNKS && DG_PRE <= 2);
+    DgradAux aux[DG_PRE];
+    DgradAux aux_x[XT ? DG_PRE : 1];
+    DgradAux aux_nxt;
+    float gp[3] = {0.f, 0.f, 0.f}, gp_x[3] = {0.f, 0.f, 0.f};
+    auto coords = [&](int tile_, int& h_, int& w_, int& n0_, bool& valid_) {
+      const int nt_ = tile_ / sp_tiles;
+      const int sp_ = tile_ - nt_ * sp_tiles;
+      const int th_ = sp_ / p.tiles_w;
+      const int tw_ = sp_ - th_ * p.tiles_w;
+      h_ = th_ * TILE_H + hl;
+      w_ = tw_ * TILE_W + wl;
+      n0_ = nt_ * BLOCK_N;
+      valid_ = h_ < p.H && w_ < p.W;
+    };
+    auto request = [&](int tile_, DgradAux* a_, float* g_) {
+      int h_, w_, n0_;
+      bool valid_;
+      coords(tile_, h_, w_, n0_, valid_);
+      if constexpr (MODE == CONV_DGRAD) {
+#pragma unroll
+        for (int c = 0; c < DG_PRE; ++c) dgrad_aux_load(p, a_[c], h_, w_, n0_ + col0 + c * DG_CH, valid_);
+      }
+      if constexpr (MODE == CONV_DGRAD_PIX) {
+        if (valid_ && p.grad_pix != nullptr) {
+          const size_t HW_ = static_cast<size_t>(p.H) * p.W;
+          const size_t o_ = static_cast<size_t>(h_) * p.W + w_;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) g_[c] = __ldg(p.grad_pix + c * HW_ + o_);
+        }
+      }
+    };
+    if constexpr (XT) {
+      if (static_cast<int>(blockIdx.x) < p.num_tiles) request(blockIdx.x, aux, gp);
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile / sp_tiles;
-      const int sp = tile - nt * sp_tiles;
-      const int th = sp / p.tiles_w;
-      const int tw = sp - th * p.tiles_w;
-      const int h = th * TILE_H + hl, w = tw * TILE_W + wl, n0 = nt * BLOCK_N;
-      const bool valid = h < p.H && w < p.W;
-      // everything that does not depend on the accumulator is fetched while the main loop still runs
-      DgradAux aux_cur, aux_nxt;
+      int h, w, n0;
+      bool valid;
+      coords(tile, h, w, n0, valid);
       if constexpr (MODE == CONV_FWD) {
         for (int j = et; j < BLOCK_N; j += Cfg::EPI_WARPS * 32) sbias[ts * BLOCK_N + j] = __ldg(p.bias + n0 + j);
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
       }
-      if constexpr (MODE == CONV_DGRAD) dgrad_aux_load(p, aux_cur, h, w, n0 + col0, valid);
+      if constexpr (XT) {
+        if (tile + static_cast<int>(gridDim.x) < p.num_tiles) request(tile + gridDim.x, aux_x, gp_x);
+      } else if constexpr (MODE == CONV_DGRAD) {
+        request(tile, aux, gp);
+      }
       NST_WAIT(wacc0, mbar_wait(&tfull_bar[ts], tphase));
       tc_fence_after();
       NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
@@ -331,23 +374,35 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           const size_t o = static_cast<size_t>(h) * p.W + w;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            float g = __uint_as_float(r[c]) * p.inv_std[c];
-            if (p.grad_pix != nullptr) g += p.grad_pix[c * HW + o];
+            const float g = __uint_as_float(r[c]) * p.inv_std[c] + gp[c];  // gp stays 0 without pixel terms
             p.out_pix[c * HW + o] = g;
           }
         }
       } else if constexpr (MODE == CONV_DGRAD) {
-#pragma unroll 1
-        for (int c = 0; c < COLS / DG_CH; ++c) {
-          if (c + 1 < COLS / DG_CH) dgrad_aux_load(p, aux_nxt, h, w, n0 + col0 + (c + 1) * DG_CH, valid);
-          uint32_t r[DG_CH];
-          tmem_ld16(taddr + c * DG_CH, r);
-          tmem_ld_wait();
-          float v[DG_CH];
+        if constexpr (DG_PRE == DG_CHUNKS) {
 #pragma unroll
-          for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux_cur);
-          aux_cur = aux_nxt;
+          for (int c = 0; c < DG_CHUNKS; ++c) {
+            uint32_t r[DG_CH];
+            tmem_ld16(taddr + c * DG_CH, r);
+            tmem_ld_wait();
+            float v[DG_CH];
+#pragma unroll
+            for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[c]);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < DG_CHUNKS; ++c) {
+            if (c + 1 < DG_CHUNKS) dgrad_aux_load(p, aux_nxt, h, w, n0 + col0 + (c + 1) * DG_CH, valid);
+            uint32_t r[DG_CH];
+            tmem_ld16(taddr + c * DG_CH, r);
+            tmem_ld_wait();
+            float v[DG_CH];
+#pragma unroll
+            for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[0]);
+            aux[0] = aux_nxt;
+          }
         }
       } else {
 #pragma unroll 1
@@ -362,6 +417,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + col0 + c * 32);
           if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
         }
+      }
+      if constexpr (XT) {
+#pragma unroll
+        for (int c = 0; c < DG_PRE; ++c) aux[c] = aux_x[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gp[c] = gp_x[c];
       }
       tc_fence_before();
       __syncwarp();
@@ -382,6 +443,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   NST_STAMP(6, threadIdx.x == 64);
+  if (p.dbg != nullptr && threadIdx.x == 64) p.dbg[16 + blockIdx.x] = clock64() - life0;  // lifetime of every CTA
   if (p.tl != nullptr && threadIdx.x == 64) atomicMax(&p.tl[1], globaltimer_ns());
 #undef NST_STAMP
 #undef NST_WAIT

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, __half* __restrict__ out_tap,
                                                         __half* __restrict__ out_act, int H, int W, PixelConsts pc) {
   __shared__ float in[3][C1_TH + 2][C1_TW + 2];
-  __shared__ __align__(16) float ws[27][64];  // [c*9 + r*3 + s][n]
+  // [c*9 + r*3 + s][n]; rows padded to 68 floats: the transposing stores below would otherwise all hit one bank
+  __shared__ __align__(16) float ws[27][68];
   const int tiles_w = (W + C1_TW - 1) / C1_TW;
   const int w0 = (blockIdx.x % tiles_w) * C1_TW, h0 = (blockIdx.x / tiles_w) * C1_TH;
   const size_t HW = static_cast<size_t>(H) * W;
@@ -210,14 +211,17 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   __syncthreads();
   const int j = threadIdx.x & 7;    // channel group: channels 8j .. 8j+7
   const int px = threadIdx.x >> 3;  // pixel column inside the tile
-  float acc[C1_TH][8];
+  // packed fp32 (fma.rn.f32x2, sm_100): two channels per instruction, bit-identical to two fmaf
+  float2 acc[C1_TH][4];
   {
     const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * j);
     const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * j + 4);
 #pragma unroll
     for (int i = 0; i < C1_TH; ++i) {
-      acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
-      acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
+      acc[i][0] = make_float2(b0.x, b0.y);
+      acc[i][1] = make_float2(b0.z, b0.w);
+      acc[i][2] = make_float2(b1.x, b1.y);
+      acc[i][3] = make_float2(b1.z, b1.w);
     }
   }
 #pragma unroll
@@ -231,17 +235,15 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       for (int r = 0; r < 3; ++r) {
         const float4 wa = *reinterpret_cast<const float4*>(&ws[c * 9 + r * 3 + s][8 * j]);
         const float4 wb = *reinterpret_cast<const float4*>(&ws[c * 9 + r * 3 + s][8 * j + 4]);
+        const float2 q0 = make_float2(wa.x, wa.y), q1 = make_float2(wa.z, wa.w);
+        const float2 q2 = make_float2(wb.x, wb.y), q3 = make_float2(wb.z, wb.w);
 #pragma unroll
         for (int i = 0; i < C1_TH; ++i) {
-          const float v = col[i + r];
-          acc[i][0] = fmaf(v, wa.x, acc[i][0]);
-          acc[i][1] = fmaf(v, wa.y, acc[i][1]);
-          acc[i][2] = fmaf(v, wa.z, acc[i][2]);
-          acc[i][3] = fmaf(v, wa.w, acc[i][3]);
-          acc[i][4] = fmaf(v, wb.x, acc[i][4]);
-          acc[i][5] = fmaf(v, wb.y, acc[i][5]);
-          acc[i][6] = fmaf(v, wb.z, acc[i][6]);
-          acc[i][7] = fmaf(v, wb.w, acc[i][7]);
+          const float2 v = make_float2(col[i + r], col[i + r]);
+          acc[i][0] = __ffma2_rn(v, q0, acc[i][0]);
+          acc[i][1] = __ffma2_rn(v, q1, acc[i][1]);
+          acc[i][2] = __ffma2_rn(v, q2, acc[i][2]);
+          acc[i][3] = __ffma2_rn(v, q3, acc[i][3]);
         }
       }
     }
@@ -255,17 +257,17 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     const size_t o = (static_cast<size_t>(h) * W + w) * 64 + 8 * j;
     uint4 u;
     if (out_tap != nullptr) {
-      u.x = pack_half2(acc[i][0], acc[i][1]);
-      u.y = pack_half2(acc[i][2], acc[i][3]);
-      u.z = pack_half2(acc[i][4], acc[i][5]);
-      u.w = pack_half2(acc[i][6], acc[i][7]);
+      u.x = pack_half2(acc[i][0].x, acc[i][0].y);
+      u.y = pack_half2(acc[i][1].x, acc[i][1].y);
+      u.z = pack_half2(acc[i][2].x, acc[i][2].y);
+      u.w = pack_half2(acc[i][3].x, acc[i][3].y);
       *reinterpret_cast<uint4*>(out_tap + o) = u;
     }
     if (out_act != nullptr) {
-      u.x = pack_half2(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f));
-      u.y = pack_half2(fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
-      u.z = pack_half2(fmaxf(acc[i][4], 0.f), fmaxf(acc[i][5], 0.f));
-      u.w = pack_half2(fmaxf(acc[i][6], 0.f), fmaxf(acc[i][7], 0.f));
+      u.x = pack_half2(fmaxf(acc[i][0].x, 0.f), fmaxf(acc[i][0].y, 0.f));
+      u.y = pack_half2(fmaxf(acc[i][1].x, 0.f), fmaxf(acc[i][1].y, 0.f));
+      u.z = pack_half2(fmaxf(acc[i][2].x, 0.f), fmaxf(acc[i][2].y, 0.f));
+      u.w = pack_half2(fmaxf(acc[i][3].x, 0.f), fmaxf(acc[i][3].y, 0.f));
       *reinterpret_cast<uint4*>(out_act + o) = u;
     }
   }

@@ -22,15 +22,22 @@ c = img(0)
 sess.prepare(c)
 sess.run(20)
 lib = nst_b200._lib.load()
-buf = (C.c_longlong * 16)()
+buf = (C.c_longlong * 176)()
 names = ["setup", "first operands", "main loop (issue)", "drain -> acc ready", "epilogue", "teardown"]
 print("%-10s %s  total | waits of CTA 0 (us): MMA patch / weights / acc stage, epilogue acc, producer patch / weight stage" % ("launch", "  ".join("%18s" % n for n in names)))
 with torch.cuda.stream(sess.stream):
     for mode, tag in ((0, "fwd"), (1, "dgrad")):
         for conv in range(0 if mode == 1 else 1, 13):
             for rep in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(sess.stream)
                 nst_b200._lib.check(lib.nst_plan_conv_phases(sess.plan.handle, conv, mode, buf, C.c_void_p(sess.stream.cuda_stream)))
+                e1.record(sess.stream)
+                e1.synchronize()
+                wall = e0.elapsed_time(e1) * 1e3
             t = list(buf)[:7]
             d = [(t[i + 1] - t[i]) / 1.965e3 for i in range(6)]
             w = [x / 1.965e3 for x in list(buf)[8:14]]
-            print("%-10s %s  %6.1f us | %5.1f %5.1f %5.1f  %5.1f  %5.1f %5.1f" % ("%s %d" % (tag, conv), "  ".join("%15.1f us" % v for v in d), (t[6] - t[0]) / 1.965e3, *w))
+            life = [x / 1.965e3 for x in list(buf)[16:176] if x > 0]
+            print("%-10s %s  %6.1f us | %5.1f %5.1f %5.1f  %5.1f  %5.1f %5.1f | CTA lifetimes: %d CTAs min %.1f mean %.1f max %.1f us | first CTA start -> last CTA end (globaltimer) %.1f us" % (
+                "%s %d" % (tag, conv), "  ".join("%15.1f us" % v for v in d), (t[6] - t[0]) / 1.965e3, *w, len(life), min(life), sum(life) / len(life), max(life), (list(buf)[15] - list(buf)[14]) / 1e3))
