@@ -206,6 +206,10 @@ struct nst_plan {
   int chain_layers[2] = {}, chain_items[2] = {};
   int* chain_done = nullptr;
   size_t chain_done_bytes = 0;
+  // the Gram-backward (1x1) layers of the shallower style layers as ONE launch of the chained kernel (no dependencies
+  // between them): five ~12 us launches of 2 GFLOP each were launch- and latency-bound
+  ChainLayer* seeds_dev = nullptr;
+  int seeds_layers = 0, seeds_items = 0;
   unsigned long long* timeline = nullptr;  // [48][2] launch spans of the conv kernels (debug, nst_plan_timeline)
   bool timeline_on = false;
 };
@@ -368,6 +372,42 @@ static int build_gram_params(nst_plan* p) {
                                       static_cast<float>(L.C) * static_cast<float>(L.C) * static_cast<float>(L.HW));
     if (make_tmap_feat(&g.tm[k], p->tap[i], L.HW, L.C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
   }
+  return NST_OK;
+}
+
+// Work list of the shallow Gram-backward launch: every style layer except one on the deepest conv (that one is on the
+// critical path and runs on the main stream).
+static int build_seed_chain(nst_plan* p) {
+  if (!p->with_grad) return NST_OK;
+  const int last = p->n_layers - 1;
+  std::vector<ChainLayer> list;
+  size_t n_done = 0;
+  std::vector<size_t> off;
+  for (int l = p->n_style - 1; l >= 0; --l) {
+    const int i = p->style_conv[l];
+    if (i == last) continue;
+    ChainLayer L;
+    memset(&L, 0, sizeof(L));
+    L.c = p->scale[i];
+    const int C = kCout[i];
+    L.c.block_n = chain_block_n(C);
+    if (make_tmap_wgt(&L.c.tmB, p->dh[l], 1, C, C, L.c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, chained)", i);
+    conv_finalize_params(L.c, CONV_SCALE);
+    L.mode = CONV_SCALE;
+    L.dep_layer[0] = L.dep_layer[1] = -1;
+    L.item_base = list.empty() ? 0 : list.back().item_base + list.back().c.num_tiles;
+    off.push_back(n_done);
+    n_done += static_cast<size_t>(L.c.tiles_h) * L.c.tiles_w;
+    list.push_back(L);
+  }
+  if (list.empty()) return NST_OK;
+  int* done = nullptr;
+  CKI(plan_alloc_t(p, &done, n_done, true));
+  for (size_t k = 0; k < list.size(); ++k) list[k].done = done + off[k];
+  CKI(plan_alloc_t(p, &p->seeds_dev, list.size()));
+  CK(cudaMemcpy(p->seeds_dev, list.data(), list.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
+  p->seeds_layers = static_cast<int>(list.size());
+  p->seeds_items = list.back().item_base + list.back().c.num_tiles;
   return NST_OK;
 }
 
@@ -558,7 +598,9 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     }
   }
   {
-    cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    cudaError_t e = cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_least);
     for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
       nst_plan_destroy(p);
@@ -603,6 +645,7 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
   }
   PA(build_conv_params(p));
   PA(build_chains(p));
+  PA(build_seed_chain(p));
 #undef PA
   *out = p;
   return NST_OK;
@@ -1070,18 +1113,30 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       TM(NST_K_CONTENT, last);
     }
   }
-  // ---- side: Gram-backward seeds of the shallower style layers (deepest first: needed first)
+  // ---- side: Gram-backward seeds of the shallower style layers
   if (grad != nullptr && use_vgg) {
-    for (int l = n_shallow - 1; l >= 0; --l) {
-      const int i = p->style_conv[l];
-      CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
+    // opt-in: measured inside the step, the single persistent launch holds all SMs for ~25 us and delays the critical
+    // path (deepest Gram -> first data gradient) more than five short launches do
+    static const bool one_launch = getenv("NST_SEEDS_ONE_LAUNCH") != nullptr;
+    bool accumulate_after = false;
+    for (int l = 0; l < n_shallow; ++l) accumulate_after = accumulate_after || content_index(p, p->style_conv[l]) >= 0;
+    if (one_launch && tm == nullptr && p->seeds_layers > 0 && !accumulate_after) {
+      CK(launch_conv_chain(p->seeds_dev, p->seeds_layers, p->seeds_items, g_num_sms, s2));
       ++nl;
-      TM(NST_K_GRAM_BWD, i);
-      const int cl = content_index(p, i);
-      if (cl >= 0) {
-        CK(content_launch(cl, 1, s2));
+    } else {
+      // shallowest (largest, bandwidth-bound) first: it then overlaps the latency-bound Gram chain of the deepest layer on
+      // the main stream instead of the first data gradients; all seeds are awaited together before conv4_2's data gradient
+      for (int l = 0; l < n_shallow; ++l) {
+        const int i = p->style_conv[l];
+        CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
         ++nl;
-        TM(NST_K_CONTENT, i);
+        TM(NST_K_GRAM_BWD, i);
+        const int cl = content_index(p, i);
+        if (cl >= 0) {
+          CK(content_launch(cl, 1, s2));
+          ++nl;
+          TM(NST_K_CONTENT, i);
+        }
       }
     }
     if (conc) CK(cudaEventRecord(p->ev[EV_SEEDS], s2));

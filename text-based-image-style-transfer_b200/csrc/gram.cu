@@ -8,6 +8,7 @@
 // TMA box).  Split-K partial tiles go to a workspace; two small kernels reduce them in a fixed order
 // (deterministic), form G - T, the per-layer MSE and the scaled fp16 operand of the backward GEMM.
 #include "gram.cuh"
+#include <stdlib.h>
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
@@ -90,6 +91,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: everything above touched only on-chip state; the taps come from the previous launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -230,6 +234,8 @@ __global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize1_kernel(const 
   __shared__ float s_part[GRAM_FIN_THREADS];
   const int l = gram_find_layer_by_finblk(p, blockIdx.x);
   const GramLayer& L = p.L[l];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   FinElem e = gram_fin_elem(p, L, blockIdx.x - L.fin_blk0, s_part);
   float sq = 0.f, mx = 0.f;
   if (e.ok) {
@@ -254,6 +260,8 @@ __global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize2_kernel(const 
   __shared__ float s_bcast[2];
   const int l = gram_find_layer_by_finblk(p, blockIdx.x);
   const GramLayer& L = p.L[l];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (L.target == nullptr) return;
   float sq = 0.f, mx = 0.f;
   for (int b = threadIdx.x; b < L.fin_blocks; b += GRAM_FIN_THREADS) {
@@ -350,15 +358,31 @@ cudaError_t gram_init() {
   return cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
 }
 
+// The three launches are chained with programmatic dependent launch: each kernel's blocks are scheduled while the previous
+// kernel drains and block in griddepcontrol.wait until it has completed, which takes the launch latency of two tiny
+// kernels off the critical path between the deepest forward convolution and the first data gradient.
+template <typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(Args...), int grid, int block, size_t smem, cudaStream_t stream, const GramParams& p) {
+  static const bool pdl = getenv("NST_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 cudaError_t launch_gram(const GramParams& p, cudaStream_t stream) {
-  gram_partial_kernel<<<p.num_items, G_THREADS, G_SMEM_BYTES, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(gram_partial_kernel, p.num_items, G_THREADS, G_SMEM_BYTES, stream, p);
   if (e != cudaSuccess) return e;
-  gram_finalize1_kernel<<<p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream>>>(p);
-  e = cudaGetLastError();
+  e = launch_pdl(gram_finalize1_kernel, p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream, p);
   if (e != cudaSuccess) return e;
-  gram_finalize2_kernel<<<p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(gram_finalize2_kernel, p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream, p);
 }
 
 }  // namespace nst

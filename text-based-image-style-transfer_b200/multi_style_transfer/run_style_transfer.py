@@ -69,7 +69,9 @@ class StyleTransferSession:
         self.style_layers = list(style_layers)
         self.weights = (float(w_style), float(w_content), float(w_tv), float(w_edge))
         self.net = get_net(self.device)
-        self.stream = torch.cuda.Stream(self.device)
+        # high priority: the library's side stream (pixel terms, shallow Gram work) is created with the lowest priority, so
+        # that when an SM frees up the block scheduler gives it to the critical path (conv chain, optimizer) first
+        self.stream = torch.cuda.Stream(self.device, priority=-1)
         H, W = int(content_hw[0]), int(content_hw[1])
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.plan = Plan(self.net, H, W, self.content_layers + self.style_layers, self.style_layers,
