@@ -272,35 +272,39 @@ def run_b200(args, rank, world, local_rank):
     enqueue_evals(120)                                            # history full (m = 100): steady state of a 320-evaluation run
     stream.synchronize()
     with torch.cuda.stream(stream):
-        raw = plan.lbfgs_step_timed() + plan.lbfgs_step_timed()
+        raw = plan.lbfgs_step_timed(grouped=True) + plan.lbfgs_step_timed(grouped=True)
     m_now = sess.status().hist_len
+    # grouped rows: (kind, launches in the run, ms of the run) - one CUDA event wherever the kind of launch changes, so
+    # the twelve forward convolutions (or the twelve data gradients) are timed as one run with programmatic dependent
+    # launch between them intact, exactly as they execute inside the captured step
     acc = {}
-    for k, l, ms_ in raw:
-        a = acc.setdefault((k, l), [0.0, 0])
+    for k, nl_, ms_ in raw:
+        a = acc.setdefault(k, [0.0, 0, 0])
         a[0] += ms_
-        a[1] += 1
-    rows = [(k, l, v[0] / v[1]) for (k, l), v in acc.items()]         # mean ms per launch of each (kind, conv)
-    n_evals_timed = acc[("pixel", -1)][1]
-    per_eval = lambda kinds: sum(v[0] for (k, l), v in acc.items() if k in kinds) / n_evals_timed  # noqa: E731
+        a[1] += nl_
+        a[2] += 1
+    n_evals_timed = acc["pixel"][2]
+    per_eval = lambda kinds: sum(v[0] for k, v in acc.items() if k in kinds) / n_evals_timed  # noqa: E731
     conv_kinds = ("conv_fwd", "conv_dgrad", "gram_bwd")
     conv_ms = per_eval(conv_kinds)
-    conv_launches = sum(1 for (k, l) in acc if k in conv_kinds)
+    conv_launches = sum(v[1] for k, v in acc.items() if k in conv_kinds) / n_evals_timed
     conv_fl = 2.0 * sum(synth.conv_flops(i, S, S) for i in range(1, 13)) + sum(synth.gram_flops(i, S, S) for i in synth._STYLE)
     lb_kinds = ("lbfgs_pass1", "lbfgs_reduce", "lbfgs_control", "lbfgs_pass2")
-    eval_ms = sum(v[0] for (k, l), v in acc.items() if k not in lb_kinds) / n_evals_timed
+    eval_ms = sum(v[0] for k, v in acc.items() if k not in lb_kinds) / n_evals_timed
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient + 5 Gram-backward launches per evaluation)",
                     achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
                     traffic=None, peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
+                    avg_launch_ms=conv_ms / conv_launches,
                     ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms,
-                    how="CUDA events after every launch of 2 x 20 evaluations run back to back on one stream (nst_lbfgs_step_timed)")
+                    how="CUDA events on the launching stream around every run of same-kind launches (forward convolutions, "
+                        "data gradients, Gram backward) of 2 x 20 evaluations executed back to back on one stream "
+                        "(nst_lbfgs_step_timed_grouped); average launch duration = run time / launches in the run")
     lb_ms = per_eval(("lbfgs_pass1", "lbfgs_pass2"))
     m_avg = m_now                                                 # 100: the history was full while the timed steps ran
     lb_gbs = synth.lbfgs_bytes(S, S, m_avg) / (lb_ms * 1e-3) / 1e9 if lb_ms > 0 else None
-    by_kind = {}
-    for (k, l), v in acc.items():
-        by_kind[k] = by_kind.get(k, 0.0) + v[0] / n_evals_timed
+    by_kind = {k: v[0] / n_evals_timed for k, v in acc.items()}
     roofline_hbm = dict(bound="hbm", kernel="lbfgs_pass1_kernel + lbfgs_pass2_kernel", achieved=lb_gbs, peak=pk["hbm"], unit="GB/s",
                         frac=(lb_gbs / pk["hbm"]) if lb_gbs else None, history_pairs=m_avg,
                         bytes_per_iteration=synth.lbfgs_bytes(S, S, m_avg), ms=lb_ms)
@@ -322,6 +326,15 @@ def run_b200(args, rank, world, local_rank):
                 ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu)
     emit(line)
     if args.kernel_table:
+        # per-launch table: the same step with an event after EVERY launch (isolates each launch: no overlap between launches)
+        with torch.cuda.stream(stream):
+            raw1 = plan.lbfgs_step_timed() + plan.lbfgs_step_timed()
+        acc1 = {}
+        for k, l, ms_ in raw1:
+            a = acc1.setdefault((k, l), [0.0, 0])
+            a[0] += ms_
+            a[1] += 1
+        rows = [(k, l, v[0] / v[1]) for (k, l), v in acc1.items()]
         with open(args.kernel_table, "w") as f:
             f.write("kind,conv,ms,gflop,tflops\n")
             for k, l, ms_ in rows + lb_rows:

@@ -183,6 +183,11 @@ int nst_plan_eval_timed(nst_plan* plan, const float* x, float* grad, nst_launch_
  * launch, i.e. every kernel timed in the middle of a long busy stream; it advances the optimizer like nst_lbfgs_step.
  * Returns the number of rows written (about 900). */
 int nst_lbfgs_step_timed(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
+/* The same step with one event wherever the KIND of launch changes: a row is a run of same-kind launches (e.g. the
+ * twelve forward convolutions) timed as a whole with programmatic dependent launch between them intact; `layer` holds
+ * the number of launches in the run.  Side launches that normally sit between forward convolutions are issued after
+ * the last one so that the runs are uninterrupted. */
+int nst_lbfgs_step_timed_grouped(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
 
 /* phase timestamps (SM clock) of CTA 0 of one convolution launch (mode 0 forward, 1 data gradient; conv 0 = conv1_1's
    data gradient) -> out[0..6], the SM cycles its roles spent waiting -> out[8..13] (slots: csrc/conv_tc.cu) and the

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "nst_lbfgs_partial_step": (C.c_int, [_P, C.c_int, _P]),
     "nst_plan_eval_timed": (C.c_int, [_P, _P, _P, C.POINTER(NstLaunchTime), C.c_int, _P]),
     "nst_lbfgs_step_timed": (C.c_int, [_P, C.POINTER(NstLaunchTime), C.c_int, _P]),
+    "nst_lbfgs_step_timed_grouped": (C.c_int, [_P, C.POINTER(NstLaunchTime), C.c_int, _P]),
     "nst_plan_conv_phases": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_longlong), _P]),
     "nst_plan_timeline": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong), _P]),
     "nst_lbfgs_ctl_clocks": (C.c_int, [_P, C.POINTER(C.c_longlong), _P]),

@@ -877,7 +877,11 @@ struct LaunchTimer {
   std::vector<cudaEvent_t> ev;
   std::vector<int> kind, layer;
   cudaStream_t s = nullptr;
-  int mark(int k, int l) {
+  // grouped: one event where the kind of launch changes (runs of same-kind launches are timed as a whole, programmatic
+  // dependent launch between them intact); otherwise one event after every launch
+  bool grouped = false;
+  int cur = -1000;
+  int push(int k, int l) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return -1;
     if (cudaEventRecord(e, s) != cudaSuccess) return -1;
@@ -885,6 +889,20 @@ struct LaunchTimer {
     kind.push_back(k);
     layer.push_back(l);
     return 0;
+  }
+  // after a launch
+  int mark(int k, int l) {
+    if (grouped) {
+      if (k != NST_K_START && !layer.empty()) layer.back() += 1;  // launches in the open group
+      return 0;
+    }
+    return push(k, l);
+  }
+  // before a launch
+  int begin(int k) {
+    if (!grouped || k == cur) return 0;
+    cur = k;
+    return push(k, 0);  // the event opens the group of kind k and closes the previous one
   }
   ~LaunchTimer() {
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
@@ -894,6 +912,10 @@ struct LaunchTimer {
   do {                                                                               \
     if (tm && tm->mark((k), (l)) != 0) return fail(NST_ERR_CUDA, "event record failed"); \
   } while (0)
+#define TB(k)                                                                        \
+  do {                                                                               \
+    if (tm && tm->begin(k) != 0) return fail(NST_ERR_CUDA, "event record failed");    \
+  } while (0)
 
 // The same evaluation with the two chained launches (conv_chain.cu): main stream = conv1_1, forward chain, Gram of the
 // deepest style layer, backward chain (Gram backward + data gradients), conv1_1's data gradient; side stream = pixel
@@ -901,6 +923,7 @@ struct LaunchTimer {
 static int eval_enqueue_chain(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
                               cudaStream_t s, LaunchTimer* tm) {
   int nl = 0;
+  TB(NST_K_START);
   TM(NST_K_START, -1);
   const bool conc = tm == nullptr && p->side != nullptr;
   cudaStream_t s2 = conc ? p->side : s;
@@ -922,6 +945,7 @@ static int eval_enqueue_chain(nst_plan* p, const float* x, float* grad, int* cou
   };
   // ---- side: pixel-space terms
   CK(edge(EV_FORK, s, s2));
+  TB(NST_K_PIXEL);
   CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
   ++nl;
   TM(NST_K_PIXEL, -1);
@@ -987,6 +1011,7 @@ static int eval_enqueue_chain(nst_plan* p, const float* x, float* grad, int* cou
   a.stop_flag = stop_flag;
   a.trace = p->trace;
   a.trace_cap = p->trace_cap;
+  TB(NST_K_ASSEMBLE);
   CK(launch_loss_assemble(a, s2));
   ++nl;
   TM(NST_K_ASSEMBLE, -1);
@@ -1023,6 +1048,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
   if (grad != nullptr && !p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
   if (p->chain && use_vgg) return eval_enqueue_chain(p, x, grad, counter, stop_flag, launches, s, tm);
+  TB(NST_K_START);
   TM(NST_K_START, -1);
   const bool conc = tm == nullptr && p->side != nullptr && use_vgg;
   cudaStream_t s2 = conc ? p->side : s;
@@ -1042,6 +1068,12 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   for (int l = 0; l < p->n_content; ++l)
     if (p->content_conv[l] != last && p->content_conv[l] > max_content) max_content = p->content_conv[l];
 
+  // grouped timing: the side launches that normally sit between forward convolutions are issued after the last one, so
+  // that the twelve forward launches form one uninterrupted run
+  const bool grouped = tm != nullptr && tm->grouped;
+  const int at_shallow = grouped && max_shallow > 0 ? last : max_shallow;
+  const int at_content = grouped && max_content > 0 ? last : max_content;
+
   auto content_launch = [&](int l, int accumulate, cudaStream_t st) -> cudaError_t {
     const int i = p->content_conv[l];
     const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
@@ -1056,29 +1088,35 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
 
   // ---- side: pixel-space terms
   CK(edge(EV_FORK, s, s2));
+  TB(NST_K_PIXEL);
   CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
   ++nl;
   TM(NST_K_PIXEL, -1);
   if (use_vgg) {
     // ---- main: VGG forward
+    TB(NST_K_CONV1_FWD);
     CK(launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
     TM(NST_K_CONV1_FWD, 0);
     if (max_shallow == 0) CK(edge(EV_TAPS, s, s2));
     if (max_content == 0) CK(edge(EV_CONTENT_IN, s, s2));
     for (int i = 1; i < p->n_layers; ++i) {
+      TB(NST_K_CONV_FWD);
       CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
       TM(NST_K_CONV_FWD, i);
-      if (i == max_shallow) {
+      if (i == at_shallow) {
         // ---- side: Gram, style MSE and backward operand of the shallower style layers
         CK(edge(EV_TAPS, s, s2));
-        CK(launch_gram(p->gram_shallow, s2));
+        TB(NST_K_GRAM);
+        TB(NST_K_GRAM);
+      CK(launch_gram(p->gram_shallow, s2));
         nl += 3;
         TM(NST_K_GRAM, 0);
       }
-      if (i == max_content) {
+      if (i == at_content) {
         CK(edge(EV_CONTENT_IN, s, s2));
         for (int l = 0; l < p->n_content; ++l) {
           if (p->content_conv[l] == last) continue;
+          TB(NST_K_CONTENT);
           CK(content_launch(l, 0, s2));
           ++nl;
           TM(NST_K_CONTENT, p->content_conv[l]);
@@ -1088,6 +1126,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     }
     nl += p->n_layers;
     if (max_shallow == 0) {
+      TB(NST_K_GRAM);
       CK(launch_gram(p->gram_shallow, s2));
       nl += 3;
       TM(NST_K_GRAM, 0);
@@ -1102,12 +1141,14 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     }
     // ---- main: the deepest layer's targets
     if (deep_style) {
+      TB(NST_K_GRAM);
       CK(launch_gram(p->gram_deep, s));
       nl += 3;
       TM(NST_K_GRAM, last);
     }
     for (int l = 0; l < p->n_content; ++l) {
       if (p->content_conv[l] != last) continue;
+      TB(NST_K_CONTENT);
       CK(content_launch(l, 0, s));
       ++nl;
       TM(NST_K_CONTENT, last);
@@ -1128,11 +1169,13 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       // the main stream instead of the first data gradients; all seeds are awaited together before conv4_2's data gradient
       for (int l = 0; l < n_shallow; ++l) {
         const int i = p->style_conv[l];
+        TB(NST_K_GRAM_BWD);
         CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
         ++nl;
         TM(NST_K_GRAM_BWD, i);
         const int cl = content_index(p, i);
         if (cl >= 0) {
+          TB(NST_K_CONTENT);
           CK(content_launch(cl, 1, s2));
           ++nl;
           TM(NST_K_CONTENT, i);
@@ -1170,6 +1213,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   a.stop_flag = stop_flag;
   a.trace = p->trace;
   a.trace_cap = p->trace_cap;
+  TB(NST_K_ASSEMBLE);
   CK(launch_loss_assemble(a, s2));
   ++nl;
   TM(NST_K_ASSEMBLE, -1);
@@ -1178,11 +1222,13 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   if (grad != nullptr) {
     if (use_vgg) {
       if (deep_style) {
+        TB(NST_K_GRAM_BWD);
         CK(launch_conv_tc(p->scale[last], CONV_SCALE, g_num_sms, s));
         ++nl;
         TM(NST_K_GRAM_BWD, last);
         const int cl = content_index(p, last);
         if (cl >= 0) {
+          TB(NST_K_CONTENT);
           CK(content_launch(cl, 1, s));
           ++nl;
           TM(NST_K_CONTENT, last);
@@ -1192,6 +1238,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
         // conv i's data gradient adds the seed of conv i-1
         if (conc && i - 1 == max_content) CK(cudaStreamWaitEvent(s, p->ev[EV_CONTENT], 0));
         if (conc && i - 1 == max_shallow) CK(cudaStreamWaitEvent(s, p->ev[EV_SEEDS], 0));
+        TB(NST_K_CONV_DGRAD);
         CK(launch_conv_tc(p->dgrad[i], CONV_DGRAD, g_num_sms, s));
         ++nl;
         TM(NST_K_CONV_DGRAD, i);
@@ -1200,11 +1247,13 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       {
         static const bool cuda_core_conv1 = getenv("NST_CONV1_CUDA_CORES") != nullptr;
         if (cuda_core_conv1) {
+          TB(NST_K_CONV1_DGRAD);
           CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
         } else {
           ConvParams d = p->dgrad[0];
           d.out_pix = grad;
           for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
+          TB(NST_K_CONV1_DGRAD);
           CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
         }
       }
@@ -1237,8 +1286,22 @@ __global__ void spin_kernel(long long cycles) {
 }
 
 static int timer_collect(LaunchTimer& tm, nst_launch_time* out, int max_out, cudaStream_t s) {
+  if (tm.grouped && tm.begin(NST_K_START) != 0) return fail(NST_ERR_CUDA, "event record failed");  // closes the last group
   CK(cudaStreamSynchronize(s));
   int n = 0;
+  if (tm.grouped) {
+    // row = one run of same-kind launches: kind, number of launches, duration of the whole run
+    for (size_t i = 0; i + 1 < tm.ev.size() && n < max_out; ++i) {
+      if (tm.kind[i] == NST_K_START) continue;
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]));
+      out[n].kind = tm.kind[i];
+      out[n].layer = tm.layer[i];
+      out[n].ms = ms;
+      ++n;
+    }
+    return n;
+  }
   for (size_t i = 1; i < tm.ev.size() && n < max_out; ++i) {
     if (tm.kind[i] == NST_K_START) continue;
     float ms = 0.f;
@@ -1268,12 +1331,20 @@ extern "C" int nst_plan_eval_timed(nst_plan* p, const float* x, float* grad, nst
 static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm);
 static void timeline_arm(nst_plan* p, bool on);
 
+static int step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream, bool grouped);
 extern "C" int nst_lbfgs_step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
+  return step_timed(p, out, max_out, stream, false);
+}
+extern "C" int nst_lbfgs_step_timed_grouped(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
+  return step_timed(p, out, max_out, stream, true);
+}
+static int step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream, bool grouped) {
   if (!p || !out || max_out < 64) return fail(NST_ERR_ARG, "nst_lbfgs_step_timed: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   LaunchTimer tm;
   tm.s = s;
+  tm.grouped = grouped;
   // let the host run ahead of the device so that event-to-event times contain no launch gaps
   spin_kernel<<<1, 1, 0, s>>>(3000000);
   CK(cudaGetLastError());
@@ -1508,13 +1579,18 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
     if (tm == nullptr) {
       CK(launch_lbfgs_iteration(b, mode, s));
     } else {
+      TB(NST_K_START);
       TM(NST_K_START, -1);
+      TB(NST_K_LBFGS_PASS1);
       CK(launch_lbfgs_pass1(b, s));
       TM(NST_K_LBFGS_PASS1, -1);
+      TB(NST_K_LBFGS_REDUCE);
       CK(launch_lbfgs_reduce(b, s));
       TM(NST_K_LBFGS_REDUCE, -1);
+      TB(NST_K_LBFGS_CONTROL);
       CK(launch_lbfgs_control(b, mode, s));
       TM(NST_K_LBFGS_CONTROL, -1);
+      TB(NST_K_LBFGS_PASS2);
       CK(launch_lbfgs_pass2(b, s));
       TM(NST_K_LBFGS_PASS2, -1);
     }

@@ -231,11 +231,13 @@ class Plan:
             n = check(self.lib.nst_plan_eval_timed(self.handle, _ptr(x), _ptr(grad), buf, 128, _stream_ptr(self.device)))
         return [(_lib.KIND_NAMES.get(buf[i].kind, str(buf[i].kind)), buf[i].layer, buf[i].ms) for i in range(n)]
 
-    def lbfgs_step_timed(self):
-        """One whole optimizer.step() with a CUDA event after every launch -> list of (kind name, conv index, ms)."""
+    def lbfgs_step_timed(self, grouped: bool = False):
+        """One whole optimizer.step() with a CUDA event after every launch -> list of (kind name, conv index, ms); grouped:
+        one event where the kind of launch changes -> list of (kind name, launches in the run, ms of the run)."""
         buf = (_lib.NstLaunchTime * 1200)()
+        fn = self.lib.nst_lbfgs_step_timed_grouped if grouped else self.lib.nst_lbfgs_step_timed
         with torch.cuda.device(self.device):
-            n = check(self.lib.nst_lbfgs_step_timed(self.handle, buf, 1200, _stream_ptr(self.device)))
+            n = check(fn(self.handle, buf, 1200, _stream_ptr(self.device)))
         return [(_lib.KIND_NAMES.get(buf[i].kind, str(buf[i].kind)), buf[i].layer, buf[i].ms) for i in range(n)]
 
     def launches_per_step(self) -> int:
