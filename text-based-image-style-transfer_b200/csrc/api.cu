@@ -1365,6 +1365,7 @@ extern "C" int nst_plan_conv_phases(nst_plan* p, int conv, int mode, long long* 
   cudaError_t e = cudaMemsetAsync(d, 0, (16 + 160) * sizeof(long long), s);
   ConvParams c = mode == 0 ? p->fwd[conv] : p->dgrad[conv];
   c.dbg = d;
+  c.dbg_flags = getenv("NST_DBG_FLAGS") ? atoi(getenv("NST_DBG_FLAGS")) : 0;
   c.tl = reinterpret_cast<unsigned long long*>(d + 14);  // out[14], out[15]: launch span in %globaltimer ns
   const unsigned long long tl_init[2] = {~0ull, 0ull};
   if (e == cudaSuccess) e = cudaMemcpyAsync(d + 14, tl_init, sizeof(tl_init), cudaMemcpyHostToDevice, s);

@@ -57,11 +57,11 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
     v[4 * q + 3] += b.w;
   }
   const size_t pix = static_cast<size_t>(h) * p.W + w;
-  if (p.out_tap != nullptr && valid) store_h32(p.out_tap + pix * p.N + n, v);
+  if (p.out_tap != nullptr && valid && !(p.dbg_flags & 1)) store_h32(p.out_tap + pix * p.N + n, v);
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
   if (!p.pool) {
-    if (p.out_act != nullptr && valid) store_h32(p.out_act + pix * p.N + n, v);
+    if (p.out_act != nullptr && valid && !(p.dbg_flags & 1)) store_h32(p.out_act + pix * p.N + n, v);
     return;
   }
   // 2x2 max-pool across the four lanes {lane, lane^1, lane^8, lane^9}: tile rows are 8 pixels
@@ -110,7 +110,7 @@ struct DgradAux {
   uint4 a[2];  // tap seed (bf16) added to the gradient
 };
 __device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x, int h, int w, int n, bool valid) {
-  if (!valid) return;
+  if (!valid || (p.dbg_flags & 2)) return;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
     const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
@@ -156,7 +156,7 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[D
         }
       }
     }
-    store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
+    if (!(p.dbg_flags & 1)) store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
   } else {
     // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
     // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
@@ -171,7 +171,7 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[D
         o[j] = rj == static_cast<uint32_t>(pos) ? v[j] : 0.f;
       }
       const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
-      store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
+      if (!(p.dbg_flags & 1)) store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
     }
   }
 }

@@ -55,6 +55,8 @@ struct ConvParams {
   // ---- launch span inside a captured step (debug; nullptr in production): tl[0] = earliest CTA start, tl[1] = latest CTA
   // end, both %globaltimer ns (atomicMin / atomicMax by every CTA): tools/conv_timeline.py
   unsigned long long* tl;
+  // ---- debug experiments (0 in production): bit 0 = skip the epilogue's global stores, bit 1 = skip its global loads
+  int dbg_flags;
 };
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
