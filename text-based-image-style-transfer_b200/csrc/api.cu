@@ -262,6 +262,8 @@ static int content_index(const nst_plan* p, int conv) {
 
 static int build_conv_params(nst_plan* p) {
   const nst_net* net = p->net;
+  // epilogue outputs through shared memory + TMA stores (conv_epilogue.cuh); NST_DIRECT_STORES=1 keeps the per-thread stores
+  const bool tma_out = getenv("NST_DIRECT_STORES") == nullptr;
   for (int i = 1; i < p->n_layers; ++i) {
     const int lv = kLevel[i];
     const int H = p->lh[lv], W = p->lw[lv];
@@ -284,6 +286,11 @@ static int build_conv_params(nst_plan* p) {
     f.out_route = p->route[i];
     f.pool = pooled ? 1 : 0;
     conv_finalize_params(f, CONV_FWD);
+    if (tma_out) {
+      if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out %d)", i);
+      if (!pooled && f.out_act && make_tmap_out(&f.tmO1, f.out_act, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (act out %d)", i);
+      f.tma_out = 1;
+    }
     if (!p->with_grad) continue;
     // ---- data-gradient of conv i: consumes gpre[i], produces gpre[i-1]
     ConvParams& d = p->dgrad[i];
@@ -308,6 +315,17 @@ static int build_conv_params(nst_plan* p) {
       d.addend = p->gadd[i - 1];
     }
     conv_finalize_params(d, CONV_DGRAD);
+    if (tma_out) {
+      const int rc = prev_pooled ? make_tmap_out(&d.tmO0, d.out_grad, d.Hup, d.Wup, kCin[i], 16, 2 * CONV_TILE_W, 8)
+                                 : make_tmap_out(&d.tmO0, d.out_grad, H, W, kCin[i], 32, CONV_TILE_W, 4);
+      if (rc != 0) return fail(NST_ERR_CUDA, "tensor map (grad out %d)", i);
+      // Measured (profiles/r01_conv_phases_tma_store.log, r01_timeline_512_tma_store.log): data gradients keep their direct
+      // 16-byte stores.  The plain masked gradient gains nothing from the TMA store (conv1_2: 40 -> 50 us).  The pool-routing
+      // scatter gains 2-6 us per layer in isolation, but inside the step the NEXT layer, which reads that gradient, loses
+      // more (conv1_2: +15 us, conv2_2: +7 us): 32-byte box rows reach L2 as single-sector writes.  NST_TMA_DGRAD=1 opts in.
+      static const bool all_dgrad = getenv("NST_TMA_DGRAD") != nullptr;
+      d.tma_out = all_dgrad ? 1 : 0;
+    }
   }
   if (!p->with_grad) return NST_OK;
   {
@@ -344,6 +362,10 @@ static int build_conv_params(nst_plan* p) {
     c.alpha = p->alpha + l;
     c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
     conv_finalize_params(c, CONV_SCALE);
+    if (tma_out) {
+      if (make_tmap_out(&c.tmO0, c.out_grad, c.H, c.W, C, 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (seed out %d)", i);
+      c.tma_out = 1;
+    }
   }
   return NST_OK;
 }

@@ -43,9 +43,96 @@ __device__ __forceinline__ void store_bf(__nv_bfloat16* dst, const float (&v)[CH
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Output through shared memory + TMA store.  One thread owns one pixel, so a direct 16-byte store instruction of a warp
+// touches 32 different 128-byte lines (one piece each): the epilogue of the shallow layers was bound by those
+// transactions, not by bandwidth (profiles/r01_conv_phases_store_experiment.log).  Instead every lane writes its pixel's
+// 64 (or 32) bytes into a small per-warp staging buffer in the layout of a TMA box [4 rows][8 pixels][channels]
+// (64- or 32-byte swizzle, which also makes the 16-byte shared-memory writes conflict-free) and one lane issues a
+// cp.async.bulk.tensor store: coalesced by the TMA engine, clipped at the image border, asynchronous.
+// Two buffers per warp alternate; a buffer is rewritten only after the bulk store that read it has finished reading.
+// ---------------------------------------------------------------------------------------------
+static constexpr int EPI_STAGE_BYTES = 2048;  // 32 pixels x 64 B; two per warp (the pool-routing scatter uses both as one 4 KB box)
+struct EpiStore {
+  uint8_t* buf;   // 2 x EPI_STAGE_BYTES of this warp, 1024-byte aligned
+  int next;       // buffer the next store uses
+  uint8_t* cur;   // buffer being filled by a store that spans two calls (data gradient: two 16-channel chunks per row)
+  int lane;
+  int w0, h0;     // tile-row origin of this warp's 8 x 4 pixel block in the output tensor
+};
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// rows of 64 bytes, 64-byte swizzle: 16-byte piece j of row r lives at piece j ^ ((r >> 1) & 3)
+__device__ __forceinline__ void stage_row64(uint8_t* buf, int row, const uint4 (&u)[4]) {
+  const int x = (row >> 1) & 3;
+  uint4* b = reinterpret_cast<uint4*>(buf + row * 64);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j ^ x] = u[j];
+}
+// rows of 32 bytes, 32-byte swizzle: piece j of row r lives at piece j ^ ((r >> 2) & 1)
+__device__ __forceinline__ void stage_row32(uint8_t* buf, int row, const uint4 (&u)[2]) {
+  const int x = (row >> 2) & 1;
+  uint4* b = reinterpret_cast<uint4*>(buf + row * 32);
+  b[x] = u[0];
+  b[x ^ 1] = u[1];
+}
+// the two halves of a warp-wide TMA store: acquire a buffer (its previous store must have finished reading it) ...
+__device__ __forceinline__ uint8_t* epi_acquire(EpiStore& st, bool both) {
+  if (st.lane == 0) {
+    if (both) bulk_wait_read<0>();
+    else bulk_wait_read<1>();
+  }
+  __syncwarp();
+  uint8_t* b = both ? st.buf : st.buf + st.next * EPI_STAGE_BYTES;
+  if (!both) st.next ^= 1;
+  return b;
+}
+// ... and, once every lane has written its rows, hand it to the TMA engine
+__device__ __forceinline__ void epi_submit(const EpiStore& st, const uint8_t* b, const CUtensorMap* tm, int c0, int w0, int h0,
+                                           bool skip) {
+  fence_async_smem();
+  __syncwarp();
+  if (st.lane == 0 && !skip) {
+    tma_store_3d(tm, b, c0, w0, h0);
+    bulk_commit();
+  }
+}
+__device__ __forceinline__ void pack_h32(const float (&v)[32], uint4 (&u)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    u[q].x = pack_h2(v[8 * q + 0], v[8 * q + 1]);
+    u[q].y = pack_h2(v[8 * q + 2], v[8 * q + 3]);
+    u[q].z = pack_h2(v[8 * q + 4], v[8 * q + 5]);
+    u[q].w = pack_h2(v[8 * q + 6], v[8 * q + 7]);
+  }
+}
+template <int CH>
+__device__ __forceinline__ void pack_bf(const float (&v)[CH], uint4 (&u)[CH / 8]) {
+#pragma unroll
+  for (int q = 0; q < CH / 8; ++q) {
+    u[q].x = pack_bf2(v[8 * q + 0], v[8 * q + 1]);
+    u[q].y = pack_bf2(v[8 * q + 2], v[8 * q + 3]);
+    u[q].z = pack_bf2(v[8 * q + 4], v[8 * q + 5]);
+    u[q].w = pack_bf2(v[8 * q + 6], v[8 * q + 7]);
+  }
+}
+
 // forward epilogue for 32 channels of one pixel
 __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
-                                             int lane, const float* sbias /* 32 values of this chunk, shared memory */) {
+                                             int lane, const float* sbias /* 32 values of this chunk, shared memory */,
+                                             EpiStore* st = nullptr /* non-null: outputs go through TMA stores */) {
   // bias (same address across the warp -> broadcast read); staged in shared memory while the main loop ran
   const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
@@ -57,11 +144,31 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
     v[4 * q + 3] += b.w;
   }
   const size_t pix = static_cast<size_t>(h) * p.W + w;
-  if (p.out_tap != nullptr && valid && !(p.dbg_flags & 1)) store_h32(p.out_tap + pix * p.N + n, v);
+  if (st != nullptr) {
+    if (p.out_tap != nullptr) {
+      uint4 u[4];
+      pack_h32(v, u);
+      uint8_t* b = epi_acquire(*st, false);
+      stage_row64(b, lane, u);
+      epi_submit(*st, b, &p.tmO0, n, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+    }
+  } else if (p.out_tap != nullptr && valid && !(p.dbg_flags & 1)) {
+    store_h32(p.out_tap + pix * p.N + n, v);
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
   if (!p.pool) {
-    if (p.out_act != nullptr && valid && !(p.dbg_flags & 1)) store_h32(p.out_act + pix * p.N + n, v);
+    if (st != nullptr) {
+      if (p.out_act != nullptr) {
+        uint4 u[4];
+        pack_h32(v, u);
+        uint8_t* b = epi_acquire(*st, false);
+        stage_row64(b, lane, u);
+        epi_submit(*st, b, &p.tmO1, n, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+      }
+    } else if (p.out_act != nullptr && valid && !(p.dbg_flags & 1)) {
+      store_h32(p.out_act + pix * p.N + n, v);
+    }
     return;
   }
   // 2x2 max-pool across the four lanes {lane, lane^1, lane^8, lane^9}: tile rows are 8 pixels
@@ -129,8 +236,8 @@ __device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x,
 
 // data-gradient epilogue for DG_CH channels of one pixel
 __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[DG_CH], int h, int w, int n, bool valid,
-                                               const DgradAux& x) {
-  if (!valid) return;
+                                               const DgradAux& x, EpiStore* st = nullptr) {
+  if (!valid && st == nullptr) return;  // with TMA stores every lane takes part (the box is clipped at the border)
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
     // ReLU mask from the stored post-ReLU activation (PyTorch: grad * (result > 0))
@@ -156,31 +263,63 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[D
         }
       }
     }
-    if (!(p.dbg_flags & 1)) store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
+    if (st != nullptr) {
+      // two consecutive 16-channel chunks fill one 64-byte row; the store goes out with the second (a 1 KB store per
+      // chunk was slower than the direct stores: twice the bulk operations, each waiting for a buffer)
+      uint4 u[DG_CH / 8];
+      pack_bf<DG_CH>(v, u);
+      const int half = (n / DG_CH) & 1;
+      if (half == 0) st->cur = epi_acquire(*st, false);
+      const int x = (st->lane >> 1) & 3;
+      uint4* row = reinterpret_cast<uint4*>(st->cur + st->lane * 64);
+      row[(2 * half) ^ x] = u[0];
+      row[(2 * half + 1) ^ x] = u[1];
+      if (half == 1) epi_submit(*st, st->cur, &p.tmO0, n - DG_CH, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+    } else if (!(p.dbg_flags & 1)) {
+      store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
+    }
   } else {
     // max-pool routing: the gradient of pooled pixel (h, w) goes to the arg-max position of its
     // 2x2 window in the un-pooled map (and only if the pooled activation was > 0: ReLU mask).
     uint32_t r[4];
     r[0] = x.m[0].x; r[1] = x.m[0].y; r[2] = x.m[0].z; r[3] = x.m[0].w;
+    // TMA path: the warp's 8 x 4 pooled pixels scatter into one 16 x 8 box of the un-pooled gradient (4 KB, both buffers)
+    uint8_t* b = st != nullptr ? epi_acquire(*st, true) : nullptr;
 #pragma unroll
     for (int pos = 0; pos < 4; ++pos) {
       float o[DG_CH];
 #pragma unroll
       for (int j = 0; j < DG_CH; ++j) {
         const uint32_t rj = (r[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        o[j] = rj == static_cast<uint32_t>(pos) ? v[j] : 0.f;
+        o[j] = (valid && rj == static_cast<uint32_t>(pos)) ? v[j] : 0.f;
       }
-      const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
-      if (!(p.dbg_flags & 1)) store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
+      if (st != nullptr) {
+        uint4 u[DG_CH / 8];
+        pack_bf<DG_CH>(o, u);
+        const int row = (2 * (st->lane >> 3) + (pos >> 1)) * 16 + 2 * (st->lane & 7) + (pos & 1);
+        stage_row32(b, row, u);
+      } else {
+        const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
+        if (!(p.dbg_flags & 1)) store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
+      }
     }
+    if (st != nullptr) epi_submit(*st, b, &p.tmO0, n, 2 * st->w0, 2 * st->h0, (p.dbg_flags & 1) != 0);
   }
 }
 
 __device__ __forceinline__ void epilogue_scale(const ConvParams& p, float (&v)[32], int h, int w, int n, bool valid,
-                                               float alpha) {
-  if (!valid) return;
+                                               float alpha, EpiStore* st = nullptr) {
+  if (!valid && st == nullptr) return;
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= alpha;
+  if (st != nullptr) {
+    uint4 u[4];
+    pack_bf<32>(v, u);
+    uint8_t* b = epi_acquire(*st, false);
+    stage_row64(b, st->lane, u);
+    epi_submit(*st, b, &p.tmO0, n, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+    return;
+  }
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   store_bf<32>(p.out_grad + pix * p.N + n, v);
 }

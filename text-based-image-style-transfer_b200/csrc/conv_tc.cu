@@ -59,7 +59,10 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
   static constexpr int OPERAND_BYTES = HALO_STAGES * HALO_STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one bias slice per accumulator stage
-  static constexpr int SMEM_BYTES = OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
+  // staging for the epilogue's TMA stores: two 2 KB buffers per epilogue warp, 1024-byte aligned
+  static constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_STAGE_BYTES;
+  static constexpr int MISC_BYTES = ((256 /*barriers*/ + BIAS_BYTES + 1023) / 1024) * 1024;
+  static constexpr int SMEM_BYTES = OPERAND_BYTES + 1024 /*align slack*/ + MISC_BYTES + EPI_BYTES;
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -71,7 +74,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool TMA_OUT>
 __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias = reinterpret_cast<float*>(smem + Cfg::OPERAND_BYTES + 256);
+  uint8_t* sEpi = smem + Cfg::OPERAND_BYTES + Cfg::MISC_BYTES;  // 1024-byte aligned (operand stages are multiples of 1024)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -300,6 +304,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     const int t = q * 32 + lane;
     const int hl = t / TILE_W, wl = t % TILE_W;
     const int et = threadIdx.x - 128;       // index among the epilogue threads
+    EpiStore est;
+    est.buf = sEpi + (warp - 4) * (2 * EPI_STAGE_BYTES);
+    est.next = 0;
+    est.lane = lane;
+    // compile-time: the direct-store instantiation must not carry the staging code (register pressure in the data gradient)
+    EpiStore* const st = TMA_OUT ? &est : nullptr;
     int ts = 0;
     uint32_t tphase = 0;
     float alpha = 0.f;
@@ -350,6 +360,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       int h, w, n0;
       bool valid;
       coords(tile, h, w, n0, valid);
+      est.w0 = w - wl;            // this warp's 8 x 4 pixel block of the tile
+      est.h0 = h - hl + q * 4;
       if constexpr (MODE == CONV_FWD) {
         for (int j = et; j < BLOCK_N; j += Cfg::EPI_WARPS * 32) sbias[ts * BLOCK_N + j] = __ldg(p.bias + n0 + j);
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             float v[DG_CH];
 #pragma unroll
             for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[c]);
+            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[c], st);
           }
         } else {
 #pragma unroll 1
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             float v[DG_CH];
 #pragma unroll
             for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[0]);
+            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[0], st);
             aux[0] = aux_nxt;
           }
         }
@@ -414,8 +426,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           const int n = n0 + col0 + c * 32;
-          if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + col0 + c * 32);
-          if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha);
+          if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + col0 + c * 32, st);
+          if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha, st);
         }
       }
       if constexpr (XT) {
@@ -436,6 +448,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   }
 
   if (dbg && threadIdx.x == 128) p.dbg[11] = wacc0;
+  if (TMA_OUT && warp >= 4 && lane == 0) bulk_wait_all();  // the staging buffers must outlive the stores reading them
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -475,6 +488,20 @@ int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int b
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (box_c * 2 != 64 && box_c * 2 != 32) return -2;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
@@ -532,28 +559,45 @@ void conv_finalize_params(ConvParams& p, int mode) {
   p.idesc = umma_idesc_f16(BLOCK_M, bn, (mode == CONV_DGRAD || mode == CONV_DGRAD_PIX) ? 1 : 0, 0, 0);
 }
 
-template <int BLOCK_N, int MODE>
-static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
+template <int BLOCK_N, int MODE, bool TMA_OUT>
+static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   static const bool pdl = getenv("NST_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  // the staging buffers of the TMA-store epilogue sit at the end of the allocation: a launch that stores directly does not
+  // reserve them - shared memory and L1 share one array, and the data-gradient epilogue's 16-byte loads of 128-byte lines
+  // live on L1 hits (34 KB less L1 cost conv1_2's data gradient 17 us inside the step)
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES - (TMA_OUT ? 0 : Cfg::EPI_BYTES);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE>, p);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, TMA_OUT>, p);
+}
+template <int BLOCK_N, int MODE>
+static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  if constexpr (MODE == CONV_DGRAD_PIX) {
+    return launch_one_t<BLOCK_N, MODE, false>(p, num_sms, stream);
+  } else {
+    return p.tma_out ? launch_one_t<BLOCK_N, MODE, true>(p, num_sms, stream) : launch_one_t<BLOCK_N, MODE, false>(p, num_sms, stream);
+  }
 }
 
 template <int BLOCK_N, int MODE>
 static cudaError_t init_one() {
-  return cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              ConvCfg<BLOCK_N>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ConvCfg<BLOCK_N>::SMEM_BYTES);
+  if constexpr (MODE != CONV_DGRAD_PIX) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<BLOCK_N>::SMEM_BYTES);
+  }
+  return e;
 }
 template <int MODE>
 static cudaError_t init_mode() {

@@ -26,6 +26,12 @@ enum ConvMode : int {
 struct ConvParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  // outputs through TMA stores (tma_out != 0): tmO0 = pre-ReLU tap (forward) / gradient (data gradient, Gram backward),
+  // tmO1 = post-ReLU activation of a layer that is not pooled; boxes of 8 x 4 pixels x 32 channels (64-byte swizzle) or
+  // x 16 channels (32-byte swizzle, data gradient), 16 x 8 pixels for the pool-routing scatter
+  CUtensorMap tmO0;
+  CUtensorMap tmO1;
+  int tma_out;
   int H, W;        // pixel grid of the GEMM M dimension
   int K, N;        // channels contracted per tap, output channels
   int taps;        // 9 (3x3, pad 1) or 1 (1x1)
@@ -62,6 +68,8 @@ struct ConvParams {
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
 int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n);
+// output map for the epilogue's TMA stores: [H][W][C] 16-bit tensor, box (box_c, box_w, box_h); box_c * 2 = 64 or 32 bytes
+int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 // filter taps the kernel loads per weight stage for this N tile (the depth of the weight tensor map's box)
 int conv_taps_per_stage(int block_n, int taps);
 
