@@ -41,6 +41,23 @@ def env_int(name, default):
         return default
 
 
+def ncu_traffic():
+    """Average DRAM bytes (read + write) per conv_tc_kernel launch from the committed `ncu --set full` capture of one
+    evaluation's launches (profiles/r01b_ncu_full_conv_tc_summary.csv); None if the summary is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_conv_tc_summary.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    try:
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    except ValueError:
+        return None
+    vals = [(float(r[ir]) + float(r[iw])) * 1e6 for r in rows[2:] if "conv_tc_kernel" in r[ik] and "<16" not in r[ik]]
+    return sum(vals) / len(vals) if vals else None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -294,7 +311,8 @@ def run_b200(args, rank, world, local_rank):
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient + 5 Gram-backward launches per evaluation)",
                     achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
-                    traffic=None, peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the 29 launches of one evaluation (ncu --set full, profiles/r01b_ncu_full_conv_tc_summary.csv)",
+                    peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
                     avg_launch_ms=conv_ms / conv_launches,
                     ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms,

@@ -186,36 +186,68 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Persistent: the grid is two blocks per SM and every block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The
+// weights are staged once per block, and the next tile's 3 x 10 x 34 input patch is fetched into registers before the
+// current tile is computed - the one-launch-per-tile version spent half of every block waiting for its own prologue
+// (ncu: fma pipe 39 % active, profiles/r01b_ncu_full_misc_summary.csv).
+static constexpr int C1_IN = 3 * (C1_TH + 2) * (C1_TW + 2);   // 1020 patch values
+static constexpr int C1_IN_PER_THREAD = (C1_IN + 255) / 256;  // 4
+
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, __half* __restrict__ out_tap,
                                                         __half* __restrict__ out_act, int H, int W, PixelConsts pc) {
-  __shared__ float in[3][C1_TH + 2][C1_TW + 2];
-  // [c*9 + r*3 + s][n]; rows padded to 68 floats: the transposing stores below would otherwise all hit one bank
-  __shared__ __align__(16) float ws[27][68];
+  __shared__ float in[2][3][C1_TH + 2][C1_TW + 2];
+  // [c*9 + r*3 + s][half][channel group j][4]: the eight channel groups of a quarter-warp read 128 contiguous bytes
+  __shared__ __align__(16) float ws[27][2][8][4];
   const int tiles_w = (W + C1_TW - 1) / C1_TW;
-  const int w0 = (blockIdx.x % tiles_w) * C1_TW, h0 = (blockIdx.x / tiles_w) * C1_TH;
+  const int tiles = tiles_w * ((H + C1_TH - 1) / C1_TH);
   const size_t HW = static_cast<size_t>(H) * W;
   for (int i = threadIdx.x; i < 27 * 64; i += 256) {
-    const int n = i / 27, k = i - n * 27;  // torch layout [n][c][r][s] -> k = c*9 + r*3 + s
-    ws[k][n] = wgt[i];
+    const int k = i / 64, n = i - k * 64;  // torch layout [n][c][r][s] -> k = c*9 + r*3 + s
+    ws[k][(n >> 2) & 1][n >> 3][n & 3] = __ldg(wgt + n * 27 + k);
   }
-  for (int i = threadIdx.x; i < 3 * (C1_TH + 2) * (C1_TW + 2); i += 256) {
-    const int c = i / ((C1_TH + 2) * (C1_TW + 2));
-    const int rem = i - c * ((C1_TH + 2) * (C1_TW + 2));
-    const int sy = rem / (C1_TW + 2), sx = rem - sy * (C1_TW + 2);
-    const int hh = h0 + sy - 1, ww = w0 + sx - 1;
-    float v = 0.f;  // zero padding lives in the normalised domain
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = (x[c * HW + static_cast<size_t>(hh) * W + ww] - pc.mean[c]) / pc.stdv[c];
-    in[c][sy][sx] = v;
-  }
-  __syncthreads();
+  const float inv_std[3] = {1.f / pc.stdv[0], 1.f / pc.stdv[1], 1.f / pc.stdv[2]};
+  // patch element e of a tile -> normalised value (zero padding lives in the normalised domain)
+  auto fetch = [&](int tile, float (&v)[C1_IN_PER_THREAD]) {
+    const int w0 = (tile % tiles_w) * C1_TW, h0 = (tile / tiles_w) * C1_TH;
+#pragma unroll
+    for (int q = 0; q < C1_IN_PER_THREAD; ++q) {
+      const int i = threadIdx.x + q * 256;
+      v[q] = 0.f;
+      if (i < C1_IN) {
+        const int c = i / ((C1_TH + 2) * (C1_TW + 2));
+        const int rem = i - c * ((C1_TH + 2) * (C1_TW + 2));
+        const int sy = rem / (C1_TW + 2), sx = rem - sy * (C1_TW + 2);
+        const int hh = h0 + sy - 1, ww = w0 + sx - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v[q] = (__ldg(x + c * HW + static_cast<size_t>(hh) * W + ww) - pc.mean[c]) / pc.stdv[c];
+      }
+    }
+  };
+  auto stash = [&](int buf, const float (&v)[C1_IN_PER_THREAD]) {
+#pragma unroll
+    for (int q = 0; q < C1_IN_PER_THREAD; ++q) {
+      const int i = threadIdx.x + q * 256;
+      if (i < C1_IN) (&in[buf][0][0][0])[i] = v[q];
+    }
+  };
+  (void)inv_std;
   const int j = threadIdx.x & 7;    // channel group: channels 8j .. 8j+7
   const int px = threadIdx.x >> 3;  // pixel column inside the tile
-  // packed fp32 (fma.rn.f32x2, sm_100): two channels per instruction, bit-identical to two fmaf
-  float2 acc[C1_TH][4];
-  {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * j);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * j + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * j);
+  const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * j + 4);
+  float nxt[C1_IN_PER_THREAD];
+  int buf = 0;
+  if (static_cast<int>(blockIdx.x) < tiles) {
+    fetch(blockIdx.x, nxt);
+    stash(0, nxt);
+  }
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
+    const bool more = tile + static_cast<int>(gridDim.x) < tiles;
+    if (more) fetch(tile + gridDim.x, nxt);  // in flight while this tile is computed
+    const int w0 = (tile % tiles_w) * C1_TW, h0 = (tile / tiles_w) * C1_TH;
+    // packed fp32 (fma.rn.f32x2, sm_100): two channels per instruction, bit-identical to two fmaf
+    float2 acc[C1_TH][4];
 #pragma unroll
     for (int i = 0; i < C1_TH; ++i) {
       acc[i][0] = make_float2(b0.x, b0.y);
@@ -223,60 +255,71 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       acc[i][2] = make_float2(b1.x, b1.y);
       acc[i][3] = make_float2(b1.z, b1.w);
     }
-  }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 3; ++c) {
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      float col[C1_TH + 2];
+      for (int s = 0; s < 3; ++s) {
+        float col[C1_TH + 2];
 #pragma unroll
-      for (int r = 0; r < C1_TH + 2; ++r) col[r] = in[c][r][px + s];
+        for (int r = 0; r < C1_TH + 2; ++r) col[r] = in[buf][c][r][px + s];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float4 wa = *reinterpret_cast<const float4*>(&ws[c * 9 + r * 3 + s][8 * j]);
-        const float4 wb = *reinterpret_cast<const float4*>(&ws[c * 9 + r * 3 + s][8 * j + 4]);
-        const float2 q0 = make_float2(wa.x, wa.y), q1 = make_float2(wa.z, wa.w);
-        const float2 q2 = make_float2(wb.x, wb.y), q3 = make_float2(wb.z, wb.w);
+        for (int r = 0; r < 3; ++r) {
+          const float4 wa = *reinterpret_cast<const float4*>(ws[c * 9 + r * 3 + s][0][j]);
+          const float4 wb = *reinterpret_cast<const float4*>(ws[c * 9 + r * 3 + s][1][j]);
+          const float2 q0 = make_float2(wa.x, wa.y), q1 = make_float2(wa.z, wa.w);
+          const float2 q2 = make_float2(wb.x, wb.y), q3 = make_float2(wb.z, wb.w);
 #pragma unroll
-        for (int i = 0; i < C1_TH; ++i) {
-          const float2 v = make_float2(col[i + r], col[i + r]);
-          acc[i][0] = __ffma2_rn(v, q0, acc[i][0]);
-          acc[i][1] = __ffma2_rn(v, q1, acc[i][1]);
-          acc[i][2] = __ffma2_rn(v, q2, acc[i][2]);
-          acc[i][3] = __ffma2_rn(v, q3, acc[i][3]);
+          for (int i = 0; i < C1_TH; ++i) {
+            const float2 v = make_float2(col[i + r], col[i + r]);
+            acc[i][0] = __ffma2_rn(v, q0, acc[i][0]);
+            acc[i][1] = __ffma2_rn(v, q1, acc[i][1]);
+            acc[i][2] = __ffma2_rn(v, q2, acc[i][2]);
+            acc[i][3] = __ffma2_rn(v, q3, acc[i][3]);
+          }
         }
       }
     }
-  }
-  const int w = w0 + px;
-  if (w >= W) return;
+    const int w = w0 + px;
+    if (w < W) {
 #pragma unroll
-  for (int i = 0; i < C1_TH; ++i) {
-    const int h = h0 + i;
-    if (h >= H) break;
-    const size_t o = (static_cast<size_t>(h) * W + w) * 64 + 8 * j;
-    uint4 u;
-    if (out_tap != nullptr) {
-      u.x = pack_half2(acc[i][0].x, acc[i][0].y);
-      u.y = pack_half2(acc[i][1].x, acc[i][1].y);
-      u.z = pack_half2(acc[i][2].x, acc[i][2].y);
-      u.w = pack_half2(acc[i][3].x, acc[i][3].y);
-      *reinterpret_cast<uint4*>(out_tap + o) = u;
+      for (int i = 0; i < C1_TH; ++i) {
+        const int h = h0 + i;
+        if (h >= H) break;
+        const size_t o = (static_cast<size_t>(h) * W + w) * 64 + 8 * j;
+        uint4 u;
+        if (out_tap != nullptr) {
+          u.x = pack_half2(acc[i][0].x, acc[i][0].y);
+          u.y = pack_half2(acc[i][1].x, acc[i][1].y);
+          u.z = pack_half2(acc[i][2].x, acc[i][2].y);
+          u.w = pack_half2(acc[i][3].x, acc[i][3].y);
+          *reinterpret_cast<uint4*>(out_tap + o) = u;
+        }
+        if (out_act != nullptr) {
+          u.x = pack_half2(fmaxf(acc[i][0].x, 0.f), fmaxf(acc[i][0].y, 0.f));
+          u.y = pack_half2(fmaxf(acc[i][1].x, 0.f), fmaxf(acc[i][1].y, 0.f));
+          u.z = pack_half2(fmaxf(acc[i][2].x, 0.f), fmaxf(acc[i][2].y, 0.f));
+          u.w = pack_half2(fmaxf(acc[i][3].x, 0.f), fmaxf(acc[i][3].y, 0.f));
+          *reinterpret_cast<uint4*>(out_act + o) = u;
+        }
+      }
     }
-    if (out_act != nullptr) {
-      u.x = pack_half2(fmaxf(acc[i][0].x, 0.f), fmaxf(acc[i][0].y, 0.f));
-      u.y = pack_half2(fmaxf(acc[i][1].x, 0.f), fmaxf(acc[i][1].y, 0.f));
-      u.z = pack_half2(fmaxf(acc[i][2].x, 0.f), fmaxf(acc[i][2].y, 0.f));
-      u.w = pack_half2(fmaxf(acc[i][3].x, 0.f), fmaxf(acc[i][3].y, 0.f));
-      *reinterpret_cast<uint4*>(out_act + o) = u;
-    }
+    if (more) stash(buf ^ 1, nxt);  // the other buffer: nobody reads it during this iteration
+    __syncthreads();
   }
 }
 
 cudaError_t launch_conv1_fwd(const float* x, const float* w, const float* b, __half* out_tap, __half* out_act, int H,
                              int W, PixelConsts pc, cudaStream_t s) {
   const int blocks = ((W + C1_TW - 1) / C1_TW) * ((H + C1_TH - 1) / C1_TH);
-  conv1_fwd_kernel<<<blocks, 256, 0, s>>>(x, w, b, out_tap, out_act, H, W, pc);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int grid = blocks < 2 * sms ? blocks : 2 * sms;
+  conv1_fwd_kernel<<<grid, 256, 0, s>>>(x, w, b, out_tap, out_act, H, W, pc);
   return cudaGetLastError();
 }
 
