@@ -9,6 +9,7 @@
 // The [0,1] clamp of run_style_transfer.py:108-109 is folded into the update.
 // No host synchronisation: loop bounds and the stop flag are read from the device control block.
 #include "lbfgs.cuh"
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace nst {
@@ -85,6 +86,9 @@ __global__ void lbfgs_step_begin_kernel(NstLbfgsCtl* ctl) {
 __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuffers b) {
   __shared__ float wpart[LB_THREADS / 32][NST_LBFGS_SLOTS][NST_LBFGS_NDOT];
   __shared__ float wscal[LB_THREADS / 32][NST_LBFGS_NSCAL];
+  // programmatic dependent launch (all four optimizer kernels): scheduled while the previous kernel drains
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const NstLbfgsCtl* ctl = b.ctl;
   if (ctl->stop != NST_RUN) return;
   const int len = ctl->hist_len, head = ctl->hist_head;
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
 
 // one warp per output: sums the per-block partials in fp64 in a fixed order
 __global__ void __launch_bounds__(256) lbfgs_pass1_reduce_kernel(const LbfgsBuffers b) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const NstLbfgsCtl* ctl = b.ctl;
   if (ctl->stop != NST_RUN) return;
   const int lane = threadIdx.x & 31;
@@ -256,6 +262,10 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
                  "l"(b.YY), "r"(BYTES), "r"(smem_u32(bar))
                  : "memory");
   }
+  // the matrices staged above are written by this kernel only (previous iteration); the dot products come from the
+  // reduction kernel: wait for it here, after the 160 KB copy has been issued
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
   if (stage) mbar_wait(bar, 0);
   __syncthreads();
@@ -268,6 +278,8 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
 __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuffers b) {
   __shared__ float coef[NST_LBFGS_NB + 3];
   __shared__ float wmax[LB_THREADS / 32];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const NstLbfgsCtl* ctl = b.ctl;
   if (ctl->run_pass2 == 0) return;
   const int len = ctl->hist_len, head = ctl->hist_head;
@@ -384,25 +396,36 @@ cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  static const bool pdl = getenv("NST_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s) {
-  lbfgs_pass1_kernel<<<b.nblocks, LB_THREADS, 0, s>>>(b);
-  return cudaGetLastError();
+  return launch_pdl(lbfgs_pass1_kernel, b.nblocks, LB_THREADS, 0, s, b);
 }
 cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s) {
   const int warps_per_blk = 8;
-  lbfgs_pass1_reduce_kernel<<<(LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s>>>(b);
-  return cudaGetLastError();
+  return launch_pdl(lbfgs_pass1_reduce_kernel, (LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s, b);
 }
 cudaError_t lbfgs_init() {
   return cudaFuncSetAttribute(lbfgs_control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_CTL_SMEM);
 }
 cudaError_t launch_lbfgs_control(const LbfgsBuffers& b, int mode, cudaStream_t s) {
-  lbfgs_control_kernel<<<1, LB_CTL_THREADS, LB_CTL_SMEM, s>>>(b, mode);
-  return cudaGetLastError();
+  return launch_pdl(lbfgs_control_kernel, 1, LB_CTL_THREADS, LB_CTL_SMEM, s, b, mode);
 }
 cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s) {
-  lbfgs_pass2_kernel<<<b.nblocks, LB_THREADS, 0, s>>>(b);
-  return cudaGetLastError();
+  return launch_pdl(lbfgs_pass2_kernel, b.nblocks, LB_THREADS, 0, s, b);
 }
 
 cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s) {
