@@ -309,7 +309,8 @@ def run_b200(args, rank, world, local_rank):
     lb_kinds = ("lbfgs_pass1", "lbfgs_reduce", "lbfgs_control", "lbfgs_pass2")
     eval_ms = sum(v[0] for k, v in acc.items() if k not in lb_kinds) / n_evals_timed
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient + 5 Gram-backward launches per evaluation)",
+    roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient launches per evaluation, the Gram backward "
+                           "of conv1_1..conv4_1 folded into the data gradients as a second accumulator, + 1 Gram-backward launch for conv5_1)",
                     achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
                     traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the 29 launches of one evaluation (ncu --set full, profiles/r01b_ncu_full_conv_tc_summary.csv)",
                     peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",

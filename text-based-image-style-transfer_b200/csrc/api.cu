@@ -20,6 +20,7 @@
 
 #include <vector>
 
+#include "common.cuh"
 #include "conv_chain.cuh"
 #include "conv_tc.cuh"
 #include "gram.cuh"
@@ -200,6 +201,8 @@ struct nst_plan {
   float* img_dev = nullptr;
   float* gate_dev = nullptr;
   float* pooled_dev = nullptr;
+  // seed_folded[i]: the Gram backward of style layer conv i runs inside the data gradient of conv i+1 (no launch of its own)
+  bool seed_folded[NST_MAX_CONV] = {};
   // chained convolution launches (conv_chain.cu): [0] forward conv1_2.., [1] Gram backward + data gradients
   bool chain = false;
   ChainLayer* chain_dev[2] = {};
@@ -365,6 +368,27 @@ static int build_conv_params(nst_plan* p) {
     if (tma_out) {
       if (make_tmap_out(&c.tmO0, c.out_grad, c.H, c.W, C, 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (seed out %d)", i);
       c.tma_out = 1;
+    }
+  }
+  // ---- fold the Gram backward of a style layer into the data gradient that produces that layer's gradient
+  // (conv_tc.cuh: seed_k).  Not for the deepest conv (its seed IS the first gradient), not when the layer is also a
+  // content layer (that seed is accumulated by the content kernel), not with N tiles above 128 (tensor memory).
+  for (int i = 0; i < NST_MAX_CONV; ++i) p->seed_folded[i] = false;
+  if (!p->chain && getenv("NST_NO_SEED_FOLD") == nullptr) {
+    for (int l = 0; l < p->n_style; ++l) {
+      const int j = p->style_conv[l];      // style layer conv j; its gradient gpre[j] is produced by dgrad[j + 1]
+      const int i = j + 1;
+      if (j == p->n_layers - 1 || i >= p->n_layers || kPoolAfter[j] || content_index(p, j) >= 0) continue;
+      ConvParams& d = p->dgrad[i];
+      if (d.block_n > 128 || d.route != nullptr) continue;
+      const int C = kCout[j];
+      if (make_tmap_act(&d.tmA2, p->tap[j], d.H, d.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d, folded)", j);
+      if (make_tmap_wgt(&d.tmB2, p->dh[l], 1, C, C, d.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
+      d.seed_k = C;
+      d.idesc2 = umma_idesc_f16(128, d.block_n, 0, 0, 0);
+      d.alpha = p->alpha + l;
+      d.addend = nullptr;
+      p->seed_folded[j] = true;
     }
   }
   return NST_OK;
@@ -1191,6 +1215,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       // the main stream instead of the first data gradients; all seeds are awaited together before conv4_2's data gradient
       for (int l = 0; l < n_shallow; ++l) {
         const int i = p->style_conv[l];
+        if (p->seed_folded[i]) continue;  // computed inside the data gradient of conv i+1
         TB(NST_K_GRAM_BWD);
         CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
         ++nl;

@@ -236,7 +236,8 @@ __device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x,
 
 // data-gradient epilogue for DG_CH channels of one pixel
 __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[DG_CH], int h, int w, int n, bool valid,
-                                               const DgradAux& x, EpiStore* st = nullptr) {
+                                               const DgradAux& x, EpiStore* st = nullptr,
+                                               const float* seed = nullptr /* DG_CH values: folded Gram backward, already scaled */) {
   if (!valid && st == nullptr) return;  // with TMA stores every lane takes part (the box is clipped at the border)
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
@@ -250,6 +251,10 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[D
         if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
         if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
       }
+    }
+    if (seed != nullptr) {
+#pragma unroll
+      for (int j = 0; j < DG_CH; ++j) v[j] += seed[j];
     }
     if (p.addend != nullptr) {
 #pragma unroll

@@ -57,6 +57,8 @@ struct ConvCfg {
   static constexpr int B_STAGES_FIT = (SMEM_BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
   static constexpr int B_STAGES = B_STAGES_FIT > 6 ? 6 : B_STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
+  // data gradient with a folded Gram backward: two more accumulator stages (columns 2N .. 4N)
+  static constexpr int TMEM_COLS_SEED = (BLOCK_N >= 64 && BLOCK_N <= 128) ? 4 * BLOCK_N : TMEM_COLS;
   static constexpr int OPERAND_BYTES = HALO_STAGES * HALO_STAGE_BYTES + B_STAGES * B_STAGE_BYTES;
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one bias slice per accumulator stage
   // staging for the epilogue's TMA stores: two 2 KB buffers per epilogue warp, 1024-byte aligned
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_slot, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -163,7 +165,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   // is then loaded once per CTA and stays resident - re-streaming it for every tile (72 KB next to a 23 KB patch at
   // N = 64) made the 64-channel layers L2-bandwidth bound (148 SMs x ~96 KB per microsecond).  All tiles of a launch
   // must then use the same weights: one N tile only.
-  const bool b_resident = p.taps == 9 && k_slices == 1 && 9 / Cfg::TPS <= Cfg::B_STAGES && p.tiles_n == 1;
+  const bool seed = MODE == CONV_DGRAD && Cfg::TMEM_COLS_SEED == 4 * BLOCK_N && p.seed_k > 0;
+  const int seed_slices = seed ? p.seed_k / BLOCK_K : 0;
+  const bool b_resident = p.taps == 9 && k_slices == 1 && 9 / Cfg::TPS <= Cfg::B_STAGES && p.tiles_n == 1 && !seed;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -193,6 +197,23 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
               bs = 0;
               bphase ^= 1u;
             }
+          }
+        }
+        // folded Gram backward: the tile of the tap (no halo) and the matching slice of dh, one 64-channel slice at a time
+        for (int ks2 = 0; ks2 < seed_slices; ++ks2) {
+          NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
+          mbar_arrive_expect_tx(&afull_bar[as], FLAT_TX_BYTES);
+          tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA2, &afull_bar[as], ks2 * BLOCK_K, w0, h0);
+          if (++as == Cfg::HALO_STAGES) {
+            as = 0;
+            aphase ^= 1u;
+          }
+          NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
+          mbar_arrive_expect_tx(&bfull_bar[bs], Cfg::B_TILE_BYTES);
+          tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB2, &bfull_bar[bs], ks2 * BLOCK_K, n0, 0);
+          if (++bs == Cfg::B_STAGES) {
+            bs = 0;
+            bphase ^= 1u;
           }
         }
       }
@@ -283,7 +304,38 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           aphase ^= 1u;
         }
       }
-      umma_commit(&tfull_bar[ts]);  // accumulator complete
+      if (seed) {
+        // second accumulator of this stage: seed[pixel, n] = sum_k tap[pixel, k] * dh[n, k]  (fp16 operands)
+        const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>((2 + ts) * BLOCK_N);
+        const uint32_t a_hi2 = static_cast<uint32_t>(umma_desc_sw128(0, 16, TILE_W * 128u) >> 32);
+        const uint32_t idesc2 = p.idesc2;
+        uint32_t acc2 = 0;
+        for (int ks2 = 0; ks2 < seed_slices; ++ks2) {
+          NST_WAIT(wacc0, mbar_wait(&afull_bar[as], aphase));
+          NST_WAIT(wacc1, mbar_wait(&bfull_bar[bs], bphase));
+          tc_fence_after();
+          const uint32_t a_lo0 = lbo_lo | (smem_u32(sA + as * HALO_STAGE_BYTES) >> 4);
+          const uint32_t b_lo0 = lbo_lo | (smem_u32(sB + bs * Cfg::B_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = (static_cast<uint64_t>(a_hi2) << 32) | (a_lo0 + static_cast<uint32_t>(k * 2));
+            const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + static_cast<uint32_t>(k * 2));
+            umma_f16(d2_tmem, da, db, idesc2, acc2);
+            acc2 = 1u;
+          }
+          umma_commit(&bempty_bar[bs]);
+          if (++bs == Cfg::B_STAGES) {
+            bs = 0;
+            bphase ^= 1u;
+          }
+          umma_commit(&aempty_bar[as]);
+          if (++as == Cfg::HALO_STAGES) {
+            as = 0;
+            aphase ^= 1u;
+          }
+        }
+      }
+      umma_commit(&tfull_bar[ts]);  // accumulator(s) complete
       NST_STAMP(3, tile == blockIdx.x);
       if (++ts == 2) {
         ts = 0;
@@ -313,7 +365,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     int ts = 0;
     uint32_t tphase = 0;
     float alpha = 0.f;
-    if (MODE == CONV_SCALE) alpha = __ldg(p.alpha);
+    if (MODE == CONV_SCALE || seed) alpha = __ldg(p.alpha);
     // Data-gradient epilogue operands (ReLU mask + tap seed, or pool routing bytes; for conv1_1 the pixel-term gradient)
     // do not depend on the accumulator.  All chunks of a tile are requested together when they fit in registers
     // (<= 4 chunks), and for narrow tiles (<= 2 chunks, and conv1_1) the NEXT tile's operands are requested before the
@@ -400,7 +452,17 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             float v[DG_CH];
 #pragma unroll
             for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[c], st);
+            if (seed) {
+              uint32_t r2[DG_CH];
+              tmem_ld16(taddr + 2 * BLOCK_N + c * DG_CH, r2);
+              tmem_ld_wait();
+              float sv[DG_CH];
+#pragma unroll
+              for (int j = 0; j < DG_CH; ++j) sv[j] = alpha * __uint_as_float(r2[j]);
+              epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[c], st, sv);
+            } else {
+              epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[c], st);
+            }
           }
         } else {
 #pragma unroll 1
@@ -412,7 +474,17 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             float v[DG_CH];
 #pragma unroll
             for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[0], st);
+            if (seed) {
+              uint32_t r2[DG_CH];
+              tmem_ld16(taddr + 2 * BLOCK_N + c * DG_CH, r2);
+              tmem_ld_wait();
+              float sv[DG_CH];
+#pragma unroll
+              for (int j = 0; j < DG_CH; ++j) sv[j] = alpha * __uint_as_float(r2[j]);
+              epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[0], st, sv);
+            } else {
+              epilogue_dgrad(p, v, h, w, n0 + col0 + c * DG_CH, valid, aux[0], st);
+            }
             aux[0] = aux_nxt;
           }
         }
@@ -453,7 +525,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
   }
   NST_STAMP(6, threadIdx.x == 64);
   if (p.dbg != nullptr && threadIdx.x == 64) p.dbg[16 + blockIdx.x] = clock64() - life0;  // lifetime of every CTA

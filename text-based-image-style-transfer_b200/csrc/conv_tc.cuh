@@ -32,6 +32,14 @@ struct ConvParams {
   CUtensorMap tmO0;
   CUtensorMap tmO1;
   int tma_out;
+  // CONV_DGRAD with the Gram backward of the produced layer folded in (seed_k > 0): after the 3x3 main loop the tile
+  // also accumulates tap[pixel, :] x dh[n, :] (1x1, fp16, K = seed_k) into a second accumulator, and the epilogue adds
+  // alpha * that to the masked gradient - instead of a separate 1x1 launch that writes the seed tensor and an epilogue
+  // that reads it back.  tmA2 = the layer's pre-ReLU tap [H][W][C] (box 64 x 8 x 16), tmB2 = dh [1][C][C].
+  CUtensorMap tmA2;
+  CUtensorMap tmB2;
+  int seed_k;
+  uint32_t idesc2;
   int H, W;        // pixel grid of the GEMM M dimension
   int K, N;        // channels contracted per tap, output channels
   int taps;        // 9 (3x3, pad 1) or 1 (1x1)
