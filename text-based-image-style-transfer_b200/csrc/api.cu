@@ -1117,7 +1117,16 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   // grouped timing: the side launches that normally sit between forward convolutions are issued after the last one, so
   // that the twelve forward launches form one uninterrupted run
   const bool grouped = tm != nullptr && tm->grouped;
-  const int at_shallow = grouped && max_shallow > 0 ? last : max_shallow;
+  // When does the shallow layers' Gram launch go out (side stream)?  0 (default): right after its last tap (conv4_1); its
+  // ~150 CTAs then push one 128-tile convolution into a second wave (conv4_4: 36 us instead of 18).  1: after the
+  // second-to-last forward convolution - it then delays the deepest layer's Gram chain by as much.  2: after the deepest
+  // layer's Gram launches - it then collides with a 128-tile data gradient.  Measured at 512^2: 1228 / 1230 / 1172
+  // evaluations/s; the work has to overlap something, so the simplest schedule stays.
+  static const int gram_when = getenv("NST_GRAM_WHEN") ? atoi(getenv("NST_GRAM_WHEN")) : 0;
+  const bool can_delay = max_shallow > 0 && last - 1 > max_shallow && deep_style;
+  const int late_at = !can_delay || gram_when == 0 ? max_shallow : (gram_when == 1 ? last - 1 : last + 100);
+  const bool shallow_after_deep = can_delay && gram_when == 2 && !grouped;
+  const int at_shallow = grouped && max_shallow > 0 ? last : late_at;
   const int at_content = grouped && max_content > 0 ? last : max_content;
 
   auto content_launch = [&](int l, int accumulate, cudaStream_t st) -> cudaError_t {
@@ -1153,8 +1162,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
         // ---- side: Gram, style MSE and backward operand of the shallower style layers
         CK(edge(EV_TAPS, s, s2));
         TB(NST_K_GRAM);
-        TB(NST_K_GRAM);
-      CK(launch_gram(p->gram_shallow, s2));
+        CK(launch_gram(p->gram_shallow, s2));
         nl += 3;
         TM(NST_K_GRAM, 0);
       }
@@ -1191,6 +1199,13 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       CK(launch_gram(p->gram_deep, s));
       nl += 3;
       TM(NST_K_GRAM, last);
+    }
+    if (shallow_after_deep) {
+      CK(edge(EV_TAPS, s, s2));
+      TB(NST_K_GRAM);
+      CK(launch_gram(p->gram_shallow, s2));
+      nl += 3;
+      TM(NST_K_GRAM, 0);
     }
     for (int l = 0; l < p->n_content; ++l) {
       if (p->content_conv[l] != last) continue;
