@@ -321,21 +321,30 @@ int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C) {
 }
 
 size_t gram_plan(GramParams& p, int target_ctas) {
-  long long total_units = 0;
+  // Work is balanced by operand bytes, not by (block pair, K chunk) units: a diagonal block of a >= 128-channel layer
+  // loads two 8 KB boxes per chunk, an off-diagonal one four, conv1_1 (64 channels) a single one - with equal unit counts
+  // the conv4_1 items moved three times the bytes of the conv1_1 items and set the duration of the whole launch.
+  long long total_boxes = 0;
+  long long layer_boxes[GRAM_MAX_LAYERS];
   for (int l = 0; l < p.num_layers; ++l) {
     GramLayer& L = p.L[l];
     L.nblk = (L.C + 127) / 128;
     L.pairs = L.nblk * (L.nblk + 1) / 2;
     L.bn = L.C < 128 ? L.C : 128;
     L.chunks = (L.HW + G_KCHUNK - 1) / G_KCHUNK;
-    total_units += static_cast<long long>(L.pairs) * L.chunks;
+    const int a_boxes = L.C >= 128 ? 2 : 1;
+    const int off_pairs = L.pairs - L.nblk;
+    // boxes per K chunk over all pairs of the layer: diagonal pairs load A only, off-diagonal pairs A and B
+    layer_boxes[l] = static_cast<long long>(L.chunks) * (static_cast<long long>(L.nblk) * a_boxes + static_cast<long long>(off_pairs) * (a_boxes + L.bn / 64));
+    total_boxes += layer_boxes[l];
   }
-  const long long per_cta = (total_units + target_ctas - 1) / target_ctas;
+  const long long per_cta = (total_boxes + target_ctas - 1) / target_ctas;  // boxes one CTA should move
   int item = 0, fin = 0;
   size_t ws = 0;
   for (int l = 0; l < p.num_layers; ++l) {
     GramLayer& L = p.L[l];
-    long long s = (L.chunks + per_cta - 1) / (per_cta > 0 ? per_cta : 1);
+    // items of this layer = pairs x splits, each moving layer_boxes / (pairs x splits) boxes on average
+    long long s = (layer_boxes[l] + per_cta * L.pairs - 1) / ((per_cta > 0 ? per_cta : 1) * L.pairs);
     if (s < 1) s = 1;
     if (s > L.chunks) s = L.chunks;
     L.splits = static_cast<int>(s);
