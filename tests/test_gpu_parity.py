@@ -428,3 +428,24 @@ def test_config5_video_frames_match_single_image_runs(nst, rst, oracle):
             single = nst.run_multi_style_transfer(torch.tensor(O.VGG_MEAN), torch.tensor(O.VGG_STD), Image.fromarray(frames[k].numpy()),
                                                   20, False, style_img1=Image.fromarray(style), device="cuda", **O.APP_WEIGHTS)
         assert np.array_equal(np.asarray(single), out[k].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ optional code paths
+@pytest.mark.parametrize("env", [
+    {"NST_CHAIN": "1"},                                    # chained launches with tile-level dataflow (conv_chain.cu)
+    {"NST_DIRECT_STORES": "1", "NST_NO_SEED_FOLD": "1"},   # per-thread stores, Gram backward as separate 1x1 launches
+    {"NST_NO_PDL": "1", "NST_NO_SIDE_STREAM": "1"},        # no programmatic dependent launch, single stream
+], ids=["chain", "direct-stores-unfolded", "no-pdl-single-stream"])
+def test_optional_paths_stay_parity_green(env):
+    """The schedule / epilogue variants that are switched by environment variables (read when the library or a plan is
+    created, hence a fresh process) must give the same answers: __graft_entry__.smoke() checks step-0 losses and
+    gradient and a 20-evaluation run against the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "smoke ok" in r.stdout
