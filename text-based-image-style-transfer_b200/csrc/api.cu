@@ -69,6 +69,7 @@ extern "C" int nst_device_check(void) {
   if (g_num_sms == 0) {
     e = conv_tc_init();
     if (e == cudaSuccess) e = conv_chain_init();
+    if (e == cudaSuccess) e = conv1_tc_init();
     if (e == cudaSuccess) e = gram_init();
     if (e == cudaSuccess) e = lbfgs_init();
     if (e != cudaSuccess) return fail(NST_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(e));
@@ -267,6 +268,27 @@ static int build_conv_params(nst_plan* p) {
   const nst_net* net = p->net;
   // epilogue outputs through shared memory + TMA stores (conv_epilogue.cuh); NST_DIRECT_STORES=1 keeps the per-thread stores
   const bool tma_out = getenv("NST_DIRECT_STORES") == nullptr;
+  {
+    // ---- conv1_1 forward on tensor cores (conv1_tc.cu): only the epilogue half of ConvParams is used
+    ConvParams& f = p->fwd[0];
+    memset(&f, 0, sizeof(f));
+    f.H = p->H;
+    f.W = p->W;
+    f.K = 64;
+    f.N = 64;
+    f.taps = 9;
+    f.block_n = 64;
+    f.bias = net->b32[0];
+    f.out_tap = p->tap[0];
+    f.out_act = p->n_layers > 1 ? p->act[0] : nullptr;
+    conv_finalize_params(f, CONV_FWD);
+    f.dbg_flags = getenv("NST_DBG_CONV1") ? atoi(getenv("NST_DBG_CONV1")) : 0;  // timing experiments only
+    if (tma_out && getenv("NST_CONV1_CUDA_CORES") == nullptr) {
+      if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, p->H, p->W, 64, 64, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out 0)");
+      if (f.out_act && make_tmap_out(&f.tmO1, f.out_act, p->H, p->W, 64, 64, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (act out 0)");
+      f.tma_out = 1;
+    }
+  }
   for (int i = 1; i < p->n_layers; ++i) {
     const int lv = kLevel[i];
     const int H = p->lh[lv], W = p->lw[lv];
@@ -727,10 +749,17 @@ extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content,
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// conv1_1 forward: tcgen05 with fp16 high/low operand splitting (conv1_tc.cu), or the fp32 CUDA-core kernel (pixel.cu)
+// when the TMA output maps are switched off (NST_DIRECT_STORES / NST_CONV1_CUDA_CORES)
+static cudaError_t conv1_forward(nst_plan* p, const float* x, cudaStream_t s) {
+  if (p->fwd[0].tma_out) return launch_conv1_tc(p->fwd[0], x, p->net->w32[0], p->pc, g_num_sms, s);
+  return launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s);
+}
+
 static int forward_enqueue(nst_plan* p, const float* x, cudaStream_t s) {
   const nst_net* net = p->net;
   if (p->chain) CK(cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s));
-  CK(launch_conv1_fwd(x, net->w32[0], net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+  CK(conv1_forward(p, x, s));
   if (p->chain) {
     CK(launch_conv_chain(p->chain_dev[0], p->chain_layers[0], p->chain_items[0], g_num_sms, s));
     return NST_OK;
@@ -997,7 +1026,7 @@ static int eval_enqueue_chain(nst_plan* p, const float* x, float* grad, int* cou
   TM(NST_K_PIXEL, -1);
   // ---- main: VGG forward
   CK(cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s));
-  CK(launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+  CK(conv1_forward(p, x, s));
   ++nl;
   TM(NST_K_CONV1_FWD, 0);
   CK(launch_conv_chain(p->chain_dev[0], p->chain_layers[0], p->chain_items[0], g_num_sms, s));
@@ -1150,7 +1179,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   if (use_vgg) {
     // ---- main: VGG forward
     TB(NST_K_CONV1_FWD);
-    CK(launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s));
+    CK(conv1_forward(p, x, s));
     TM(NST_K_CONV1_FWD, 0);
     if (max_shallow == 0) CK(edge(EV_TAPS, s, s2));
     if (max_content == 0) CK(edge(EV_CONTENT_IN, s, s2));
@@ -1419,7 +1448,7 @@ static int step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stre
 // timestamps of CTA 0 -> out[7] (SM clock): 0 start, 1 setup done, 2 first operands landed, 3 last MMA issued,
 // 4 accumulator complete, 5 epilogue done, 6 exit.
 extern "C" int nst_plan_conv_phases(nst_plan* p, int conv, int mode, long long* out7, void* stream) {
-  if (!p || conv < (mode == 1 ? 0 : 1) || conv >= p->n_layers || !out7) return fail(NST_ERR_ARG, "nst_plan_conv_phases: bad arguments");
+  if (!p || conv < 0 || conv >= p->n_layers || !out7) return fail(NST_ERR_ARG, "nst_plan_conv_phases: bad arguments");
   if (mode == 1 && !p->with_grad) return fail(NST_ERR_STATE, "plan has no gradient buffers");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long* d = nullptr;
@@ -1435,7 +1464,12 @@ extern "C" int nst_plan_conv_phases(nst_plan* p, int conv, int mode, long long* 
     c.out_pix = p->lb.g != nullptr ? p->lb.g : p->grad_pix;
     for (int k = 0; k < 3; ++k) c.inv_std[k] = 1.f / p->pc.stdv[k];
   }
-  if (e == cudaSuccess) e = launch_conv_tc(c, mode == 0 ? CONV_FWD : (conv == 0 ? CONV_DGRAD_PIX : CONV_DGRAD), g_num_sms, s);
+  if (mode == 0 && conv == 0) {
+    c.tl = nullptr;
+    if (e == cudaSuccess) e = c.tma_out ? launch_conv1_tc(c, p->lb.x != nullptr ? p->lb.x : p->grad_pix, p->net->w32[0], p->pc, g_num_sms, s) : cudaErrorNotSupported;
+  } else if (e == cudaSuccess) {
+    e = launch_conv_tc(c, mode == 0 ? CONV_FWD : (conv == 0 ? CONV_DGRAD_PIX : CONV_DGRAD), g_num_sms, s);
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, (16 + 160) * sizeof(long long), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(d);

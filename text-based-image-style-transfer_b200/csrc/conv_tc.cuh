@@ -76,7 +76,7 @@ struct ConvParams {
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
 int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n);
-// output map for the epilogue's TMA stores: [H][W][C] 16-bit tensor, box (box_c, box_w, box_h); box_c * 2 = 64 or 32 bytes
+// output map for the epilogue's TMA stores: [H][W][C] 16-bit tensor, box (box_c, box_w, box_h); box_c * 2 = 128, 64 or 32 bytes
 int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 // filter taps the kernel loads per weight stage for this N tile (the depth of the weight tensor map's box)
 int conv_taps_per_stage(int block_n, int taps);
@@ -89,5 +89,11 @@ void conv_finalize_params(ConvParams& p, int mode);
 cudaError_t conv_tc_init();
 // enqueue
 cudaError_t launch_conv_tc(const ConvParams& p, int mode, int num_sms, cudaStream_t stream);
+
+// conv1_1 forward on tensor cores (conv1_tc.cu): p = forward ConvParams of conv1_1 (N = 64, TMA output maps), x = [3][H][W]
+// fp32 image, w = [64][27] fp32 weights.  PixelConsts: pixel.cuh.
+struct PixelConsts;
+cudaError_t conv1_tc_init();
+cudaError_t launch_conv1_tc(const ConvParams& p, const float* x, const float* w, PixelConsts pc, int num_sms, cudaStream_t stream);
 
 }  // namespace nst

@@ -26,6 +26,10 @@ buf = (C.c_longlong * 176)()
 names = ["setup", "first operands", "main loop (issue)", "drain -> acc ready", "epilogue", "teardown"]
 print("%-10s %s  total | waits of CTA 0 (us): MMA patch / weights / acc stage, epilogue acc, producer patch / weight stage" % ("launch", "  ".join("%18s" % n for n in names)))
 with torch.cuda.stream(sess.stream):
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nst_b200._lib.check(lib.nst_plan_conv_phases(sess.plan.handle, 0, 0, buf, C.c_void_p(sess.stream.cuda_stream)))
+    print("conv1_1 forward (tensor cores), CTA 0, us: build %.1f  wait stage %.1f  write+fence %.1f  stash+barrier %.1f | epilogue group 0 waits for accumulator %.1f" % tuple(x / 1.965e3 for x in list(buf)[:5]))
     for mode, tag in ((0, "fwd"), (1, "dgrad")):
         for conv in range(0 if mode == 1 else 1, 13):
             for rep in range(2):
