@@ -141,40 +141,59 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   warp_reduce8(sc, lane);
   if ((lane & 3) == 0) wscal[warp][lane >> 2] = (lane >> 2) == 6 ? gmax : sc[0];
 
-  // software pipeline over the stored pairs: the loads of pair i+1 are in flight while pair i is reduced
-  float4 na[LB_VEC_PER_THREAD], nc[LB_VEC_PER_THREAD];
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto load_pair = [&](int i) {
+  // The stored pairs stream through a ring of LB_RING shared-memory stages filled by bulk copies (see pass 2)
+  extern __shared__ __align__(128) uint8_t lb_smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lb_smem);
+  uint64_t* empty_bar = full_bar + LB_RING;
+  uint8_t* ring = lb_smem + 128;
+  const uint32_t pair_bytes = static_cast<uint32_t>(row) * 8u;  // S row + Y row
+  const uint32_t stage_bytes = (pair_bytes + 127u) & ~127u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LB_RING; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], LB_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int i) {  // thread 0: pair i (age order) -> stage i % LB_RING
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
-    const float* Sp = hblk + (2 * p) * row;
-    const float* Yp = Sp + row;
-#pragma unroll
-    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      na[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z4;
-      nc[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z4;
-    }
+    const int st = i % LB_RING;
+    mbar_arrive_expect_tx(&full_bar[st], pair_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(ring + st * stage_bytes)),
+                 "l"(hblk + static_cast<size_t>(2 * p) * row), "r"(pair_bytes), "r"(smem_u32(&full_bar[st]))
+                 : "memory");
   };
-  if (len > 0) load_pair(0);
+  if (threadIdx.x == 0)
+    for (int i = 0; i < LB_RING && i < len; ++i) issue(i);
   for (int i = 0; i < len; ++i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
-    float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      a4[k] = na[k];
-      c4[k] = nc[k];
+    const int st = i % LB_RING;
+    const uint32_t ph = static_cast<uint32_t>(i / LB_RING) & 1u;
+    if (threadIdx.x == 0 && i >= 1 && i - 1 + LB_RING < len) {
+      mbar_wait(&empty_bar[(i - 1) % LB_RING], static_cast<uint32_t>((i - 1) / LB_RING) & 1u);
+      issue(i - 1 + LB_RING);
     }
-    if (i + 1 < len) load_pair(i + 1);
+    mbar_wait(&full_bar[st], ph);
+    const float* Sp = reinterpret_cast<const float*>(ring + st * stage_bytes);
+    const float* Yp = Sp + row;
     // S_p.y  S_p.g  Y_p.y  Y_p.g : all the recursion needs (lbfgs_ctl.h)
     float r[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      r[0] = dot4(a4[k], y4[k], r[0]);
-      r[1] = dot4(a4[k], g4[k], r[1]);
-      r[2] = dot4(c4[k], y4[k], r[2]);
-      r[3] = dot4(c4[k], g4[k], r[3]);
+      if (!ok[k]) continue;
+      const float4 a4 = ld4(Sp + hoff[k]);
+      const float4 c4 = ld4(Yp + hoff[k]);
+      r[0] = dot4(a4, y4[k], r[0]);
+      r[1] = dot4(a4, g4[k], r[1]);
+      r[2] = dot4(c4, y4[k], r[2]);
+      r[3] = dot4(c4, g4[k], r[3]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
     warp_reduce4(r, lane);
     if ((lane & 7) == 0) wpart[warp][p][lane >> 3] = r[0];
   }
@@ -313,40 +332,61 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
       acc[i] = make_float4(cg * g.x, cg * g.y, cg * g.z, cg * g.w);
     }
   }
-  // software pipeline over the stored pairs (as in pass 1): the loads of pair i+1 are in flight while pair i is consumed
-  float4 na[LB_VEC_PER_THREAD], nc[LB_VEC_PER_THREAD];
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto load_pair = [&](int i) {
+  // The stored pairs stream through a ring of LB_RING shared-memory stages filled by bulk copies (cp.async.bulk, one
+  // 2 x row copy per pair: S_p and Y_p are adjacent in the chunk-major history): four pairs (~85 KB) per block are in
+  // flight instead of the two a register pipeline can hold, which is what a pure read stream needs to saturate HBM.
+  extern __shared__ __align__(128) uint8_t lb_smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lb_smem);
+  uint64_t* empty_bar = full_bar + LB_RING;
+  uint8_t* ring = lb_smem + 128;
+  const uint32_t pair_bytes = static_cast<uint32_t>(row) * 8u;  // S row + Y row
+  const uint32_t stage_bytes = (pair_bytes + 127u) & ~127u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LB_RING; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], LB_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int i) {  // thread 0: pair i (age order) -> stage i % LB_RING
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
-    const float* Sp = hblk + (2 * p) * row;
-    const float* Yp = Sp + row;
-#pragma unroll
-    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      na[k] = ok[k] ? ld4_stream(Sp + hoff[k]) : z4;
-      nc[k] = ok[k] ? ld4_stream(Yp + hoff[k]) : z4;
-    }
+    const int st = i % LB_RING;
+    mbar_arrive_expect_tx(&full_bar[st], pair_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(ring + st * stage_bytes)),
+                 "l"(hblk + static_cast<size_t>(2 * p) * row), "r"(pair_bytes), "r"(smem_u32(&full_bar[st]))
+                 : "memory");
   };
-  if (len > 0) load_pair(0);
-#pragma unroll 2
+  if (threadIdx.x == 0)
+    for (int i = 0; i < LB_RING && i < len; ++i) issue(i);
   for (int i = 0; i < len; ++i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    const int st = i % LB_RING;
+    const uint32_t ph = static_cast<uint32_t>(i / LB_RING) & 1u;
+    // refill the stage consumed one iteration ago (every warp has had a full iteration to release it)
+    if (threadIdx.x == 0 && i >= 1 && i - 1 + LB_RING < len) {
+      mbar_wait(&empty_bar[(i - 1) % LB_RING], static_cast<uint32_t>((i - 1) / LB_RING) & 1u);
+      issue(i - 1 + LB_RING);
+    }
     const float cs = coef[p], cy = coef[NST_LBFGS_SLOTS + p];
-    float4 a4[LB_VEC_PER_THREAD], c4[LB_VEC_PER_THREAD];
+    mbar_wait(&full_bar[st], ph);
+    const float* Sp = reinterpret_cast<const float*>(ring + st * stage_bytes);
+    const float* Yp = Sp + row;
 #pragma unroll
     for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      a4[k] = na[k];
-      c4[k] = nc[k];
+      if (!ok[k]) continue;
+      const float4 a4 = ld4(Sp + hoff[k]);
+      const float4 c4 = ld4(Yp + hoff[k]);
+      acc[k].x = fmaf(cs, a4.x, fmaf(cy, c4.x, acc[k].x));
+      acc[k].y = fmaf(cs, a4.y, fmaf(cy, c4.y, acc[k].y));
+      acc[k].z = fmaf(cs, a4.z, fmaf(cy, c4.z, acc[k].z));
+      acc[k].w = fmaf(cs, a4.w, fmaf(cy, c4.w, acc[k].w));
     }
-    if (i + 1 < len) load_pair(i + 1);
-#pragma unroll
-    for (int k = 0; k < LB_VEC_PER_THREAD; ++k) {
-      acc[k].x = fmaf(cs, a4[k].x, fmaf(cy, c4[k].x, acc[k].x));
-      acc[k].y = fmaf(cs, a4[k].y, fmaf(cy, c4[k].y, acc[k].y));
-      acc[k].z = fmaf(cs, a4[k].z, fmaf(cy, c4[k].z, acc[k].z));
-      acc[k].w = fmaf(cs, a4[k].w, fmaf(cy, c4[k].w, acc[k].w));
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
   }
   float mtd = 0.f;
 #pragma unroll
@@ -387,6 +427,12 @@ void lbfgs_plan(LbfgsBuffers& b, int num_sms) {
   b.vec_per_blk = (nv + nblocks - 1) / nblocks;
 }
 
+// dynamic shared memory of the streaming passes: barriers + LB_RING stages of one (s, y) pair of a block's chunk
+size_t lbfgs_ring_bytes(const LbfgsBuffers& b) {
+  const size_t pair_bytes = static_cast<size_t>(b.vec_per_blk) * 32;
+  return 128 + LB_RING * ((pair_bytes + 127) & ~static_cast<size_t>(127));
+}
+
 size_t lbfgs_hist_floats(const LbfgsBuffers& b) {
   return static_cast<size_t>(b.nblocks) * (2 * NST_LBFGS_SLOTS) * static_cast<size_t>(b.vec_per_blk) * 4;
 }
@@ -412,20 +458,24 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s) {
-  return launch_pdl(lbfgs_pass1_kernel, b.nblocks, LB_THREADS, 0, s, b);
+  return launch_pdl(lbfgs_pass1_kernel, b.nblocks, LB_THREADS, lbfgs_ring_bytes(b), s, b);
 }
 cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s) {
   const int warps_per_blk = 8;
   return launch_pdl(lbfgs_pass1_reduce_kernel, (LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s, b);
 }
 cudaError_t lbfgs_init() {
-  return cudaFuncSetAttribute(lbfgs_control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_CTL_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(lbfgs_control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_CTL_SMEM);
+  const int ring_max = 128 + LB_RING * LB_MAX_VEC_PER_BLOCK * 32;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lbfgs_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lbfgs_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_max);
+  return e;
 }
 cudaError_t launch_lbfgs_control(const LbfgsBuffers& b, int mode, cudaStream_t s) {
   return launch_pdl(lbfgs_control_kernel, 1, LB_CTL_THREADS, LB_CTL_SMEM, s, b, mode);
 }
 cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s) {
-  return launch_pdl(lbfgs_pass2_kernel, b.nblocks, LB_THREADS, 0, s, b);
+  return launch_pdl(lbfgs_pass2_kernel, b.nblocks, LB_THREADS, lbfgs_ring_bytes(b), s, b);
 }
 
 cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s) {

@@ -7,7 +7,8 @@
 namespace nst {
 
 static constexpr int LB_THREADS = 256;
-static constexpr int LB_VEC_PER_THREAD = 4;                        // float4 per thread per vector
+static constexpr int LB_VEC_PER_THREAD = 3;                        // float4 per thread per vector
+static constexpr int LB_RING = 4;                                  // stored pairs in flight per block (shared-memory stages)
 static constexpr int LB_MAX_VEC_PER_BLOCK = LB_THREADS * LB_VEC_PER_THREAD;
 static constexpr int LB_PART_STRIDE = NST_LBFGS_SLOTS * NST_LBFGS_NDOT + NST_LBFGS_NSCAL;  // floats per block in pass-1 partials
 static constexpr int LB_CTL_THREADS = 512;
