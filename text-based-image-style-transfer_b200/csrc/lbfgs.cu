@@ -86,11 +86,16 @@ __global__ void lbfgs_step_begin_kernel(NstLbfgsCtl* ctl) {
 __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuffers b) {
   __shared__ float wpart[LB_THREADS / 32][NST_LBFGS_SLOTS][NST_LBFGS_NDOT];
   __shared__ float wscal[LB_THREADS / 32][NST_LBFGS_NSCAL];
-  // programmatic dependent launch (all four optimizer kernels): scheduled while the previous kernel drains
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Programmatic dependent launch (all four optimizer kernels): scheduled while the previous kernel drains.  The control
+  // block and the stored pairs were written by earlier optimizer kernels (complete: every kernel of the chain waits for
+  // its predecessor), only the gradient comes from the kernel right before this one - so the ring of stored pairs is
+  // primed BEFORE griddepcontrol.wait, while the last data-gradient kernel is still running.
   const NstLbfgsCtl* ctl = b.ctl;
-  if (ctl->stop != NST_RUN) return;
+  if (ctl->stop != NST_RUN) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    return;
+  }
   const int len = ctl->hist_len, head = ctl->hist_head;
   const bool first = ctl->n_iter == 0;
   const float t = static_cast<float>(ctl->t);
@@ -102,6 +107,36 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   const int v1 = min(nv, v0 + b.vec_per_blk);
   const size_t row = static_cast<size_t>(b.vec_per_blk) * 4;  // floats per (slot, s|y) row of this block's region
   float* hblk = b.hist + static_cast<size_t>(blockIdx.x) * (2 * NST_LBFGS_SLOTS) * row;
+
+  // The stored pairs stream through a ring of LB_RING shared-memory stages filled by bulk copies (see pass 2)
+  extern __shared__ __align__(128) uint8_t lb_smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lb_smem);
+  uint64_t* empty_bar = full_bar + LB_RING;
+  uint8_t* ring = lb_smem + 128;
+  const uint32_t pair_bytes = static_cast<uint32_t>(row) * 8u;  // S row + Y row
+  const uint32_t stage_bytes = (pair_bytes + 127u) & ~127u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LB_RING; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], LB_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  auto issue = [&](int i) {  // thread 0: pair i (age order) -> stage i % LB_RING
+    int p = head + i;
+    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
+    const int st = i % LB_RING;
+    mbar_arrive_expect_tx(&full_bar[st], pair_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(ring + st * stage_bytes)),
+                 "l"(hblk + static_cast<size_t>(2 * p) * row), "r"(pair_bytes), "r"(smem_u32(&full_bar[st]))
+                 : "memory");
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < LB_RING && i < len; ++i) issue(i);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
 
   float4 s4[LB_VEC_PER_THREAD], y4[LB_VEC_PER_THREAD], g4[LB_VEC_PER_THREAD];
   size_t off[LB_VEC_PER_THREAD];   // offset in the flat vectors (x, g, d, ...)
@@ -141,33 +176,7 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   warp_reduce8(sc, lane);
   if ((lane & 3) == 0) wscal[warp][lane >> 2] = (lane >> 2) == 6 ? gmax : sc[0];
 
-  // The stored pairs stream through a ring of LB_RING shared-memory stages filled by bulk copies (see pass 2)
-  extern __shared__ __align__(128) uint8_t lb_smem[];
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lb_smem);
-  uint64_t* empty_bar = full_bar + LB_RING;
-  uint8_t* ring = lb_smem + 128;
-  const uint32_t pair_bytes = static_cast<uint32_t>(row) * 8u;  // S row + Y row
-  const uint32_t stage_bytes = (pair_bytes + 127u) & ~127u;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < LB_RING; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], LB_THREADS / 32);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&](int i) {  // thread 0: pair i (age order) -> stage i % LB_RING
-    int p = head + i;
-    if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
-    const int st = i % LB_RING;
-    mbar_arrive_expect_tx(&full_bar[st], pair_bytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_u32(ring + st * stage_bytes)),
-                 "l"(hblk + static_cast<size_t>(2 * p) * row), "r"(pair_bytes), "r"(smem_u32(&full_bar[st]))
-                 : "memory");
-  };
-  if (threadIdx.x == 0)
-    for (int i = 0; i < LB_RING && i < len; ++i) issue(i);
+  __syncthreads();  // the ring's barriers (initialised by thread 0 at kernel entry) are visible to every thread
   for (int i = 0; i < len; ++i) {
     int p = head + i;
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
