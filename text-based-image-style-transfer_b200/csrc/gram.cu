@@ -20,7 +20,10 @@ static constexpr int G_KCHUNK = 64;                       // pixels per pipeline
 static constexpr int G_BOX_BYTES = G_KCHUNK * 128;        // 64 pixels x 64 channels x 2 B
 static constexpr int G_STAGE_BYTES = 4 * G_BOX_BYTES;     // A: 2 boxes, B: up to 2 boxes
 static constexpr int G_STAGES = 5;
-static constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 1024 + 256;
+// + one box of padding: with 64 channels the M = 128 operand's second 64-channel box does not exist and the tensor core
+// reads whatever follows the first one (those accumulator rows are never stored); behind the last packed chunk of the last
+// stage that must still be inside the allocation
+static constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + G_BOX_BYTES + 1024 + 256;
 static constexpr int G_TMEM_COLS = 128;
 
 __device__ __forceinline__ int gram_find_layer_by_item(const GramParams& p, int item) {
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES + G_BOX_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + G_STAGES;
   uint64_t* done_bar = bars + 2 * G_STAGES;
@@ -96,20 +99,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  // A stage holds 32 KB: four 64-pixel x 64-channel boxes.  An off-diagonal block of a >= 128-channel layer needs all four
+  // for one 64-pixel K chunk (A: 2, B: 2); a diagonal block needs two and conv1_1 (64 channels) one - those pack two / four
+  // consecutive K chunks into a stage, so that every kind of item keeps the same number of bytes in flight (conv1_1's Gram
+  // is a pure 33 MB read; with one 8 KB box per stage it was latency bound and set the duration of the whole launch).
+  const int nb = a_boxes + b_boxes;        // boxes per 64-pixel chunk
+  const int kmul = 4 / nb;                 // chunks per stage: 4, 2 or 1
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = static_cast<uint32_t>((a_boxes + b_boxes) * G_BOX_BYTES);
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int c = c_begin; c < c_end; c += kmul) {
+        const int n = c_end - c < kmul ? c_end - c : kmul;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[stage], bytes);
-        uint8_t* sa = smem + stage * G_STAGE_BYTES;
-        uint8_t* sb = sa + 2 * G_BOX_BYTES;
-        for (int b = 0; b < a_boxes; ++b)
-          tma_load_2d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], bi * 128 + b * 64, c * G_KCHUNK);
-        for (int b = 0; b < b_boxes; ++b)
-          tma_load_2d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], bj * 128 + b * 64, c * G_KCHUNK);
+        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(n * nb * G_BOX_BYTES));
+        for (int j = 0; j < n; ++j) {
+          uint8_t* sa = smem + stage * G_STAGE_BYTES + j * nb * G_BOX_BYTES;
+          uint8_t* sb = sa + a_boxes * G_BOX_BYTES;
+          for (int b = 0; b < a_boxes; ++b)
+            tma_load_2d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], bi * 128 + b * 64, (c + j) * G_KCHUNK);
+          for (int b = 0; b < b_boxes; ++b)
+            tma_load_2d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], bj * 128 + b * 64, (c + j) * G_KCHUNK);
+        }
         if (++stage == G_STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -120,21 +131,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t idesc = umma_idesc_f16(128, L.bn, 0, 1, 1);
-    for (int c = c_begin; c < c_end; ++c) {
+    for (int c = c_begin; c < c_end; c += kmul) {
+      const int n = c_end - c < kmul ? c_end - c : kmul;
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + stage * G_STAGE_BYTES);
-        const uint32_t b_addr = bi == bj ? a_addr : a_addr + 2 * G_BOX_BYTES;
+        for (int j = 0; j < n; ++j) {
+          const uint32_t a_addr = smem_u32(smem + stage * G_STAGE_BYTES + j * nb * G_BOX_BYTES);
+          const uint32_t b_addr = bi == bj ? a_addr : a_addr + a_boxes * G_BOX_BYTES;
 #pragma unroll
-        for (int k = 0; k < G_KCHUNK / 16; ++k) {
-          // MN-major: LBO = distance between the two 64-channel boxes, SBO = 8 pixel rows
-          const uint64_t da = umma_desc_sw128(a_addr + k * 16 * 128, G_BOX_BYTES, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + k * 16 * 128, G_BOX_BYTES, 1024);
-          umma_f16(tmem_base, da, db, idesc, (c > c_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < G_KCHUNK / 16; ++k) {
+            // MN-major: LBO = distance between the two 64-channel boxes, SBO = 8 pixel rows
+            const uint64_t da = umma_desc_sw128(a_addr + k * 16 * 128, G_BOX_BYTES, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 16 * 128, G_BOX_BYTES, 1024);
+            umma_f16(tmem_base, da, db, idesc, (c > c_begin || j > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);
-        if (c == c_end - 1) umma_commit(done_bar);
+        if (c + kmul >= c_end) umma_commit(done_bar);
       }
       __syncwarp();
       if (++stage == G_STAGES) {
