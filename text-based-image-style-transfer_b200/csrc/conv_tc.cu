@@ -167,7 +167,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   // must then use the same weights: one N tile only.
   const bool seed = MODE == CONV_DGRAD && Cfg::TMEM_COLS_SEED == 4 * BLOCK_N && p.seed_k > 0;
   const int seed_slices = seed ? p.seed_k / BLOCK_K : 0;
-  const bool b_resident = p.taps == 9 && k_slices == 1 && 9 / Cfg::TPS <= Cfg::B_STAGES && p.tiles_n == 1 && !seed;
+  // dbg_flags bit 2 (timing experiment, wrong results): never re-stream the weights - how fast is the main loop without
+  // the TMA writes of the B operand competing with the tensor core's shared-memory reads?
+  const bool b_resident = p.taps == 9 && 9 / Cfg::TPS <= Cfg::B_STAGES && !seed &&
+                          ((k_slices == 1 && p.tiles_n == 1) || (p.dbg_flags & 4));
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             as = 0;
             aphase ^= 1u;
           }
-          if (b_resident && tile != static_cast<int>(blockIdx.x)) continue;
+          if (b_resident && (tile != static_cast<int>(blockIdx.x) || ks > 0)) continue;
           for (int tap = 0; tap < p.taps; tap += tps) {
             NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
             mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
