@@ -240,23 +240,34 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     // dependent chain with everything in registers (lane l owns one row, its 32 matrix entries of the diagonal block
     // are preloaded, al_k travels by one 64-bit shuffle: a step is shuffle + multiply-add), then the whole block applies
     // the 32 new al_k to all older rows in parallel.  Same arithmetic as the loop below up to the fp64 summation order.
-    for (int hi = len; hi > 0; hi -= 32) {
+    // Warp b owns diagonal block b (at most four: len <= 100).  All four preload their 32 x 32 piece of the matrix into
+    // registers at once, up front - the entries do not depend on the recurrence; preloading block after block inside
+    // the loop put 1.4 us of shared-memory latency in front of every 1.2 us chain.
+    const int my_blk = tid >> 5, lane_c = tid & 31;
+    double rr[32];
+    {
+      const int hi_b = len - 32 * my_blk;
+      const int lo_b = hi_b > 32 ? hi_b - 32 : 0, nb_b = hi_b > 0 ? hi_b - lo_b : 0;
+      const bool own_b = my_blk < 4 && lane_c < nb_b;
+      const int pa_b = nst_ctl_slot(head, own_b ? lo_b + lane_c : 0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rr[j] = (own_b && j < nb_b) ? w.R[pa_b * TOT + nst_ctl_slot(head, lo_b + (j < nb_b ? j : 0))] : 0.0;
+    }
+    int blk = 0;
+    for (int hi = len; hi > 0; hi -= 32, ++blk) {
       const int lo = hi > 32 ? hi - 32 : 0, nb = hi - lo;
-      if (tid < 32) {
-        const bool own = tid < nb;
-        const int pa = nst_ctl_slot(head, own ? lo + tid : lo);
+      if (my_blk == blk) {
+        const bool own = lane_c < nb;
+        const int pa = nst_ctl_slot(head, own ? lo + lane_c : lo);
         double run = own ? w.c[pa] : 0.0;
         const double rok = own ? w.ro[pa] : 0.0;
-        double rr[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rr[j] = (own && j < nb) ? w.R[pa * TOT + nst_ctl_slot(head, lo + (j < nb ? j : 0))] : 0.0;
         double mine = 0.0;
 #pragma unroll
         for (int kk = 31; kk >= 0; --kk) {
           if (kk < nb) {
             const double al = __shfl_sync(0xffffffffu, rok * run, kk);
-            if (tid < kk) run -= al * rr[kk];
-            if (tid == kk) mine = al;
+            if (lane_c < kk) run -= al * rr[kk];
+            if (lane_c == kk) mine = al;
           }
         }
         if (own) w.al[pa] = mine;
@@ -311,23 +322,30 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
 #if defined(__CUDA_ARCH__)
     // device: the same blocking, forward
-    for (int lo = 0; lo < len; lo += 32) {
+    {
+      // preload, all four warps at once (see loop 1): warp b takes the block that starts at 32 b
+      const int lo_b = 32 * my_blk;
+      const int hi_b = lo_b + 32 < len ? lo_b + 32 : len, nb_b = hi_b > lo_b ? hi_b - lo_b : 0;
+      const bool own_b = my_blk < 4 && lane_c < nb_b;
+      const int pa_b = nst_ctl_slot(head, own_b ? lo_b + lane_c : 0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rr[j] = (own_b && j < nb_b) ? w.R[nst_ctl_slot(head, lo_b + (j < nb_b ? j : 0)) * TOT + pa_b] : 0.0;
+    }
+    blk = 0;
+    for (int lo = 0; lo < len; lo += 32, ++blk) {
       const int hi = lo + 32 < len ? lo + 32 : len, nb = hi - lo;
-      if (tid < 32) {
-        const bool own = tid < nb;
-        const int pa = nst_ctl_slot(head, own ? lo + tid : lo);
+      if (my_blk == blk) {
+        const bool own = lane_c < nb;
+        const int pa = nst_ctl_slot(head, own ? lo + lane_c : lo);
         double run = own ? w.yq[pa] : 0.0;
         const double rok = own ? w.ro[pa] : 0.0, alk = own ? w.al[pa] : 0.0;
-        double rr[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rr[j] = (own && j < nb) ? w.R[nst_ctl_slot(head, lo + (j < nb ? j : 0)) * TOT + pa] : 0.0;
         double mine = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 32; ++kk) {
           if (kk < nb) {
             const double ck = __shfl_sync(0xffffffffu, alk - rok * run, kk);
-            if (tid > kk) run += ck * rr[kk];
-            if (tid == kk) mine = ck;
+            if (lane_c > kk) run += ck * rr[kk];
+            if (lane_c == kk) mine = ck;
           }
         }
         if (own) w.c[pa] = mine;
