@@ -358,8 +358,10 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
     mbar_fence_init();
   }
   __syncthreads();
-  auto issue = [&](int i) {  // thread 0: pair i (age order) -> stage i % LB_RING
-    int p = head + i;
+  // Visiting order: NEWEST pair first.  Pass 1 streamed oldest -> newest two small kernels ago, so the newest ~100 MB of the
+  // history are still in the 126 MB L2 when this pass starts with them.
+  auto issue = [&](int i) {  // thread 0: i-th visited pair (age len-1-i) -> stage i % LB_RING
+    int p = head + (len - 1 - i);
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
     const int st = i % LB_RING;
     mbar_arrive_expect_tx(&full_bar[st], pair_bytes);
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass2_kernel(const LbfgsBuff
   if (threadIdx.x == 0)
     for (int i = 0; i < LB_RING && i < len; ++i) issue(i);
   for (int i = 0; i < len; ++i) {
-    int p = head + i;
+    int p = head + (len - 1 - i);
     if (p >= NST_LBFGS_SLOTS) p -= NST_LBFGS_SLOTS;
     const int st = i % LB_RING;
     const uint32_t ph = static_cast<uint32_t>(i / LB_RING) & 1u;
