@@ -288,8 +288,15 @@ def run_b200(args, rank, world, local_rank):
     sess.prepare(content, trace_capacity=Wm + K + 64)
     enqueue_evals(120)                                            # history full (m = 100): steady state of a 320-evaluation run
     stream.synchronize()
-    with torch.cuda.stream(stream):
-        raw = plan.lbfgs_step_timed(grouped=True) + plan.lbfgs_step_timed(grouped=True)
+    # three repetitions of (2 x 20 evaluations); the repetition with the smallest total is reported (a transient on the box -
+    # one run showed pass 1 at 180 us instead of 114 - would otherwise decide the roofline line)
+    raw, raw_total = None, None
+    for _rep in range(3):
+        with torch.cuda.stream(stream):
+            r_ = plan.lbfgs_step_timed(grouped=True) + plan.lbfgs_step_timed(grouped=True)
+        t_ = sum(ms_ for _, _, ms_ in r_)
+        if raw_total is None or t_ < raw_total:
+            raw, raw_total = r_, t_
     m_now = sess.status().hist_len
     # grouped rows: (kind, launches in the run, ms of the run) - one CUDA event wherever the kind of launch changes, so
     # the twelve forward convolutions (or the twelve data gradients) are timed as one run with programmatic dependent
@@ -319,7 +326,7 @@ def run_b200(args, rank, world, local_rank):
                     ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms,
                     how="CUDA events on the launching stream around every run of same-kind launches (forward convolutions, "
                         "data gradients, Gram backward) of 2 x 20 evaluations executed back to back on one stream "
-                        "(nst_lbfgs_step_timed_grouped); average launch duration = run time / launches in the run")
+                        "(nst_lbfgs_step_timed_grouped), best of 3 repetitions; average launch duration = run time / launches in the run")
     lb_ms = per_eval(("lbfgs_pass1", "lbfgs_pass2"))
     m_avg = m_now                                                 # 100: the history was full while the timed steps ran
     lb_gbs = synth.lbfgs_bytes(S, S, m_avg) / (lb_ms * 1e-3) / 1e9 if lb_ms > 0 else None
