@@ -319,7 +319,7 @@ def run_b200(args, rank, world, local_rank):
     roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient launches per evaluation, the Gram backward "
                            "of conv1_1..conv4_1 folded into the data gradients as a second accumulator, + 1 Gram-backward launch for conv5_1)",
                     achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
-                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the 29 launches of one evaluation (ncu --set full, profiles/r01c_ncu_full_conv_tc_summary.csv)",
+                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the conv_tc_kernel launches of one evaluation (ncu --set full, profiles/r01c_ncu_full_conv_tc_summary.csv)",
                     peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
                     avg_launch_ms=conv_ms / conv_launches,
