@@ -58,6 +58,46 @@ def ncu_traffic():
     return sum(vals) / len(vals) if vals else None
 
 
+def bench_mask_composite(dev, pk):
+    """text/segmentation_style_transfer.py on the device (csrc/mask.cu): GB/s on the algorithmic bytes (7 read + 3 written per
+    pixel) against the measured copy bandwidth, CUDA events, inputs larger than L2 at the large size; CPU = the oracle port."""
+    import numpy as np
+    import torch
+    from importlib import import_module
+    seg = import_module("text-based-image-style-transfer_b200.text.segmentation_style_transfer")
+    from oracle import mask_oracle as M
+    out = {}
+    for S in (1024, 8192):
+        g = torch.Generator(device="cpu").manual_seed(S)
+        content = torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, generator=g).to(dev)
+        style = torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, generator=g).to(dev)
+        yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+        mask = (((yy - S / 2) ** 2 + (xx - S / 3) ** 2) < (S / 2.5) ** 2).to(dev)
+        for _ in range(3):
+            res = seg.composite_tensors(content, style, mask, 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            res = seg.composite_tensors(content, style, mask, 5)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = 10.0 * S * S / (ms * 1e-3) / 1e9
+        row = dict(ms=ms, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], bytes=10 * S * S)
+        if S == 1024:
+            c, s_, m = content.cpu().numpy(), style.cpu().numpy(), mask.cpu().numpy()
+            t0 = time.perf_counter()
+            want = M.segmentation_style_transfer(c, s_, m, 5)
+            row["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+            row["bit_exact"] = bool(np.array_equal(res.cpu().numpy(), want))
+        out["%dx%d" % (S, S)] = row
+    out["what"] = ("segmentation_style_transfer(edge_smoothing=5) on uint8 HWC device tensors: mask blur (cv2.GaussianBlur fixed point) + "
+                   "fp64 blend in one kernel; 8192^2 = 671 MB of traffic (larger than L2); cpu_ms = oracle port (numpy), one thread")
+    return out
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -336,6 +376,11 @@ def run_b200(args, rank, world, local_rank):
                         bytes_per_iteration=synth.lbfgs_bytes(S, S, m_avg), ms=lb_ms)
     lb_rows = []
 
+    # ---- next row of the scope table: mask compositing right behind the loop, measured the same way
+    mask_row = None
+    if world == 1:
+        mask_row = bench_mask_composite(dev, pk)
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -349,7 +394,7 @@ def run_b200(args, rank, world, local_rank):
                             l2="working set per evaluation (activations ~0.3 GB + L-BFGS history up to 0.63 GB) exceeds the 126 MB L2; no flush needed",
                             history_pairs_at_end=hist_len, final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S)),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
-                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu)
+                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, mask_composite=mask_row)
     emit(line)
     if args.kernel_table:
         # per-launch table: the same step with an event after EVERY launch (isolates each launch: no overlap between launches)

@@ -212,6 +212,16 @@ int nst_plan_chain_waits(nst_plan* plan, int which, long long* out, int max_ctas
 int nst_run_frame_host(nst_plan* plan, const uint8_t* content_u8, uint8_t* out_u8, int num_steps, int channel_attention,
                        const float* ca_w1, const float* ca_w2, void* stream);
 
+/* ---- mask compositing: text/segmentation_style_transfer.py:5-94 (segmentation_style_transfer + _edge_smoothing), the step that
+ * follows run_multi_style_transfer in app.py:203,318,407,512.  content, style, out: [H][W][C] uint8 device buffers (C <= 4),
+ * mask: [H][W] bytes (non-zero = stylised pixel).  edge_smoothing = 0 selects (np.where, :52); otherwise the mask is blurred
+ * with cv2.GaussianBlur's 8-bit fixed-point arithmetic (even sizes + 1, :76-77; at most 127) and the images are blended in
+ * fp64 and truncated (:91).  Bit-exact with the reference. */
+int nst_mask_composite(const uint8_t* content, const uint8_t* style, const uint8_t* mask, int H, int W, int C, int edge_smoothing,
+                       uint8_t* out, void* stream);
+/* the k integer weights (sum 256) of that blur, host side; k odd, 1..127 */
+int nst_mask_gaussian_weights(int k, int* w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -449,3 +449,31 @@ def test_optional_paths_stay_parity_green(env):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "smoke ok" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ mask compositing
+def test_mask_composite_bit_exact_against_reference_golden():
+    """text/segmentation_style_transfer.py through the CUDA kernel: byte arithmetic, so bit-exact against the vectors the
+    unmodified reference function wrote (tests/golden/make_golden_mask.py) - crops, even sizes, hard selection included."""
+    from PIL import Image
+    seg = importlib.import_module("text-based-image-style-transfer_b200.text.segmentation_style_transfer")
+    g = golden("mask_composite")
+    for n in range(int(g["n"])):
+        out = seg.segmentation_style_transfer(Image.fromarray(g["content_%d" % n]), Image.fromarray(g["style_%d" % n]),
+                                              g["mask_%d" % n], edge_smoothing=int(g["k_%d" % n]))
+        assert np.array_equal(np.asarray(out), g["out_%d" % n]), n
+
+
+@pytest.mark.parametrize("k", [0, 1, 3, 5, 6, 9, 11, 31, 63, 127])
+def test_mask_composite_bit_exact_against_oracle(k):
+    from oracle import mask_oracle as M
+    seg = importlib.import_module("text-based-image-style-transfer_b200.text.segmentation_style_transfer")
+    rng = np.random.default_rng(k)
+    for H, W in ((97, 131), (33, 40), (7, 5), (256, 320)):
+        content = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        style = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        yy, xx = np.mgrid[0:H, 0:W]
+        mask = ((yy - H / 2) ** 2 + (xx - W / 3) ** 2 < (min(H, W) / 2.5) ** 2) ^ (rng.random((H, W)) > 0.97)
+        want = M.segmentation_style_transfer(content, style, mask, k)
+        got = seg.composite_tensors(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), torch.from_numpy(mask).cuda(), k)
+        assert np.array_equal(got.cpu().numpy(), want), (k, H, W)

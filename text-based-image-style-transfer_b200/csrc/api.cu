@@ -25,6 +25,7 @@
 #include "conv_tc.cuh"
 #include "gram.cuh"
 #include "lbfgs.cuh"
+#include "mask.cuh"
 #include "pixel.cuh"
 
 using namespace nst;
@@ -60,6 +61,9 @@ extern "C" int nst_device_check(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(NST_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  // cudaGetDeviceProperties costs milliseconds: a device that passed once is not queried again
+  static bool checked[64] = {};
+  if (dev >= 0 && dev < 64 && checked[dev] && g_num_sms != 0) return NST_OK;
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) return fail(NST_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
@@ -75,6 +79,7 @@ extern "C" int nst_device_check(void) {
     if (e != cudaSuccess) return fail(NST_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(e));
     g_num_sms = prop.multiProcessorCount;
   }
+  if (dev >= 0 && dev < 64) checked[dev] = true;
   return NST_OK;
 }
 
@@ -1527,6 +1532,26 @@ extern "C" int nst_plan_timeline(nst_plan* p, int enable, unsigned long long* ou
   p->timeline_on = enable != 0;
   if (!p->timeline_on) timeline_arm(p, false);
   drop_graph(p);
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask compositing (the step after the loop in six of the reference's call sites)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nst_mask_composite(const uint8_t* content, const uint8_t* style, const uint8_t* mask, int H, int W, int C,
+                                  int edge_smoothing, uint8_t* out, void* stream) {
+  if (!content || !style || !mask || !out || H < 1 || W < 1 || C < 1 || C > 4 || edge_smoothing < 0)
+    return fail(NST_ERR_ARG, "nst_mask_composite: bad arguments");
+  CKI(nst_device_check());
+  int k = edge_smoothing;
+  if (k != 0 && (k & 1) == 0) k += 1;  // segmentation_style_transfer.py:76-77
+  if (k > MASK_MAX_K) return fail(NST_ERR_UNSUPPORTED, "nst_mask_composite: edge_smoothing %d > %d", edge_smoothing, MASK_MAX_K);
+  CK(launch_mask_composite(content, style, mask, out, H, W, C, k, static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+extern "C" int nst_mask_gaussian_weights(int k, int* w) {
+  if (!w || mask_gaussian_weights(k, w) != 0) return fail(NST_ERR_ARG, "nst_mask_gaussian_weights: k must be odd, 1..%d", MASK_MAX_K);
   return NST_OK;
 }
 
