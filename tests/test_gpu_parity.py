@@ -469,11 +469,14 @@ def test_mask_composite_bit_exact_against_oracle(k):
     from oracle import mask_oracle as M
     seg = importlib.import_module("text-based-image-style-transfer_b200.text.segmentation_style_transfer")
     rng = np.random.default_rng(k)
-    for H, W in ((97, 131), (33, 40), (7, 5), (256, 320)):
+    # widths that are multiples of 64 take the 64 x 64-tile kernel for k <= 9, the others the general one; the clean masks
+    # (noise = 0) have tiles that are plain copies
+    for H, W, noise in ((97, 131, 0.03), (33, 40, 0.03), (7, 5, 0.03), (256, 320, 0.03), (200, 192, 0.0), (3, 64, 0.03), (65, 128, 0.0),
+                        (300, 448, 0.001)):
         content = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
         style = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
         yy, xx = np.mgrid[0:H, 0:W]
-        mask = ((yy - H / 2) ** 2 + (xx - W / 3) ** 2 < (min(H, W) / 2.5) ** 2) ^ (rng.random((H, W)) > 0.97)
+        mask = ((yy - H / 2) ** 2 + (xx - W / 3) ** 2 < (min(H, W) / 2.5) ** 2) ^ (rng.random((H, W)) < noise)
         want = M.segmentation_style_transfer(content, style, mask, k)
         got = seg.composite_tensors(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), torch.from_numpy(mask).cuda(), k)
         assert np.array_equal(got.cpu().numpy(), want), (k, H, W)
