@@ -102,6 +102,42 @@ def bench_mask_composite(dev, pk):
     return out
 
 
+def bench_video_assemble(dev, pk):
+    """app.py:800-840 on the device (csrc/video.cu): 64 stylised 720p frames, 3 cross-dissolved frames between neighbours
+    (253 output frames).  Bytes: every input frame read twice (as `prev` and as `frame`; the second read may hit in L2),
+    every output frame written once - `achieved` counts each input frame ONCE (the minimum).  CPU = cv2 on the host."""
+    import numpy as np
+    import torch
+    from importlib import import_module
+    video = import_module("text-based-image-style-transfer_b200.video")
+    from oracle import video_oracle as V
+    F, H, W, n = 64, 720, 1280, 3
+    g = torch.Generator(device="cpu").manual_seed(7)
+    frames = torch.randint(0, 256, (F, H, W, 3), dtype=torch.uint8, generator=g).to(dev)
+    for _ in range(3):
+        out = video.assemble_frames(frames, n)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        out = video.assemble_frames(frames, n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = (F + out.shape[0]) * H * W * 3
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    row = dict(ms=ms, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], bytes=nbytes, frames_in=F, frames_out=int(out.shape[0]),
+               what="RGB->BGR + 3 cross-dissolved frames between neighbours, 64 frames 1280x720 (0.88 GB moved, larger than L2)")
+    sub = frames[:4].cpu().numpy()
+    t0 = time.perf_counter()
+    want = np.stack(V.assemble_frames(list(sub), n), 0)
+    row["cpu_ms_per_output_frame"] = 1e3 * (time.perf_counter() - t0) / want.shape[0]
+    row["gpu_ms_per_output_frame"] = ms / out.shape[0]
+    row["bit_exact"] = bool(np.array_equal(out[:want.shape[0]].cpu().numpy(), want))
+    return row
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -381,9 +417,10 @@ def run_b200(args, rank, world, local_rank):
     lb_rows = []
 
     # ---- next row of the scope table: mask compositing right behind the loop, measured the same way
-    mask_row = None
+    mask_row = video_row = None
     if world == 1:
         mask_row = bench_mask_composite(dev, pk)
+        video_row = bench_video_assemble(dev, pk)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu = None
@@ -398,7 +435,7 @@ def run_b200(args, rank, world, local_rank):
                             l2="working set per evaluation (activations ~0.3 GB + L-BFGS history up to 0.63 GB) exceeds the 126 MB L2; no flush needed",
                             history_pairs_at_end=hist_len, final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S)),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
-                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, mask_composite=mask_row)
+                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, mask_composite=mask_row, video_assemble=video_row)
     emit(line)
     if args.kernel_table:
         # per-launch table: the same step with an event after EVERY launch (isolates each launch: no overlap between launches)

@@ -222,6 +222,13 @@ int nst_mask_composite(const uint8_t* content, const uint8_t* style, const uint8
 /* the k integer weights (sum 256) of that blur, host side; k odd, 1..127 */
 int nst_mask_gaussian_weights(int k, int* w);
 
+/* ---- video back end: the frame list apply_video_process hands to the encoder, app.py:800-806 (cv2.cvtColor RGB2BGR of every
+ * stylised frame) and app.py:820-840 (n_interp cross-dissolved frames cv2.addWeighted(prev, 1 - a, frame, a, 0),
+ * a = (i + 1) / (n_interp + 1), between consecutive frames).  frames_rgb: [F][H][W][3] uint8 device; out_bgr:
+ * [(F - 1) * (n_interp + 1) + 1][H][W][3] uint8 device.  n_interp <= 15 (the reference's slider: 0..5).  Bit-exact with
+ * OpenCV's 8-bit addWeighted (fp32 fma(a, alpha, b * beta), round to nearest even). */
+int nst_video_assemble(const uint8_t* frames_rgb, int F, int H, int W, int n_interp, uint8_t* out_bgr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -480,3 +480,44 @@ def test_mask_composite_bit_exact_against_oracle(k):
         want = M.segmentation_style_transfer(content, style, mask, k)
         got = seg.composite_tensors(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), torch.from_numpy(mask).cuda(), k)
         assert np.array_equal(got.cpu().numpy(), want), (k, H, W)
+
+
+# ------------------------------------------------------------------------------------------------ video back end
+def test_video_assemble_bit_exact_against_reference_golden():
+    """app.py:800-840 (RGB -> BGR + cross-dissolve) through the CUDA kernel against the frame lists the reference's own
+    statements wrote with cv2 (tests/golden/make_golden_video.py)."""
+    video = importlib.import_module("text-based-image-style-transfer_b200.video")
+    g = golden("video_assemble")
+    for n in range(int(g["n"])):
+        got = video.assemble_frames(torch.from_numpy(g["frames_%d" % n]).cuda(), int(g["k_%d" % n]))
+        assert np.array_equal(got.cpu().numpy(), g["final_%d" % n]), n
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4, 5, 6, 15])
+def test_video_assemble_bit_exact_against_oracle(k):
+    from oracle import video_oracle as V
+    video = importlib.import_module("text-based-image-style-transfer_b200.video")
+    rng = np.random.default_rng(k)
+    # frame sizes with H * W a multiple of 16 take the 48-bytes-per-thread kernel, the others the per-pixel one
+    for F, H, W in ((3, 64, 48), (2, 17, 23), (1, 32, 32), (5, 120, 160), (2, 1, 16), (4, 3, 5)):
+        frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+        if F > 1:  # every byte pair the rounding could trip on: all 65 536 (a, b) combinations somewhere in the first two frames
+            a, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+            cnt = min(H * W * 3, 65536)
+            frames[0].reshape(-1)[:cnt] = a.reshape(-1)[:cnt]
+            frames[1].reshape(-1)[:cnt] = b.reshape(-1)[:cnt]
+        want = np.stack(V.assemble_frames(list(frames), k), 0)
+        got = video.assemble_frames(torch.from_numpy(frames).cuda(), k)
+        assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want), (k, F, H, W)
+
+
+def test_video_assemble_all_byte_pairs():
+    """all 65 536 (prev, frame) byte pairs for every slider value, vector kernel"""
+    from oracle import video_oracle as V
+    video = importlib.import_module("text-based-image-style-transfer_b200.video")
+    a, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    frames = np.stack([np.repeat(a.reshape(-1), 3).reshape(128, 512, 3), np.repeat(b.reshape(-1), 3).reshape(128, 512, 3)], 0)
+    for k in range(1, 16):
+        want = np.stack(V.assemble_frames(list(frames), k), 0)
+        got = video.assemble_frames(torch.from_numpy(frames).cuda(), k)
+        assert np.array_equal(got.cpu().numpy(), want), k

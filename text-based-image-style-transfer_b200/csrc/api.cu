@@ -26,6 +26,7 @@
 #include "gram.cuh"
 #include "lbfgs.cuh"
 #include "mask.cuh"
+#include "video.cuh"
 #include "pixel.cuh"
 
 using namespace nst;
@@ -1552,6 +1553,18 @@ extern "C" int nst_mask_composite(const uint8_t* content, const uint8_t* style, 
 
 extern "C" int nst_mask_gaussian_weights(int k, int* w) {
   if (!w || mask_gaussian_weights(k, w) != 0) return fail(NST_ERR_ARG, "nst_mask_gaussian_weights: k must be odd, 1..%d", MASK_MAX_K);
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// video back end: RGB -> BGR + cross-dissolved in-between frames (app.py:800-806, 820-840)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nst_video_assemble(const uint8_t* frames_rgb, int F, int H, int W, int n_interp, uint8_t* out_bgr, void* stream) {
+  if (!frames_rgb || !out_bgr || F < 1 || H < 1 || W < 1 || n_interp < 0) return fail(NST_ERR_ARG, "nst_video_assemble: bad arguments");
+  if (n_interp > VIDEO_MAX_INTERP)
+    return fail(NST_ERR_UNSUPPORTED, "nst_video_assemble: %d interpolation frames > %d", n_interp, VIDEO_MAX_INTERP);
+  CKI(nst_device_check());
+  CK(launch_video_assemble(frames_rgb, F, static_cast<size_t>(H) * W, n_interp, out_bgr, static_cast<cudaStream_t>(stream)));
   return NST_OK;
 }
 

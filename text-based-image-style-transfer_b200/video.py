@@ -120,3 +120,29 @@ class FrameStyler:
 
     def close(self):
         self.session.close()
+
+
+def assemble_frames(frames_rgb: torch.Tensor, number_of_interpolations: int = 0) -> torch.Tensor:
+    """The frame list apply_video_process writes to the encoder (app.py:800-806, 820-840), built on the device.
+
+    frames_rgb: (F, H, W, 3) uint8 CUDA tensor of stylised RGB frames.  Returns ((F - 1) * (n + 1) + 1, H, W, 3) uint8 BGR
+    frames: every input frame with its channels swapped (cv2.cvtColor(..., COLOR_RGB2BGR)) and, between two consecutive
+    frames, n cross-dissolved ones (cv2.addWeighted(prev, 1 - alpha, frame, alpha, 0), alpha = (i + 1) / (n + 1)).
+    One kernel (csrc/video.cu), bit-exact with OpenCV's 8-bit arithmetic."""
+    import ctypes as C
+    from . import _lib
+    from .engine import _require_cuda
+    dev = _require_cuda(frames_rgb.device)
+    if frames_rgb.dtype != torch.uint8 or frames_rgb.dim() != 4 or frames_rgb.shape[-1] != 3 or frames_rgb.shape[0] < 1:
+        raise ValueError("frames_rgb must be a non-empty (F, H, W, 3) uint8 tensor")
+    n = int(number_of_interpolations or 0)
+    if n < 0:
+        raise ValueError("number_of_interpolations must be >= 0")
+    frames_rgb = frames_rgb.contiguous()
+    F, H, W, _ = frames_rgb.shape
+    out = torch.empty(((F - 1) * (n + 1) + 1, H, W, 3), dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.nst_video_assemble(C.c_void_p(frames_rgb.data_ptr()), int(F), int(H), int(W), n, C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
