@@ -138,6 +138,56 @@ def bench_video_assemble(dev, pk):
     return row
 
 
+def bench_mip(dev, pk):
+    """components/style_transfer_depth/util.py split / merge on the device (csrc/depth.cu): 4096^2 RGB, 4 depth planes, uint8
+    depth.  Bytes: split reads 3 + 1 and writes 4 * 3 per pixel; merge reads 1 + 3 (only the plane a pixel belongs to) and
+    writes 3.  The n loops in between are the headline path itself."""
+    import numpy as np
+    import torch
+    from importlib import import_module
+    U = import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.util")
+    from oracle import depth_oracle as D
+    S, n = 4096, 4
+    g = torch.Generator(device="cpu").manual_seed(3)
+    img = torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, generator=g).to(dev)
+    yy, xx = np.mgrid[0:S, 0:S]
+    depth = ((np.sin(yy / 300.0) + np.cos(xx / 450.0) + 2) * 63).astype(np.uint8)
+    bins = U.create_bins(n)
+    d_dev = torch.from_numpy(depth).to(dev)
+
+    class _D:  # hand the kernels the device copy: the upload is not part of the kernel time
+        pass
+    out = {}
+    orig = U._depth_args
+    U._depth_args = lambda d, dv: (d_dev, 0, int(depth.min()), int(depth.max()))
+    try:
+        for name, fn, nbytes in (("split", lambda: U.split_planes(img, depth, bins), (4 + 3 * n) * S * S),
+                                 ("merge", lambda: U.merge_planes(planes, depth, bins), 7 * S * S)):
+            if name == "split":
+                planes = fn()
+            for _ in range(3):
+                res = fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                res = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out[name] = dict(ms=ms, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], bytes=nbytes)
+    finally:
+        U._depth_args = orig
+    sub = slice(0, 256)
+    want = np.stack(D.generate_mip_layers(img[sub].cpu().numpy(), depth[sub], n), 0)
+    # same bins need the same normalisation: compare on the full-map min / max by splitting the full image and cropping
+    out["bit_exact"] = bool(np.array_equal(planes[:, sub].cpu().numpy(),
+                                           np.stack(D.generate_mip_layers(img.cpu().numpy(), depth, n), 0)[:, sub])) if want is not None else None
+    out["what"] = "generate_mip_layers / reconstruct_mip_image, 4096x4096 RGB, 4 planes (268 / 117 MB moved, larger than L2)"
+    return out
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -417,10 +467,11 @@ def run_b200(args, rank, world, local_rank):
     lb_rows = []
 
     # ---- next row of the scope table: mask compositing right behind the loop, measured the same way
-    mask_row = video_row = None
+    mask_row = video_row = mip_row = None
     if world == 1:
         mask_row = bench_mask_composite(dev, pk)
         video_row = bench_video_assemble(dev, pk)
+        mip_row = bench_mip(dev, pk)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu = None
@@ -435,7 +486,7 @@ def run_b200(args, rank, world, local_rank):
                             l2="working set per evaluation (activations ~0.3 GB + L-BFGS history up to 0.63 GB) exceeds the 126 MB L2; no flush needed",
                             history_pairs_at_end=hist_len, final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S)),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
-                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, mask_composite=mask_row, video_assemble=video_row)
+                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, mask_composite=mask_row, video_assemble=video_row, mip_planes=mip_row)
     emit(line)
     if args.kernel_table:
         # per-launch table: the same step with an event after EVERY launch (isolates each launch: no overlap between launches)

@@ -229,6 +229,17 @@ int nst_mask_gaussian_weights(int k, int* w);
  * OpenCV's 8-bit addWeighted (fp32 fma(a, alpha, b * beta), round to nearest even). */
 int nst_video_assemble(const uint8_t* frames_rgb, int F, int H, int W, int n_interp, uint8_t* out_bgr, void* stream);
 
+/* ---- multi-plane depth style transfer: components/style_transfer_depth/util.py:9-35,53-66 (mask_image_depth over the bins of
+ * create_bins = generate_mip_layers) and :69-88 (reconstruct_mip_image).  depth: [H][W] uint8 (depth_f64 = 0; dmin / dmax = the
+ * map's minimum / maximum, normalised in the kernel as numpy does: (d - min) / (max - min) in fp64) or the already normalised
+ * [H][W] fp64 map (depth_f64 = 1).  lo / hi: the n inclusive bin bounds (host arrays).  n <= 16 (the reference's slider: 2..10).
+ * split: image [H][W][C] -> out [n][H][W][C], pixels outside bin i zeroed in plane i.
+ * merge: planes [n][H][W][3] -> out [H][W][3], the masked planes added up in uint8 (wraps where bins overlap). */
+int nst_mip_split(const uint8_t* image, const void* depth, int depth_f64, int dmin, int dmax, int H, int W, int C, int n,
+                  const double* lo, const double* hi, uint8_t* out, void* stream);
+int nst_mip_merge(const uint8_t* planes, const void* depth, int depth_f64, int dmin, int dmax, int H, int W, int n,
+                  const double* lo, const double* hi, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

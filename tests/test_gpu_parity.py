@@ -521,3 +521,79 @@ def test_video_assemble_all_byte_pairs():
         want = np.stack(V.assemble_frames(list(frames), k), 0)
         got = video.assemble_frames(torch.from_numpy(frames).cuda(), k)
         assert np.array_equal(got.cpu().numpy(), want), k
+
+
+# ------------------------------------------------------------------------------------------------ depth-aware / multi-plane variant
+def test_mip_split_merge_bit_exact_against_reference_golden(nst):
+    """components/style_transfer_depth/util.py byte functions through the CUDA kernels against what the unmodified reference
+    functions returned (incl. depth values exactly on bin edges, a flat depth map = nan, fp32 depth, a grayscale image)."""
+    U = importlib.import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.util")
+    from PIL import Image
+    g = golden("depth_mip")
+    for k in range(int(g["b_count"])):
+        img, depth, n = g["b_img_%d" % k], g["b_depth_%d" % k], int(g["b_n_%d" % k])
+        planes = np.stack([np.asarray(p) for p in U.generate_mip_layers(Image.fromarray(img), depth, n)], 0)
+        assert np.array_equal(planes, g["b_planes_%d" % k]), k
+        merged = U.reconstruct_mip_image([Image.fromarray(s) for s in g["b_styl_%d" % k]], depth, n)
+        assert np.array_equal(np.asarray(merged), g["b_merged_%d" % k]), k
+        one = U.mask_image_depth(Image.fromarray(img), depth, U.create_bins(n)[n - 1])
+        assert np.array_equal(np.asarray(one), g["b_planes_%d" % k][n - 1]), k
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 10, 16])
+def test_mip_split_merge_bit_exact_against_oracle(nst, n):
+    from oracle import depth_oracle as D
+    U = importlib.import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.util")
+    rng = np.random.default_rng(n)
+    for H, W, kind in ((64, 48, "u8"), (33, 31, "u8"), (128, 96, "edges"), (17, 4, "f64"), (40, 40, "edges")):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        if kind == "u8":
+            depth = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        elif kind == "edges":
+            depth = (rng.integers(0, 2 * n + 1, (H, W)) * 3 + 5).astype(np.uint8)    # range 6n: every bin edge is hit exactly
+        else:
+            depth = rng.random((H, W)) * 5 - 2
+        bins = D.create_bins(n)
+        planes = U.split_planes(torch.from_numpy(img).cuda(), depth, bins)
+        want = np.stack(D.generate_mip_layers(img, depth, n), 0)
+        assert np.array_equal(planes.cpu().numpy(), want), (n, H, W, kind)
+        styl = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+        merged = U.merge_planes(torch.from_numpy(styl).cuda(), depth, bins)
+        assert np.array_equal(merged.cpu().numpy(), D.reconstruct_mip_image(list(styl), depth, n)), (n, H, W, kind)
+
+
+def test_style_mip_against_reference_golden(nst):
+    """DepthStyle.style_MIP (n loops with per-plane style weight + split / merge) against the run of the unmodified reference:
+    planes bit-exact, per-plane loss curves within 1e-2, stylised planes and merged image >= 40 dB."""
+    from PIL import Image
+    mod = importlib.import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.style_transfer_depth")
+    g = golden("depth_mip")
+    n, steps = int(g["mip_n"]), int(g["mip_num_steps"])
+    depth = g["mip_depth"]
+    ds = mod.DepthStyle("cuda", depth_pipeline=lambda image: {"depth": Image.fromarray(depth)})
+    ds.style_model.num_steps = steps
+    ds.style_model.print_iter = 0
+    try:
+        planes = ds.depth_split(Image.fromarray(g["mip_content"]), n)
+        assert np.array_equal(np.stack([np.asarray(p) for p in planes], 0), g["mip_planes"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            final, stylized = ds.style_MIP(Image.fromarray(g["mip_content"]), Image.fromarray(g["mip_style"]), n)
+        traces = ds.style_model.traces[-n:]
+    finally:
+        ds.close()
+
+    def psnr_u8(a, b):
+        mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+        return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+    for i in range(n):
+        ours, ref = traces[i][:, 0].double().numpy(), g["mip_losses"][i]
+        assert len(ours) == len(ref) == 20 * (steps // 20 + 1)
+        assert abs(ours[0] - ref[0]) <= LOSS_TOL * abs(ref[0]), i
+        assert np.abs(ours - ref).max() <= CURVE_TOL * np.abs(ref).max(), (i, np.abs(ours - ref).max() / np.abs(ref).max())
+        assert psnr_u8(np.asarray(stylized[i]), g["mip_stylized"][i]) >= PSNR_MIN, i
+    # pixels exactly on an inner bin edge are the wrapped sum of two planes (util.py:30,86): a one-level difference there can
+    # show up as 255 - the merge itself is checked bit for bit above, so they are left out of the PSNR
+    from oracle import depth_oracle as D
+    shared = sum((np.stack(D.generate_mip_layers(np.ones_like(g["mip_content"]), depth, n), 0)[:, :, :, 0] > 0).astype(int)) > 1
+    assert psnr_u8(np.asarray(final)[~shared], g["mip_final"][~shared]) >= PSNR_MIN

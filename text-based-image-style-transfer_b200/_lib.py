@@ -81,6 +81,10 @@ PROTOTYPES = {
     "nst_plan_chain_waits": (C.c_int, [_P, C.c_int, C.POINTER(C.c_longlong), C.c_int, _P]),
     "nst_mask_composite": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "nst_mask_gaussian_weights": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "nst_mip_split": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), _P, _P]),
+    "nst_mip_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), _P, _P]),
     "nst_video_assemble": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "nst_run_frame_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
 }

@@ -27,6 +27,7 @@
 #include "lbfgs.cuh"
 #include "mask.cuh"
 #include "video.cuh"
+#include "depth.cuh"
 #include "pixel.cuh"
 
 using namespace nst;
@@ -1565,6 +1566,40 @@ extern "C" int nst_video_assemble(const uint8_t* frames_rgb, int F, int H, int W
     return fail(NST_ERR_UNSUPPORTED, "nst_video_assemble: %d interpolation frames > %d", n_interp, VIDEO_MAX_INTERP);
   CKI(nst_device_check());
   CK(launch_video_assemble(frames_rgb, F, static_cast<size_t>(H) * W, n_interp, out_bgr, static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-plane depth style transfer: split into depth bins / merge the stylised planes (components/style_transfer_depth/util.py)
+// ------------------------------------------------------------------------------------------------
+static int mip_bins(MipBins* b, int n, const double* lo, const double* hi, int depth_f64, int dmin, int dmax, const char* who) {
+  if (n < 1 || !lo || !hi) return fail(NST_ERR_ARG, "%s: bad bins", who);
+  if (n > MIP_MAX_PLANES) return fail(NST_ERR_UNSUPPORTED, "%s: %d planes > %d", who, n, MIP_MAX_PLANES);
+  if (!depth_f64 && (dmin < 0 || dmax > 255 || dmax < dmin)) return fail(NST_ERR_ARG, "%s: bad depth range", who);
+  b->n = n;
+  b->dmin = dmin;
+  b->range = dmax - dmin;
+  for (int i = 0; i < n; ++i) b->lo[i] = lo[i], b->hi[i] = hi[i];
+  return NST_OK;
+}
+
+extern "C" int nst_mip_split(const uint8_t* image, const void* depth, int depth_f64, int dmin, int dmax, int H, int W, int C, int n,
+                             const double* lo, const double* hi, uint8_t* out, void* stream) {
+  if (!image || !depth || !out || H < 1 || W < 1 || C < 1 || C > 4) return fail(NST_ERR_ARG, "nst_mip_split: bad arguments");
+  MipBins b;
+  CKI(mip_bins(&b, n, lo, hi, depth_f64, dmin, dmax, "nst_mip_split"));
+  CKI(nst_device_check());
+  CK(launch_mip_split(image, depth, depth_f64, static_cast<size_t>(H) * W, C, b, out, static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+extern "C" int nst_mip_merge(const uint8_t* planes, const void* depth, int depth_f64, int dmin, int dmax, int H, int W, int n,
+                             const double* lo, const double* hi, uint8_t* out, void* stream) {
+  if (!planes || !depth || !out || H < 1 || W < 1) return fail(NST_ERR_ARG, "nst_mip_merge: bad arguments");
+  MipBins b;
+  CKI(mip_bins(&b, n, lo, hi, depth_f64, dmin, dmax, "nst_mip_merge"));
+  CKI(nst_device_check());
+  CK(launch_mip_merge(planes, depth, depth_f64, static_cast<size_t>(H) * W, b, out, static_cast<cudaStream_t>(stream)));
   return NST_OK;
 }
 

@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "text-based-image-style-transfer_b200")
 CSRC = os.path.join(PKG, "csrc")
-CU = ["api.cu", "conv_tc.cu", "conv_chain.cu", "conv1_tc.cu", "gram.cu", "pixel.cu", "lbfgs.cu", "loss_fn.cu", "mask.cu", "video.cu"]
+CU = ["api.cu", "conv_tc.cu", "conv_chain.cu", "conv1_tc.cu", "gram.cu", "pixel.cu", "lbfgs.cu", "loss_fn.cu", "mask.cu", "video.cu", "depth.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
