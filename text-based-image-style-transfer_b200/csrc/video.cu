@@ -33,12 +33,19 @@ __device__ __forceinline__ uint32_t pack4(float v0, float v1, float v2, float v3
 // One thread: 16 pixels = 48 bytes = three 16-byte words of `prev` and of `frame`, all six loads in flight at once.
 __global__ void __launch_bounds__(256) video_assemble_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out,
                                                              size_t frame_bytes, int F, const __grid_constant__ VideoWeights vw) {
+  // a thread's 48 output bytes go through shared memory so that every store instruction of a warp writes 512 contiguous
+  // bytes: 16-byte stores 48 bytes apart are half-sector writes and cost a third of the bandwidth (measured on the plane split)
+  __shared__ uint4 stage[8][96];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f = blockIdx.y;
+  const size_t chunks = frame_bytes / 48;
   const size_t chunk = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (chunk >= frame_bytes / 48) return;
+  const bool live = chunk < chunks;
+  if (chunk - lane >= chunks) return;  // whole warp past the end
   const int n = (f + 1 < F) ? vw.n : 0;  // the last frame has no successor
-  const uint4* pa = reinterpret_cast<const uint4*>(frames + static_cast<size_t>(f) * frame_bytes) + 3 * chunk;
-  const uint4* pb = reinterpret_cast<const uint4*>(frames + static_cast<size_t>(f + (n ? 1 : 0)) * frame_bytes) + 3 * chunk;
+  const size_t ld = live ? chunk : chunks - 1;  // lanes past the end load the last chunk and store nothing
+  const uint4* pa = reinterpret_cast<const uint4*>(frames + static_cast<size_t>(f) * frame_bytes) + 3 * ld;
+  const uint4* pb = reinterpret_cast<const uint4*>(frames + static_cast<size_t>(f + (n ? 1 : 0)) * frame_bytes) + 3 * ld;
   uint32_t wa[12], wb[12];
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -53,6 +60,18 @@ __global__ void __launch_bounds__(256) video_assemble_kernel(const uint8_t* __re
     }
   }
   uint8_t* po = out + static_cast<size_t>(f) * (vw.n + 1) * frame_bytes;
+  const size_t q0 = 3 * (chunk - lane), q_end = 3 * chunks;  // the warp's first 16-byte word, the end of the frame
+  auto store_frame = [&](uint8_t* frame_out, const uint32_t (&w)[12]) {
+    stage[warp][3 * lane] = make_uint4(w[0], w[1], w[2], w[3]);
+    stage[warp][3 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    stage[warp][3 * lane + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(frame_out) + q0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (q0 + 32 * j + lane < q_end) dst[32 * j + lane] = stage[warp][32 * j + lane];
+    __syncwarp();
+  };
   // output byte j comes from input byte j - (j % 3) + 2 - (j % 3): RGB -> BGR          app.py:803
   float fa[48];
 #pragma unroll
@@ -61,17 +80,10 @@ __global__ void __launch_bounds__(256) video_assemble_kernel(const uint8_t* __re
     fa[j] = byte_as_float(wa[sj >> 2], sj & 3);
   }
   {
-    uint4* o = reinterpret_cast<uint4*>(po) + 3 * chunk;
+    uint32_t w[12];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 16 * q + 4 * e;
-        w[e] = pack4(fa[j], fa[j + 1], fa[j + 2], fa[j + 3]);
-      }
-      o[q] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    for (int e = 0; e < 12; ++e) w[e] = pack4(fa[4 * e], fa[4 * e + 1], fa[4 * e + 2], fa[4 * e + 3]);
+    store_frame(po, w);
   }
   if (n == 0) return;
   float fb[48];
@@ -82,18 +94,14 @@ __global__ void __launch_bounds__(256) video_assemble_kernel(const uint8_t* __re
   }
   for (int i = 0; i < n; ++i) {
     const float a1 = vw.a1[i], a2 = vw.a2[i];
-    uint4* o = reinterpret_cast<uint4*>(po + static_cast<size_t>(i + 1) * frame_bytes) + 3 * chunk;
+    uint32_t w[12];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 16 * q + 4 * e;
-        w[e] = pack4(__fmaf_rn(fa[j], a1, __fmul_rn(fb[j], a2)), __fmaf_rn(fa[j + 1], a1, __fmul_rn(fb[j + 1], a2)),
-                     __fmaf_rn(fa[j + 2], a1, __fmul_rn(fb[j + 2], a2)), __fmaf_rn(fa[j + 3], a1, __fmul_rn(fb[j + 3], a2)));  // :833
-      }
-      o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int e = 0; e < 12; ++e) {
+      const int j = 4 * e;
+      w[e] = pack4(__fmaf_rn(fa[j], a1, __fmul_rn(fb[j], a2)), __fmaf_rn(fa[j + 1], a1, __fmul_rn(fb[j + 1], a2)),
+                   __fmaf_rn(fa[j + 2], a1, __fmul_rn(fb[j + 2], a2)), __fmaf_rn(fa[j + 3], a1, __fmul_rn(fb[j + 3], a2)));  // :833
     }
+    store_frame(po + static_cast<size_t>(i + 1) * frame_bytes, w);
   }
 }
 
