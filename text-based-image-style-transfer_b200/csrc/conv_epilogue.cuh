@@ -17,29 +17,52 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  One thread owns one pixel, so the lanes of a warp are a whole pixel
+// row (>= 128 bytes) apart: with 16-byte accesses every instruction touches half of 32 different 32-byte sectors and a
+// second instruction the other halves; with 32-byte accesses every lane reads / writes one whole sector.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_global_cg_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ void store_h32(__half* dst, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_h2(v[8 * q + 0], v[8 * q + 1]);
-    u.y = pack_h2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_h2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack_h2(v[8 * q + 6], v[8 * q + 7]);
-    d[q] = u;
+  for (int q = 0; q < 4; q += 2) {
+    uint4 u[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      u[e].x = pack_h2(v[8 * (q + e) + 0], v[8 * (q + e) + 1]);
+      u[e].y = pack_h2(v[8 * (q + e) + 2], v[8 * (q + e) + 3]);
+      u[e].z = pack_h2(v[8 * (q + e) + 4], v[8 * (q + e) + 5]);
+      u[e].w = pack_h2(v[8 * (q + e) + 6], v[8 * (q + e) + 7]);
+    }
+    st_global_256(reinterpret_cast<uint8_t*>(dst) + 16 * q, u[0], u[1]);
   }
 }
 template <int CH>
 __device__ __forceinline__ void store_bf(__nv_bfloat16* dst, const float (&v)[CH]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
+  static_assert(CH % 16 == 0, "32-byte stores");
 #pragma unroll
-  for (int q = 0; q < CH / 8; ++q) {
-    uint4 u;
-    u.x = pack_bf2(v[8 * q + 0], v[8 * q + 1]);
-    u.y = pack_bf2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack_bf2(v[8 * q + 6], v[8 * q + 7]);
-    d[q] = u;
+  for (int q = 0; q < CH / 8; q += 2) {
+    uint4 u[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      u[e].x = pack_bf2(v[8 * (q + e) + 0], v[8 * (q + e) + 1]);
+      u[e].y = pack_bf2(v[8 * (q + e) + 2], v[8 * (q + e) + 3]);
+      u[e].z = pack_bf2(v[8 * (q + e) + 4], v[8 * (q + e) + 5]);
+      u[e].w = pack_bf2(v[8 * (q + e) + 6], v[8 * (q + e) + 7]);
+    }
+    st_global_256(reinterpret_cast<uint8_t*>(dst) + 16 * q, u[0], u[1]);
   }
 }
 
@@ -220,14 +243,10 @@ __device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x,
   if (!valid || (p.dbg_flags & 2)) return;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
-    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask_act + pix * p.N + n);
-    x.m[0] = __ldg(m4);
-    x.m[1] = __ldg(m4 + 1);
+    ld_global_nc_256(p.mask_act + pix * p.N + n, x.m[0], x.m[1]);
     if (p.addend != nullptr) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + pix * p.N + n);
-      // L2-coherent loads: in the chained kernel the seed is written earlier in the same launch (by another SM)
-      x.a[0] = __ldcg(a4);
-      x.a[1] = __ldcg(a4 + 1);
+      // L2-coherent load: in the chained kernel the seed is written earlier in the same launch (by another SM)
+      ld_global_cg_256(p.addend + pix * p.N + n, x.a[0], x.a[1]);
     }
   } else {
     x.m[0] = __ldg(reinterpret_cast<const uint4*>(p.route + pix * p.N + n));

@@ -169,11 +169,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
       tmem_ld_wait();
       if (row_ok) {
-        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+        // 32-byte stores: the lanes of a warp are whole rows apart, so a 16-byte store would write half sectors
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                              __uint_as_float(r[4 * j + 3]));
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c * 32 + 8 * j), "r"(r[8 * j]), "r"(r[8 * j + 1]),
+                       "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]), "r"(r[8 * j + 6]), "r"(r[8 * j + 7])
+                       : "memory");
       }
     }
   }
