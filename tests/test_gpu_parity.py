@@ -597,3 +597,28 @@ def test_style_mip_against_reference_golden(nst):
     from oracle import depth_oracle as D
     shared = sum((np.stack(D.generate_mip_layers(np.ones_like(g["mip_content"]), depth, n), 0)[:, :, :, 0] > 0).astype(int)) > 1
     assert psnr_u8(np.asarray(final)[~shared], g["mip_final"][~shared]) >= PSNR_MIN
+
+
+def test_stylise_frames_against_oracle(nst, oracle, vgg_weights):
+    """video.stylise_frames = per-frame loop + frame list: real frames >= 40 dB against the oracle's loop, and the whole list
+    bit-exact against the video oracle applied to OUR stylised frames (the cross-dissolve is byte arithmetic)."""
+    from oracle import video_oracle as V
+    O = oracle
+    ws, bs = vgg_weights
+    video = importlib.import_module("text-based-image-style-transfer_b200.video")
+    H, W, steps, n = 48, 64, 0, 2
+    frames = np.stack([O.synth_image(H, W, 40 + k) for k in range(3)], 0)
+    style = O.synth_image(40, 56, 9)
+    styler = video.FrameStyler(O.VGG_MEAN, O.VGG_STD, (H, W), [O.to_tensor_u8(style).cuda()], num_steps=steps, device="cuda",
+                               **O.APP_WEIGHTS)
+    try:
+        out = video.stylise_frames(torch.from_numpy(frames), styler, n).cpu().numpy()
+        own = [np.ascontiguousarray(out[k * (n + 1)][:, :, ::-1]) for k in range(3)]
+    finally:
+        styler.close()
+    assert out.shape == (2 * (n + 1) + 1, H, W, 3)
+    assert np.array_equal(out, np.stack(V.assemble_frames(own, n), 0))
+    for k in range(3):
+        ref = O.to_u8(O.run_oracle(ws, bs, frames[k], [style], steps, **O.APP_WEIGHTS).image)
+        mse = np.mean((own[k].astype(np.float64) - ref.astype(np.float64)) ** 2)
+        assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= PSNR_MIN, k

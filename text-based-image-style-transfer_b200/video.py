@@ -146,3 +146,16 @@ def assemble_frames(frames_rgb: torch.Tensor, number_of_interpolations: int = 0)
         _lib.check(lib.nst_video_assemble(C.c_void_p(frames_rgb.data_ptr()), int(F), int(H), int(W), n, C.c_void_p(out.data_ptr()),
                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return out
+
+
+def stylise_frames(frames: torch.Tensor, styler: "FrameStyler", number_of_interpolations: int = 0) -> Optional[torch.Tensor]:
+    """The compute of apply_video_process (app.py:784-842) between the decoder and the encoder: every frame through
+    run_multi_style_transfer (frame-sharded over the ranks), then the BGR frame list with cross-dissolves, built on the
+    device of rank 0.  frames: (N, H, W, 3) uint8 RGB (host).  Returns the ((N - 1) * (n + 1) + 1, H, W, 3) uint8 BGR
+    frames as a CUDA tensor on rank 0 and None on the other ranks."""
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    done = run_sharded(frames, styler, styler.device)
+    if rank != 0:
+        return None
+    return assemble_frames(done.to(styler.device), number_of_interpolations)
