@@ -71,6 +71,36 @@ def test_no_cpu_fallback(built_libs):
         L.gram_matrix(torch.zeros(1, 64, 4, 4))
 
 
+def test_mirrors_around_the_loop_keep_reference_names_and_have_no_cpu_path(built_libs):
+    """text/segmentation_style_transfer.py:5, components/style_transfer_depth/*.py, app.py:800-840"""
+    pkg = importlib.import_module("text-based-image-style-transfer_b200")
+    seg = importlib.import_module("text-based-image-style-transfer_b200.text.segmentation_style_transfer")
+    assert list(inspect.signature(seg.segmentation_style_transfer).parameters)[:4] == ["content_image", "style_image", "segmentation_mask",
+                                                                                      "edge_smoothing"]
+    assert inspect.signature(seg.segmentation_style_transfer).parameters["edge_smoothing"].default == 5
+    D = importlib.import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.style_transfer_depth")
+    for name in ("get_depth_map", "style_transfer", "process_mip_layers", "style_MIP", "style_Dept", "depth_split"):
+        assert callable(getattr(D.DepthStyle, name)), name
+    assert list(inspect.signature(D.DepthStyle.style_MIP).parameters) == ["self", "image", "style", "n"]
+    A = importlib.import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.Style_a3")
+    sig = inspect.signature(A.StyleA3.__init__)
+    assert list(sig.parameters)[:11] == ["self", "device", "print_iter", "num_steps", "w_style", "w_content", "w_tv", "w_edge", "w_depth",
+                                         "random_init", "depth_pipeline"]
+    assert sig.parameters["num_steps"].default == 400 and sig.parameters["w_style"].default == 5e5          # Style_a3.py:18
+    U = importlib.import_module("text-based-image-style-transfer_b200.components.style_transfer_depth.util")
+    for name in ("mask_image_depth", "create_bins", "generate_mip_layers", "reconstruct_mip_image", "image_loader", "save_image", "Vgg19",
+                 "normalize", "content_loss", "gram_matrix", "style_loss", "total_variation_loss", "get_gradient_imgs", "edge_loss"):
+        assert hasattr(U, name), name
+    assert [list(map(float, b)) for b in U.create_bins(4)] == [[0.0, 0.25], [0.25, 0.5], [0.5, 0.75], [0.75, 1.0]]
+    V = importlib.import_module("text-based-image-style-transfer_b200.video")
+    with pytest.raises(pkg.NstError):
+        D.DepthStyle("cpu", depth_pipeline=lambda image: None)
+    with pytest.raises(pkg.NstError):
+        V.assemble_frames(torch.zeros((2, 4, 4, 3), dtype=torch.uint8), 1)
+    with pytest.raises(pkg.NstError):
+        seg.composite_tensors(torch.zeros((4, 4, 3), dtype=torch.uint8), torch.zeros((4, 4, 3), dtype=torch.uint8), torch.zeros((4, 4), dtype=torch.bool))
+
+
 def test_product_never_imports_the_oracle():
     pkg_dir = os.path.join(ROOT, "text-based-image-style-transfer_b200")
     for dirpath, _, files in os.walk(pkg_dir):
