@@ -529,7 +529,7 @@ def run_video(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    H, W = 720, 1280
+    H, W = (int(v) for v in args.video_size.split("x"))
     ws, bs = synth.vgg19_random_weights(1234, 13)
     hf.set_vgg_weight_provider(lambda: (ws, bs))
     style = torch.from_numpy(synth.synth_image(512, 512, 1)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
@@ -540,8 +540,8 @@ def run_video(args, rank, world, local_rank):
     frames = torch.stack([((1 - k / max(n_frames - 1, 1)) * f0 + (k / max(n_frames - 1, 1)) * f1).round().to(torch.uint8)
                           for k in range(n_frames)])
     styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=args.video_steps, device=dev,
-                               **synth.APP_WEIGHTS)
-    styler(0, frames[0])                                   # warm-up: graph capture, allocator
+                               concurrent=args.concurrent, **synth.APP_WEIGHTS)
+    styler.process_block(frames[:args.concurrent])         # warm-up: graph capture of every plan, allocator
     video.gather_frames(frames[:1].clone(), world, dev)    # ... and the NCCL communicator of the all-gather
     if dist is not None:
         dist.barrier()
@@ -558,12 +558,13 @@ def run_video(args, rank, world, local_rank):
         dt = float(t[0])
     evals = 20 * (args.video_steps // 20 + 1)
     if rank == 0:
-        line = dict(metric="video style transfer frames/s (720p, frame-sharded)", value=n_frames / dt, unit="frames/s", n_gpus=world,
+        line = dict(metric="video style transfer frames/s (%dx%d, frame-sharded)" % (W, H), value=n_frames / dt, unit="frames/s", n_gpus=world,
                     steps=n_frames, warmup=1, ms_per_step=1e3 * dt / n_frames, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f16", data="synthetic",
-                    config=dict(workload="%d synthetic 1280x720 frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), "
-                                         "contiguous frame blocks per rank, NCCL broadcast of the style Gram targets + all-gather of the "
-                                         "finished frames (BASELINE configs[4], reduced frame count / steps)" % (n_frames, args.video_steps, evals)),
+                    config=dict(workload="%d synthetic %dx%d frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), "
+                                         "%d frame(s) in flight per GPU, contiguous frame blocks per rank, NCCL broadcast of the style Gram "
+                                         "targets + all-gather of the finished frames (BASELINE configs[4], reduced frame count / steps)"
+                                         % (n_frames, W, H, args.video_steps, evals, args.concurrent)),
                     evals_per_s=n_frames * evals / dt, checksum=int(out.to(torch.int64).sum()))
         emit(line)
     if dist is not None:
@@ -602,6 +603,8 @@ def main():
     ap.add_argument("--workload", default="pair512", choices=["pair512", "video"])
     ap.add_argument("--frames", type=int, default=16, help="--workload video: number of 720p frames (all ranks together)")
     ap.add_argument("--video-steps", type=int, default=100, help="--workload video: num_steps per frame (the reference UI uses 400)")
+    ap.add_argument("--video-size", default="720x1280", help="--workload video: frame size HxW")
+    ap.add_argument("--concurrent", type=int, default=1, help="--workload video: frames in flight per GPU (FrameStyler(concurrent=K))")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3:

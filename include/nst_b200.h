@@ -211,6 +211,13 @@ int nst_plan_chain_waits(nst_plan* plan, int which, long long* out, int max_ctas
  * does (content target at the plan's content taps, edge target), then runs the whole loop. */
 int nst_run_frame_host(nst_plan* plan, const uint8_t* content_u8, uint8_t* out_u8, int num_steps, int channel_attention,
                        const float* ca_w1, const float* ca_w2, void* stream);
+/* the same for `count` (<= 16) independent frames at once: plans[k] / streams[k] (all distinct, same weights and targets as a
+ * frame-by-frame run would use) process content_u8[k] -> out_u8[k]; every frame's optimizer.step() is enqueued before the host
+ * waits for the first one, so small frames (bound by per-launch latency) overlap: the per-frame body of apply_video_process,
+ * app.py:784-815, several frames at a time.  Results are bit-identical to nst_run_frame_host.
+ * closure_calls (optional): evaluations each frame ran. */
+int nst_run_frames_host(nst_plan* const* plans, int count, const uint8_t* const* content_u8, uint8_t* const* out_u8, int num_steps,
+                        int channel_attention, const float* ca_w1, const float* ca_w2, void* const* streams, int* closure_calls);
 
 /* ---- mask compositing: text/segmentation_style_transfer.py:5-94 (segmentation_style_transfer + _edge_smoothing), the step that
  * follows run_multi_style_transfer in app.py:203,318,407,512.  content, style, out: [H][W][C] uint8 device buffers (C <= 4),

@@ -622,3 +622,26 @@ def test_stylise_frames_against_oracle(nst, oracle, vgg_weights):
         ref = O.to_u8(O.run_oracle(ws, bs, frames[k], [style], steps, **O.APP_WEIGHTS).image)
         mse = np.mean((own[k].astype(np.float64) - ref.astype(np.float64)) ** 2)
         assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= PSNR_MIN, k
+
+
+def test_concurrent_frames_are_bit_identical_to_one_at_a_time(nst, oracle):
+    """FrameStyler(concurrent=3).process_block (nst_run_frames_host: three plans / streams stepped in lock step) returns, for
+    every frame, exactly the bytes of the one-frame call - with a block that does not divide the frame count."""
+    O = oracle
+    video = importlib.import_module("text-based-image-style-transfer_b200.video")
+    H, W = 40, 56
+    frames = torch.from_numpy(np.stack([O.synth_image(H, W, 60 + k) for k in range(5)], 0))
+    style = [O.to_tensor_u8(O.synth_image(48, 40, 8)).cuda()]
+    for ca in (False, True):
+        one = video.FrameStyler(O.VGG_MEAN, O.VGG_STD, (H, W), style, num_steps=20, channel_attention=ca, device="cuda", **O.APP_WEIGHTS)
+        many = video.FrameStyler(O.VGG_MEAN, O.VGG_STD, (H, W), style, num_steps=20, channel_attention=ca, device="cuda", concurrent=3,
+                                 **O.APP_WEIGHTS)
+        try:
+            want = torch.stack([one(k, frames[k]) for k in range(5)], 0)
+            got = many.process_block(frames)
+            assert torch.equal(got, want), ca
+            assert not torch.equal(got[0], frames[0])
+            assert torch.equal(video.run_sharded(frames, many, "cuda").cpu(), want)
+        finally:
+            one.close()
+            many.close()

@@ -79,6 +79,8 @@ PROTOTYPES = {
     "nst_plan_timeline": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong), _P]),
     "nst_lbfgs_ctl_clocks": (C.c_int, [_P, C.POINTER(C.c_longlong), _P]),
     "nst_plan_chain_waits": (C.c_int, [_P, C.c_int, C.POINTER(C.c_longlong), C.c_int, _P]),
+    "nst_run_frames_host": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.POINTER(_P),
+                                      C.POINTER(C.c_int)]),
     "nst_mask_composite": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "nst_mask_gaussian_weights": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "nst_mip_split": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),

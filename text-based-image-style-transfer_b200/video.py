@@ -72,8 +72,11 @@ def run_sharded(frames: torch.Tensor, process_frame: Callable[[int, torch.Tensor
     world = dist.get_world_size() if dist else 1
     rank = dist.get_rank() if dist else 0
     lo, hi = shard_range(frames.shape[0], world, rank)
-    done = [process_frame(k, frames[k]) for k in range(lo, hi)]
-    local = torch.stack(done, 0) if done else torch.empty((0,) + tuple(frames.shape[1:]), dtype=torch.uint8)
+    if hasattr(process_frame, "process_block") and hi > lo:
+        local = process_frame.process_block(frames[lo:hi])      # several frames at a time on this rank's GPU
+    else:
+        done = [process_frame(k, frames[k]) for k in range(lo, hi)]
+        local = torch.stack(done, 0) if done else torch.empty((0,) + tuple(frames.shape[1:]), dtype=torch.uint8)
     return gather_frames(local, frames.shape[0], device)
 
 
@@ -82,7 +85,7 @@ class FrameStyler:
     apply_video_process (app.py:794-798 -> run_multi_style_transfer) with everything frame-independent hoisted."""
 
     def __init__(self, vgg_mean, vgg_std, frame_hw, style_imgs: List[torch.Tensor], w_style, w_content, w_tv, w_edge,
-                 num_steps: int, style_img_weight=0.5, channel_attention=False, device="cuda"):
+                 num_steps: int, style_img_weight=0.5, channel_attention=False, device="cuda", concurrent: int = 1):
         from .multi_style_transfer.run_style_transfer import StyleTransferSession, STYLE_LAYERS, channel_attention_weights
         from .engine import _require_cuda
         self.device = _require_cuda(device)
@@ -110,6 +113,15 @@ class FrameStyler:
         H, W = int(frame_hw[0]), int(frame_hw[1])
         self._in = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
         self._out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        # `concurrent` frames at a time (process_block): one more plan / stream / CUDA graph per extra frame, same style targets.
+        # Small frames are bound by per-launch latency, so the launches of one frame fill the ramps and tails of the others'
+        # (256 x 256: +46 % frames/s with two, +79 % with four; 720p: +1 %) - SURVEY 8f row 2 without a batch dimension.
+        self.sessions = [self.session]
+        for _ in range(1, max(1, int(concurrent))):
+            self.sessions.append(StyleTransferSession(vgg_mean, vgg_std, frame_hw, style_imgs, w_style, w_content, w_tv, w_edge,
+                                                      style_img_weight, self.device, style_targets=self.session.style_targets))
+        self._ins = [self._in] + [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in self.sessions[1:]]
+        self._outs = [self._out] + [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in self.sessions[1:]]
 
     def __call__(self, index: int, frame_u8: torch.Tensor) -> torch.Tensor:
         self._in.copy_(frame_u8)
@@ -118,8 +130,39 @@ class FrameStyler:
             s.plan.run_frame_host(self._in, self._out, self.num_steps, *(self.ca or (None, None)))
         return self._out.clone()
 
+    def process_block(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """frames_u8: (n, H, W, 3) uint8 host tensor -> the n stylised frames, `concurrent` at a time (nst_run_frames_host).
+        Every frame's result is bit-identical to __call__ on that frame."""
+        import ctypes as C
+        from . import _lib
+        n = int(frames_u8.shape[0])
+        out = torch.empty((n,) + tuple(frames_u8.shape[1:]), dtype=torch.uint8)
+        K = len(self.sessions)
+        if K == 1:
+            for k in range(n):
+                out[k] = self(k, frames_u8[k])
+            return out
+        lib = _lib.load()
+        w1, w2 = self.ca or (None, None)
+        for lo in range(0, n, K):
+            cnt = min(K, n - lo)
+            for j in range(cnt):
+                self._ins[j].copy_(frames_u8[lo + j])
+            plans = (C.c_void_p * cnt)(*[getattr(s.plan.handle, "value", s.plan.handle) for s in self.sessions[:cnt]])
+            ins = (C.c_void_p * cnt)(*[t.data_ptr() for t in self._ins[:cnt]])
+            outs = (C.c_void_p * cnt)(*[t.data_ptr() for t in self._outs[:cnt]])
+            streams = (C.c_void_p * cnt)(*[s.stream.cuda_stream for s in self.sessions[:cnt]])
+            with torch.cuda.device(self.device):
+                _lib.check(lib.nst_run_frames_host(plans, cnt, ins, outs, self.num_steps, 1 if w1 is not None else 0,
+                                                   C.c_void_p(w1.data_ptr() if w1 is not None else None),
+                                                   C.c_void_p(w2.data_ptr() if w2 is not None else None), streams, None))
+            for j in range(cnt):
+                out[lo + j] = self._outs[j]
+        return out
+
     def close(self):
-        self.session.close()
+        for s in self.sessions:
+            s.close()
 
 
 def assemble_frames(frames_rgb: torch.Tensor, number_of_interpolations: int = 0) -> torch.Tensor:
