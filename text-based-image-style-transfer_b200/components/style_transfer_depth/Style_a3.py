@@ -34,6 +34,8 @@ class StyleA3:
         self._session = None
         self._session_key = None
         self.last_trace = None
+        self._extra = []   # further sessions of style_transfer_planes (one per plane after the first)
+        self._extra_key = None
         self.traces = []   # loss rows {total, content, style, tv, edge} of the most recent runs (at most 16)
 
     def _get_depth_map(self, image):
@@ -88,7 +90,60 @@ class StyleA3:
         optim_img, _ = self._run_style_transfer(style, content)
         return save_image(optim_img)
 
+    def style_transfer_planes(self, style, contents, strengths):
+        """style_transfer (:168-193) for several equally sized content images at once - the planes of a multi-plane run
+        (style_transfer_depth.py:72) - each with its own strength: one plan / stream per image, stepped in lock step
+        (nst_run_frames_host), so the planes overlap on the GPU instead of queueing.  Same results as one call per image."""
+        import ctypes as C
+        from ... import _lib
+        arrs = [np.ascontiguousarray(np.asarray(c)) for c in contents]
+        if len(arrs) < 2 or self.random_init or any(a.shape != arrs[0].shape or a.ndim != 3 or a.shape[2] != 3 or a.dtype != np.uint8
+                                                    for a in arrs):
+            return [self.style_transfer(style, c, strength=s) for c, s in zip(contents, strengths)]
+        self.w_depth = 0
+        style_img = image_loader(style, device=self.device)
+        H, W = arrs[0].shape[:2]
+        key = ((H, W), tuple(style_img.shape), hash(style_img.cpu().numpy().tobytes()))
+        first = self._session_for(style_img, (H, W))
+        if getattr(self, "_extra_key", None) != key:
+            self._close_extra()
+            self._extra_key = key
+        while len(self._extra) < len(arrs) - 1:
+            self._extra.append(StyleTransferSession(self.vgg_mean, self.vgg_std, (H, W), [style_img], self.w_style, self.w_content, self.w_tv,
+                                                    self.w_edge, 0.5, self.device, self.content_layers, self.style_layers,
+                                                    style_targets=first.style_targets))
+        sessions = [first] + self._extra[:len(arrs) - 1]
+        evals = 20 * (int(self.num_steps) // 20 + 1)
+        for sess, strength in zip(sessions, strengths):
+            w_style = 5e5 if strength < 0 else 5e5 * (np.e ** (strength - 1 / strength))       # :184-187
+            print(f"w_style: {w_style}")
+            print(f"Style Transfer with strength {strength}")
+            with torch.cuda.device(self.device), torch.cuda.stream(sess.stream):
+                sess.plan.set_weights(float(w_style), float(self.w_content), float(self.w_tv), float(self.w_edge))
+            sess.weights = (float(w_style), float(self.w_content), float(self.w_tv), float(self.w_edge))
+            self.w_style = w_style
+        ins = [torch.from_numpy(a).pin_memory() for a in arrs]
+        outs = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in arrs]
+        n = len(arrs)
+        plans = (C.c_void_p * n)(*[getattr(s.plan.handle, "value", s.plan.handle) for s in sessions])
+        pin = (C.c_void_p * n)(*[t.data_ptr() for t in ins])
+        pout = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+        streams = (C.c_void_p * n)(*[s.stream.cuda_stream for s in sessions])
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().nst_run_frames_host(plans, n, pin, pout, int(self.num_steps), 0, None, None, streams, None))
+        from PIL import Image
+        for sess in sessions:
+            self.last_trace = sess.trace(evals + 32)
+            self.traces = (self.traces + [self.last_trace])[-16:]
+        return [Image.fromarray(o.numpy().copy()) for o in outs]
+
+    def _close_extra(self):
+        for s in getattr(self, "_extra", []):
+            s.close()
+        self._extra = []
+
     def close(self):
+        self._close_extra()
         if self._session is not None:
             self._session.close()
             self._session = None

@@ -27,8 +27,10 @@ class DepthStyle:
         return self.style_pipeline(style, image, strength=strength)
 
     def process_mip_layers(self, masked_images, style):
-        """:61-72: plane ind is stylised with strength 1 - ind / n; all planes share one VGG plan and one set of style targets."""
-        return [self.style_transfer(img, style, (1 - ind / len(masked_images))) for ind, img in enumerate(masked_images)]
+        """:61-72: plane ind is stylised with strength 1 - ind / n; the planes share the style targets and run at the same time
+        (one plan / stream each, nst_run_frames_host)."""
+        strengths = [(1 - ind / len(masked_images)) for ind in range(len(masked_images))]
+        return self.style_model.style_transfer_planes(style, masked_images, strengths)
 
     def style_MIP(self, image, style, n=2):
         """:74-90"""
