@@ -59,6 +59,21 @@ def _worker(rank, world, port, n_frames, q):
             return (255 - f.to(torch.int16)).to(torch.uint8) + torch.tensor(k % 3, dtype=torch.uint8)
 
         out = v.run_sharded(frames, process, "cpu")
+
+        class BlockProcessor:      # the shape of FrameStyler(concurrent=K): run_sharded hands it this rank's whole block
+            blocks = []
+
+            def __call__(self, k, f):
+                raise AssertionError("run_sharded must use process_block when there is one")
+
+            def process_block(self, fr):
+                self.blocks.append(int(fr.shape[0]))
+                return 255 - fr
+
+        bp = BlockProcessor()
+        out_b = v.run_sharded(frames, bp, "cpu")
+        lo, hi = v.shard_range(n_frames, world, rank)
+        assert torch.equal(out_b, 255 - frames) and bp.blocks == ([hi - lo] if hi > lo else [])
         want = torch.stack([(255 - frames[k].to(torch.int16)).to(torch.uint8) + torch.tensor(k % 3, dtype=torch.uint8)
                             for k in range(n_frames)])
         q.put((rank, chk, seen, bool(torch.equal(out, want))))
