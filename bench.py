@@ -43,9 +43,9 @@ def env_int(name, default):
 
 def ncu_traffic():
     """Average DRAM bytes (read + write) per conv_tc_kernel launch from the committed `ncu --set full` capture of one
-    evaluation's launches (profiles/r01c_ncu_full_conv_tc_summary.csv); None if the summary is missing."""
+    evaluation's launches (profiles/r01d_ncu_full_conv_tc_summary.csv); None if the summary is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01c_ncu_full_conv_tc_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r01d_ncu_full_conv_tc_summary.csv")
     if not os.path.exists(path):
         return None
     rows = list(csv.reader(open(path)))
@@ -449,7 +449,7 @@ def run_b200(args, rank, world, local_rank):
     roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient launches per evaluation, the Gram backward "
                            "of conv1_1..conv4_1 folded into the data gradients as a second accumulator, + 1 Gram-backward launch for conv5_1)",
                     achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
-                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the conv_tc_kernel launches of one evaluation (ncu --set full, profiles/r01c_ncu_full_conv_tc_summary.csv)",
+                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the conv_tc_kernel launches of one evaluation (ncu --set full, profiles/r01d_ncu_full_conv_tc_summary.csv)",
                     peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
                     avg_launch_ms=conv_ms / conv_launches,
