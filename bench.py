@@ -156,28 +156,23 @@ def bench_mip(dev, pk):
     d_dev = torch.from_numpy(depth).to(dev)
 
     out = {}
-    orig = U._depth_args
-    lo_hi = (int(depth.min()), int(depth.max()))
-    U._depth_args = lambda d, dv: (d_dev, 0) + lo_hi   # the depth map is already on the device: its upload is not kernel time
-    try:
-        for name, fn, nbytes in (("split", lambda: U.split_planes(img, depth, bins), (4 + 3 * n) * S * S2),
-                                 ("merge", lambda: U.merge_planes(planes, depth, bins), 7 * S * S2)):
-            if name == "split":
-                planes = fn()
-            for _ in range(3):
-                res = fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(10):
-                res = fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 10
-            gbs = nbytes / (ms * 1e-3) / 1e9
-            out[name] = dict(ms=ms, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], bytes=nbytes)
-    finally:
-        U._depth_args = orig
+    lo_hi = (int(depth.min()), int(depth.max()))   # the depth map is already on the device: its upload is not kernel time
+    for name, fn, nbytes in (("split", lambda: U.split_planes(img, d_dev, bins, depth_range=lo_hi), (4 + 3 * n) * S * S2),
+                             ("merge", lambda: U.merge_planes(planes, d_dev, bins, depth_range=lo_hi), 7 * S * S2)):
+        if name == "split":
+            planes = fn()
+        for _ in range(3):
+            res = fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = dict(ms=ms, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], bytes=nbytes)
     c_img, c_depth = img[:512, :512].contiguous(), depth[:512, :512]
     got_p = U.split_planes(c_img, c_depth, bins)
     got_m = U.merge_planes(got_p, c_depth, bins)

@@ -557,6 +557,10 @@ def test_mip_split_merge_bit_exact_against_oracle(nst, n):
         planes = U.split_planes(torch.from_numpy(img).cuda(), depth, bins)
         want = np.stack(D.generate_mip_layers(img, depth, n), 0)
         assert np.array_equal(planes.cpu().numpy(), want), (n, H, W, kind)
+        if depth.dtype == np.uint8:   # the depth map handed over as a device tensor, with and without its range
+            d_dev = torch.from_numpy(depth).cuda()
+            assert torch.equal(U.split_planes(torch.from_numpy(img).cuda(), d_dev, bins), planes)
+            assert torch.equal(U.split_planes(torch.from_numpy(img).cuda(), d_dev, bins, depth_range=(int(depth.min()), int(depth.max()))), planes)
         styl = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
         merged = U.merge_planes(torch.from_numpy(styl).cuda(), depth, bins)
         assert np.array_equal(merged.cpu().numpy(), D.reconstruct_mip_image(list(styl), depth, n)), (n, H, W, kind)

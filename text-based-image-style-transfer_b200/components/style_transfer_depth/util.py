@@ -19,9 +19,15 @@ from ...multi_style_transfer.style_transfer_losses import (content_loss, edge_lo
 _DEVICE = "cuda"
 
 
-def _depth_args(depth, dev):
+def _depth_args(depth, dev, depth_range=None):
     """The depth map as the kernels take it: uint8 maps go up as they are with their min / max (normalised in the kernel exactly
-    like util.py:27), any other dtype is normalised here with the reference's own expression and goes up as fp64."""
+    like util.py:27), any other dtype is normalised here with the reference's own expression and goes up as fp64.
+    A uint8 CUDA tensor is used where it is (depth_range = its (min, max) if the caller knows them, else one reduction)."""
+    if isinstance(depth, torch.Tensor) and depth.is_cuda:
+        if depth.dtype != torch.uint8 or depth.dim() != 2:
+            raise ValueError("a device depth map must be a (H, W) uint8 tensor")
+        lo, hi = depth_range if depth_range is not None else (int(depth.min()), int(depth.max()))
+        return depth.to(dev).contiguous(), 0, int(lo), int(hi)
     depth = np.asarray(depth)
     if len(depth.shape) > 2:
         raise ValueError("The depth map (image2) must be a single-channel image.")          # util.py:24-25
@@ -38,12 +44,12 @@ def _bounds(bins):
     return lo, hi
 
 
-def split_planes(image_u8: torch.Tensor, depth, bins, device=None) -> torch.Tensor:
+def split_planes(image_u8: torch.Tensor, depth, bins, device=None, depth_range=None) -> torch.Tensor:
     """image_u8: (H, W, C) uint8 CUDA tensor -> (len(bins), H, W, C): plane i keeps the pixels whose normalised depth is in bins[i]."""
     dev = _require_cuda(device or image_u8.device)
     image_u8 = image_u8.to(dev).contiguous()
     H, W, Cc = image_u8.shape
-    d, f64, dmin, dmax = _depth_args(depth, dev)
+    d, f64, dmin, dmax = _depth_args(depth, dev, depth_range)
     if tuple(d.shape) != (H, W):
         raise IndexError("boolean index did not match indexed array: depth %s vs image %s" % (tuple(d.shape), (H, W)))
     out = torch.empty((len(bins), H, W, Cc), dtype=torch.uint8, device=dev)
@@ -55,14 +61,14 @@ def split_planes(image_u8: torch.Tensor, depth, bins, device=None) -> torch.Tens
     return out
 
 
-def merge_planes(planes_u8: torch.Tensor, depth, bins, device=None) -> torch.Tensor:
+def merge_planes(planes_u8: torch.Tensor, depth, bins, device=None, depth_range=None) -> torch.Tensor:
     """planes_u8: (n, H, W, 3) uint8 CUDA tensor -> (H, W, 3): the planes masked with their bins and added up in uint8."""
     dev = _require_cuda(device or planes_u8.device)
     planes_u8 = planes_u8.to(dev).contiguous()
     n, H, W, Cc = planes_u8.shape
     if Cc != 3 or n != len(bins):
         raise ValueError("planes must be (len(bins), H, W, 3)")
-    d, f64, dmin, dmax = _depth_args(depth, dev)
+    d, f64, dmin, dmax = _depth_args(depth, dev, depth_range)
     if tuple(d.shape) != (H, W):
         raise IndexError("boolean index did not match indexed array: depth %s vs image %s" % (tuple(d.shape), (H, W)))
     out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)

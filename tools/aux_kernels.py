@@ -31,7 +31,6 @@ depth = ((np.sin(y2 / 300.0) + np.cos(x2 / 450.0) + 2) * 63).astype(np.uint8)
 bins = U.create_bins(n)
 d_dev = torch.from_numpy(depth).to(dev)
 lo_hi = (int(depth.min()), int(depth.max()))
-U._depth_args = lambda d, dv: (d_dev, 0) + lo_hi
 planes = None
 
 
@@ -55,5 +54,5 @@ def run(name, fn, nbytes):
 
 run("mask_composite", lambda: seg.composite_tensors(content, style, mask, 5), 7 * S * S)
 run("video_assemble", lambda: video.assemble_frames(frames, 3), (64 + 253) * 720 * 1280 * 3)
-planes = run("mip_split", lambda: U.split_planes(img, depth, bins), (4 + 3 * n) * H2 * W2)
-run("mip_merge", lambda: U.merge_planes(planes, depth, bins), 7 * H2 * W2)
+planes = run("mip_split", lambda: U.split_planes(img, d_dev, bins, depth_range=lo_hi), (4 + 3 * n) * H2 * W2)
+run("mip_merge", lambda: U.merge_planes(planes, d_dev, bins, depth_range=lo_hi), 7 * H2 * W2)
