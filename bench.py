@@ -41,11 +41,21 @@ def env_int(name, default):
         return default
 
 
+def _ncu_summary_name():
+    for name in ("r02_ncu_full_conv_tc_summary.csv", "r01d_ncu_full_conv_tc_summary.csv"):
+        if os.path.exists(os.path.join(ROOT, "profiles", name)):
+            return name
+    return "r02_ncu_full_conv_tc_summary.csv"
+
+
+NCU_SUMMARY = _ncu_summary_name()
+
+
 def ncu_traffic():
     """Average DRAM bytes (read + write) per conv_tc_kernel launch from the committed `ncu --set full` capture of one
-    evaluation's launches (profiles/r01d_ncu_full_conv_tc_summary.csv); None if the summary is missing."""
+    evaluation's launches (profiles/<NCU_SUMMARY>: the newest round's capture); None if the summary is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01d_ncu_full_conv_tc_summary.csv")
+    path = os.path.join(ROOT, "profiles", NCU_SUMMARY)
     if not os.path.exists(path):
         return None
     rows = list(csv.reader(open(path)))
@@ -272,6 +282,95 @@ def time_oracle(size, budget_s, max_evals, warm_evals=1):
                        % (evals, size, size, torch.__version__, cores)), evals, dt
 
 
+def time_torch_eager_gpu(size, dev, budget_s=20.0, max_evals=60, warm_evals=2):
+    """The reference's algorithm under plain torch eager ON THE GPU: the oracle port with device="cuda" - cuDNN convolutions
+    (torch's default cudnn.allow_tf32=True: TF32), fp32 cuBLAS bmm for the Gram matrices (cuda.matmul.allow_tf32=False), autograd
+    with the reference's dead weight gradients and per-evaluation style targets, and L-BFGS with its 4-5 host syncs per
+    iteration.  This is what a maintainer gets today by passing device="cuda" to the reference on a B200 (SURVEY section 7 step 0);
+    none of this repo's kernels run in it."""
+    import torch
+    from oracle import nst_oracle as O
+    ws, bs = O.vgg19_random_weights(1234, 13)
+    content, style = O.synth_image(size, size, 0), O.synth_image(size, size, 1)
+    stamps = []
+
+    def on_eval(k):
+        torch.cuda.synchronize(dev)
+        stamps.append(time.perf_counter())
+        timed = len(stamps) - warm_evals
+        return timed >= max_evals or (timed >= 40 and stamps[-1] - stamps[warm_evals - 1] >= budget_s)
+
+    free0 = torch.cuda.mem_get_info(dev)[0]
+    O.run_oracle(ws, bs, content, [style], 10 ** 9, emulate_reference_cost=True, on_eval=on_eval, device=dev, **O.APP_WEIGHTS)
+    dt = stamps[-1] - stamps[warm_evals - 1]
+    evals = len(stamps) - warm_evals
+    peak_mb = torch.cuda.max_memory_allocated(dev) / 2 ** 20
+    torch.cuda.empty_cache()
+    return dict(value=evals / dt, unit=UNIT, evals=evals, seconds=dt, ms_per_eval=1e3 * dt / evals,
+                cudnn_allow_tf32=bool(torch.backends.cudnn.allow_tf32), matmul_allow_tf32=bool(torch.backends.cuda.matmul.allow_tf32),
+                torch=torch.__version__, cudnn=torch.backends.cudnn.version(), peak_alloc_mb=peak_mb, free_mb_before=free0 / 2 ** 20,
+                what="reference algorithm (oracle port, emulate_reference_cost) on device=cuda under torch eager: %d closure evaluations "
+                     "(+ L-BFGS updates) of one %dx%d run after %d untimed evaluations; wall clock with a device sync per evaluation "
+                     "(the reference syncs there too: float(closure()))" % (evals, size, size, warm_evals))
+
+
+def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
+    """BASELINE configs[4] / metric "video frames/s at 1/2/4/8 B200", app.py:784-815: a FIXED number of synthetic 720p frames
+    (the same total at every N: strong scaling), one shared 512x512 style, frame-sharded in contiguous blocks, style Gram
+    targets computed on rank 0 and broadcast, finished uint8 frames all-gathered in order.  Every frame is a whole
+    run_multi_style_transfer on host uint8 buffers (H2D, content / edge targets, the loop, D2H).  Frame count and num_steps are
+    reduced against the reference UI's 240 x num_steps=400 so that the row fits the bench's time budget; both are stated."""
+    import torch
+    from nst_b200 import video
+    H, W = (int(v) for v in args.video_size.split("x"))
+    n_frames = args.video_row_frames
+    steps = args.video_row_steps
+    evals = 20 * (steps // 20 + 1)
+    style = torch.from_numpy(synth.synth_image(512, 512, 1)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
+    f0 = torch.from_numpy(synth.synth_image(H, W, 100)).float()
+    f1 = torch.from_numpy(synth.synth_image(H, W, 101)).float()
+    frames = torch.stack([((1 - k / max(n_frames - 1, 1)) * f0 + (k / max(n_frames - 1, 1)) * f1).round().to(torch.uint8)
+                          for k in range(n_frames)])
+    t_setup = time.perf_counter()
+    styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=steps, device=dev, **synth.APP_WEIGHTS)
+    styler.process_block(frames[:1])                       # warm-up: graph capture, allocator, pinned buffers
+    video.gather_frames(frames[:1].clone().to(dev), world, dev)   # ... and the communicator of the all-gather
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    lo, hi = video.shard_range(n_frames, world, rank)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    local = styler.process_block(frames[lo:hi]) if hi > lo else torch.empty((0, H, W, 3), dtype=torch.uint8)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    out = video.gather_frames(local, n_frames, dev)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t2 = time.perf_counter()
+    dt, gather = t2 - t0, t2 - t1
+    if dist is not None:
+        t = torch.tensor([dt, t1 - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, compute = float(t[0]), float(t[1])
+    else:
+        compute = t1 - t0
+    checksum = int(out.to(torch.int64).sum()) if rank == 0 else None
+    styler.close()
+    del styler
+    torch.cuda.empty_cache()
+    return dict(metric="video style transfer frames/s (%dx%d, frame-sharded)" % (W, H), value=n_frames / dt, unit="frames/s",
+                frames=n_frames, frames_per_rank=hi - lo, n_gpus=world, num_steps=steps, evals_per_frame=evals, seconds=dt,
+                slowest_rank_compute_s=compute, gather_s_rank0=gather, setup_s_untimed=setup_s, evals_per_s=n_frames * evals / dt,
+                scaling="strong", h2d_bytes_per_frame=3 * H * W, d2h_bytes_per_frame=3 * H * W, checksum=checksum,
+                what="%d synthetic %dx%d frames in total at every N (strong scaling), one shared 512x512 style, num_steps=%d (%d evaluations per "
+                     "frame; the reference UI uses 240 frames x num_steps=400), contiguous frame blocks per rank, NCCL broadcast of the style Gram "
+                     "targets (untimed setup) + all-gather of the finished frames (timed); wall clock, barrier on both sides, max over ranks"
+                     % (n_frames, W, H, steps, evals))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -280,8 +379,8 @@ def run_reference(args, rank, world):
     line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 / base["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
-                config=dict(workload=workload_name(args.size),
-                            note="reference's CPU path (oracle port; /root/reference is Python and cannot travel to the GPU box), "
+                config=dict(workload=workload_name(args.size)),
+                detail=dict(note="reference's CPU path (oracle port; /root/reference is Python and cannot travel to the GPU box), "
                                  "host cores only, bounded sample"),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -350,10 +449,19 @@ def run_b200(args, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
 
-    # ---- warm-up (also captures the CUDA graph and fills part of the L-BFGS history)
-    sess.prepare(content, trace_capacity=Wm + K + 64)
-    enqueue_evals(max(Wm, 3))
+    # ---- warm-up.  The CUDA graph of optimizer.step() (~800 nodes) is captured, instantiated and uploaded HERE, explicitly
+    #      (nst_lbfgs_prepare_graph), and at least one whole graph launch runs before the timed region whatever --warmup
+    #      is: in r01 a --warmup below 20 only ran directly-enqueued evaluations and the capture fell inside ev0..ev1.
+    #      One trace capacity for every prepare() of this process: a larger capacity drops the graph (api.cu).
+    JOB_STEPS, JOB_EVALS = 300, 320                       # BASELINE configs[1]: num_steps=300 -> 320 closure evaluations
+    trace_cap = max(Wm + K, JOB_EVALS) + 64
+    sess.prepare(content, trace_capacity=trace_cap)
+    with torch.cuda.stream(stream):
+        plan.lbfgs_prepare_graph()
+    warm_evals = 20 * ((max(Wm, 3) + 19) // 20)           # whole optimizer.step()s: >= --warmup evaluations, >= 1 graph launch
+    enqueue_evals(warm_evals)
     stream.synchronize()
+    hist_start = sess.status().hist_len
 
     # ---- timed region: K evaluations, CUDA events on the launching stream, barrier + sync on both sides
     sampler = ClockSampler(local_rank)
@@ -370,37 +478,71 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     st = sess.status()
     hist_len = st.hist_len
     final_loss = st.loss
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+        return float(t[0])
+
+    ms = max_over_ranks(ms)
     value = world * K / (ms * 1e-3)
 
-    # ---- e2e: the public host-buffer call (uint8 image in pinned host memory -> stylised uint8 image in pinned host memory)
-    evals_e2e = max(20, (K // 20) * 20)
+    # ---- the whole job of BASELINE configs[1], device-timed: fresh optimizer state, num_steps=300 -> 320 evaluations =
+    #      16 graph launches (the history grows 0 -> 100 pairs on the way, run-average ~84)
+    sess.prepare(content, trace_capacity=trace_cap)       # same capacity: the captured graph survives
+    with torch.cuda.stream(stream):
+        plan.lbfgs_prepare_graph()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        ev2.record(stream)
+    launches_320 = enqueue_evals(JOB_EVALS)
+    with torch.cuda.stream(stream):
+        ev3.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms_320 = max_over_ranks(ev2.elapsed_time(ev3))
+    st320 = sess.status()
+    value_320 = dict(value=world * JOB_EVALS / (ms_320 * 1e-3), unit=UNIT, evals=JOB_EVALS, ms=ms_320, history_pairs_at_end=st320.hist_len,
+                     final_loss=st320.loss, gpu_launches=launches_320,
+                     what="BASELINE configs[1] as one job, device-timed (CUDA events): fresh L-BFGS state, 16 optimizer.step() graph launches")
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the public host-buffer call on the WHOLE job (uint8 image in pinned host memory -> H2D -> content / edge
+    #      targets -> num_steps=300 loop with a status read-back per optimizer.step() -> D2H uint8 result), wall clock
     pin_in = torch.from_numpy(content_u8).contiguous().pin_memory()
     pin_out = torch.empty_like(pin_in).pin_memory()
     with torch.cuda.stream(stream):
-        plan.run_frame_host(pin_in, pin_out, 0)              # warm: graph already captured; 20 evals
+        plan.run_frame_host(pin_in, pin_out, 0)              # warm: 20 evaluations through the same call
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.cuda.stream(stream):
-        n_e2e = plan.run_frame_host(pin_in, pin_out, evals_e2e - 20)
+        n_e2e = plan.run_frame_host(pin_in, pin_out, JOB_STEPS)
     torch.cuda.synchronize()
-    dt_e2e = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([dt_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_e2e = float(t[0])
+    dt_e2e = max_over_ranks(time.perf_counter() - t0)
     status_bytes = 2700 + 4 * 16  # control block + loss vector read back after every optimizer.step()
     e2e = dict(value=world * n_e2e / dt_e2e, unit=UNIT, h2d_bytes_per_step=3 * S * S / n_e2e,
-               d2h_bytes_per_step=(3 * S * S + status_bytes * (n_e2e // 20)) / n_e2e,
-               call="nst_run_frame_host: H2D uint8 image, content/edge targets, %d evaluations, D2H uint8 result; wall clock" % n_e2e)
+               d2h_bytes_per_step=(3 * S * S + status_bytes * (n_e2e // 20)) / n_e2e, evals=n_e2e, seconds=dt_e2e,
+               call="nst_run_frame_host(num_steps=%d): H2D uint8 image, content/edge targets, %d evaluations (the whole job of BASELINE "
+                    "configs[1]), one status read-back per optimizer.step(), D2H uint8 result; wall clock, max over ranks" % (JOB_STEPS, n_e2e))
+    # sanity (r01's line had value < e2e because the graph capture sat inside the timed region): the device-timed job
+    # cannot be slower than the same job through the host-buffer call, which adds copies and 16 host round trips
+    sanity = dict(e2e_le_value_320=bool(e2e["value"] <= 1.02 * value_320["value"]),
+                  graph_captured_before_timed_region=True, warmup_evals_run=warm_evals)
+    if not sanity["e2e_le_value_320"]:
+        sys.stderr.write("bench.py: WARNING e2e (%.1f) exceeds the device-timed job (%.1f) by more than 2%%\n" % (e2e["value"], value_320["value"]))
+
+    # ---- BASELINE configs[4] in front of the driver: 720p frames, frame-sharded, FIXED total frame count across N
+    video_row = None
+    if not args.no_video_row:
+        video_row = video_strong_scaling(args, rank, world, dev, dist, hf, synth)
 
     if rank != 0:
         if dist is not None:
@@ -443,12 +585,17 @@ def run_b200(args, rank, world, local_rank):
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 implicit GEMM: 12 forward + 12 data-gradient launches per evaluation, the Gram backward "
                            "of conv1_1..conv4_1 folded into the data gradients as a second accumulator, + 1 Gram-backward launch for conv5_1)",
-                    achieved=achieved_tf, peak=pk["tc_sustained"], unit="TFLOP/s", frac=achieved_tf / pk["tc_sustained"],
-                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the conv_tc_kernel launches of one evaluation (ncu --set full, profiles/r01d_ncu_full_conv_tc_summary.csv)",
-                    peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                    achieved=achieved_tf, peak=pk["tc_burst"], unit="TFLOP/s", frac=achieved_tf / pk["tc_burst"],
+                    peak_sustained=pk["tc_sustained"], frac_sustained=achieved_tf / pk["tc_sustained"],
+                    traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the conv_tc_kernel launches of one evaluation (ncu --set full, profiles/" + NCU_SUMMARY + ")",
+                    peak_source=pk["source"] + ": `peak` / `frac` use the BURST bf16 figure (the step runs at full SM clock, it is not in the power-limited "
+                                "regime the sustained figure was measured in); `peak_sustained` / `frac_sustained` are printed beside it",
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
                     avg_launch_ms=conv_ms / conv_launches,
                     ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms,
+                    fwd_tflops=sum(synth.conv_flops(i, S, S) for i in range(1, 13)) / (per_eval(("conv_fwd",)) * 1e-3) / 1e12,
+                    dgrad_tflops=(sum(synth.conv_flops(i, S, S) for i in range(1, 13)) + sum(synth.gram_flops(i, S, S) for i in synth._STYLE)) /
+                                 (per_eval(("conv_dgrad", "gram_bwd")) * 1e-3) / 1e12,
                     how="CUDA events on the launching stream around every run of same-kind launches (forward convolutions, "
                         "data gradients, Gram backward) of 2 x 20 evaluations executed back to back on one stream "
                         "(nst_lbfgs_step_timed_grouped), best of 3 repetitions; average launch duration = run time / launches in the run")
@@ -460,13 +607,48 @@ def run_b200(args, rank, world, local_rank):
                         frac=(lb_gbs / pk["hbm"]) if lb_gbs else None, history_pairs=m_avg,
                         bytes_per_iteration=synth.lbfgs_bytes(S, S, m_avg), ms=lb_ms)
     lb_rows = []
+    # every other kernel of the step against ITS bound: algorithmic bytes / time in the same grouped
+    # timing / measured copy bandwidth.  At 512^2 most of them move a few MB in ~10 us: latency-sized launches that run on
+    # the side stream, off the critical path (conv forward -> deepest Gram -> data gradients -> optimizer).
+    hw = S * S
+    tap_bytes = 2.0 * sum(synth._COUT[i] * (S >> synth._LEVEL[i]) * (S >> synth._LEVEL[i]) for i in synth._STYLE)
+    small = {
+        "pixel": (2.0 / 3.0 + 2.0) * 3 * hw * 4,                    # x read, edge target read (2 planes), gradient written
+        "content": 512 * (S // 8) * (S // 8) * (2 + 4 + 2),          # tap fp16 + target fp32 read, seed bf16 written
+        "gram": tap_bytes,                                            # every style tap read once (partial + 2 finalize launches per set)
+        "conv1_fwd": 3 * hw * 4 + 2 * 64 * hw * 2,                    # image read, tap + activation written
+        "conv1_dgrad": 64 * hw * 2 + 2 * 3 * hw * 4,                  # gradient of conv1_1 read, pixel-term gradient read, g written
+        "assemble": 0.0,
+    }
+    on_critical_path = {"pixel": False, "content": False, "gram": "conv5_1's Gram only (the shallow layers' launch is on the side stream)",
+                        "conv1_fwd": True, "conv1_dgrad": True, "assemble": False}
+    roofline_small = {}
+    for k, nbytes in small.items():
+        if k not in by_kind or by_kind[k] <= 0:
+            continue
+        gbs = nbytes / (by_kind[k] * 1e-3) / 1e9
+        roofline_small[k] = dict(bound="hbm", ms=by_kind[k], bytes=nbytes, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                                 on_critical_path=on_critical_path[k])
+    roofline_small["gram"]["tensor_tflops"] = sum(synth.gram_flops(i, S, S) for i in synth._STYLE) / (by_kind["gram"] * 1e-3) / 1e12
+    it_ms = sum(by_kind[k] for k in lb_kinds)
+    roofline_small["lbfgs_iteration"] = dict(bound="hbm", ms=it_ms, bytes=synth.lbfgs_bytes(S, S, m_avg), unit="GB/s", peak=pk["hbm"],
+                                             achieved=synth.lbfgs_bytes(S, S, m_avg) / (it_ms * 1e-3) / 1e9,
+                                             frac=synth.lbfgs_bytes(S, S, m_avg) / (it_ms * 1e-3) / 1e9 / pk["hbm"],
+                                             serial_ms=by_kind["lbfgs_reduce"] + by_kind["lbfgs_control"], on_critical_path=True,
+                                             what="pass 1 + reduction + controller + pass 2 at %d stored pairs; serial_ms = reduction + one-block controller" % m_avg)
 
-    # ---- next row of the scope table: mask compositing right behind the loop, measured the same way
-    mask_row = video_row = mip_row = None
+    # ---- next rows of the scope table: kernels right behind the loop, measured the same way
+    mask_row = assemble_row = mip_row = None
     if world == 1:
         mask_row = bench_mask_composite(dev, pk)
-        video_row = bench_video_assemble(dev, pk)
+        assemble_row = bench_video_assemble(dev, pk)
         mip_row = bench_mip(dev, pk)
+
+    # ---- the reference's own eager path on THIS GPU (cuDNN TF32 convolutions, fp32 bmm, torch.optim-style L-BFGS with a host
+    #      sync per iteration): the only pre-existing Blackwell path for the workload
+    eager = None
+    if world == 1 and not args.no_torch_eager:
+        eager = time_torch_eager_gpu(S, dev)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu = None
@@ -476,12 +658,16 @@ def run_b200(args, rank, world, local_rank):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f16", data="synthetic",
-                config=dict(workload=workload_name(S),
-                            precision="fp16 operands / fp32 accumulate (VGG forward, Gram), bf16 operands (data gradients), fp32 pixel terms and optimizer",
+                config=dict(workload=workload_name(S)),    # identical in both arms (the driver compares the dicts)
+                detail=dict(precision="fp16 operands / fp32 accumulate (VGG forward, Gram), bf16 operands (data gradients), fp32 pixel terms and optimizer",
                             l2="working set per evaluation (activations ~0.3 GB + L-BFGS history up to 0.63 GB) exceeds the 126 MB L2; no flush needed",
-                            history_pairs_at_end=hist_len, final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S)),
-                clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
-                ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, mask_composite=mask_row, video_assemble=video_row, mip_planes=mip_row)
+                            history_pairs_at_start=hist_start, history_pairs_at_end=hist_len, warmup_evals_run=warm_evals,
+                            final_loss=final_loss, flops_per_eval=synth.eval_flops(S, S),
+                            note="`value` times exactly --steps evaluations after the warm-up (history length above); `value_320` and `e2e` time the "
+                                 "whole 320-evaluation job of BASELINE configs[1]"),
+                clocks=clocks, e2e=e2e, value_320=value_320, sanity=sanity, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
+                roofline_small=roofline_small, ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, torch_eager_gpu=eager, video=video_row,
+                mask_composite=mask_row, video_assemble=assemble_row, mip_planes=mip_row)
     emit(line)
     if args.kernel_table:
         # per-launch table: the same step with an event after EVERY launch (isolates each launch: no overlap between launches)
@@ -554,7 +740,8 @@ def run_video(args, rank, world, local_rank):
     evals = 20 * (args.video_steps // 20 + 1)
     if rank == 0:
         line = dict(metric="video style transfer frames/s (%dx%d, frame-sharded)" % (W, H), value=n_frames / dt, unit="frames/s", n_gpus=world,
-                    steps=n_frames, warmup=1, ms_per_step=1e3 * dt / n_frames, higher_is_better=True, scaling="strong",
+                    steps=n_frames, warmup=1, ms_per_step=1e3 * dt / n_frames, higher_is_better=True,
+                    scaling="strong (--frames is the TOTAL over all ranks: keep it fixed when comparing N)",
                     vs_baseline=None, dtype="f16", data="synthetic",
                     config=dict(workload="%d synthetic %dx%d frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), "
                                          "%d frame(s) in flight per GPU, contiguous frame blocks per rank, NCCL broadcast of the style Gram "
@@ -594,6 +781,10 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager-on-GPU timing of the reference algorithm")
+    ap.add_argument("--no-video-row", action="store_true", help="skip the 720p frame-sharded `video` row of the default workload")
+    ap.add_argument("--video-row-frames", type=int, default=64, help="`video` row: total 720p frames, the same at every N (strong scaling)")
+    ap.add_argument("--video-row-steps", type=int, default=60, help="`video` row: num_steps per frame (60 -> 80 evaluations)")
     ap.add_argument("--kernel-table", default=None, help="write the per-launch timing table (CSV) here")
     ap.add_argument("--workload", default="pair512", choices=["pair512", "video"])
     ap.add_argument("--frames", type=int, default=16, help="--workload video: number of 720p frames (all ranks together)")

@@ -142,6 +142,11 @@ int nst_style_mix_tensors(const float* a, int Ha, int Wa, const float* b, int Hb
 int nst_lbfgs_init(nst_plan* plan, const float* x0 /* [3,H,W] device */, int trace_capacity, void* stream);
 /* one optimizer.step(closure): up to 20 evaluations enqueued without host synchronisation */
 int nst_lbfgs_step(nst_plan* plan, void* stream);
+/* Captures and instantiates the CUDA graph nst_lbfgs_step launches (about 800 kernel nodes, milliseconds of host time)
+ * without running it; nst_lbfgs_step does this lazily on its first call otherwise.  Call it after the last change of
+ * weights / normalisation / trace capacity (each drops the graph) when the first step must not pay for the capture,
+ * e.g. before a timed region.  No-op when steps are enqueued directly (NST_NO_GRAPH, or the NULL stream). */
+int nst_lbfgs_prepare_graph(nst_plan* plan, void* stream);
 /* synchronises the stream and copies the control block */
 int nst_lbfgs_status(nst_plan* plan, nst_status* out, void* stream);
 /* current iterate, clamped to [0,1] (run_style_transfer.py:153-155) -> [3,H,W] fp32 device */
@@ -189,6 +194,10 @@ int nst_lbfgs_step_timed(nst_plan* plan, nst_launch_time* out, int max_out, void
  * the last one so that the runs are uninterrupted. */
 int nst_lbfgs_step_timed_grouped(nst_plan* plan, nst_launch_time* out, int max_out, void* stream);
 
+/* ---- tuning aids: exported ONLY by the instrumented build (tools/build.py --instrument -> libnst_b200_instr.so, compiled
+ * with -DNST_INSTRUMENT and loaded by tools/ alone).  The product library contains neither these entry points nor the
+ * stamps / wait counters / wrong-result timing experiments behind them. */
+#ifdef NST_INSTRUMENT
 /* phase timestamps (SM clock) of CTA 0 of one convolution launch (mode 0 forward, 1 data gradient; conv 0 = conv1_1's
    data gradient) -> out[0..6], the SM cycles its roles spent waiting -> out[8..13] (slots: csrc/conv_tc.cu) and the
    lifetime in SM cycles of every CTA -> out[16 + cta]; out holds 176 values: tuning aid, see tools/conv_phases.py */
@@ -200,10 +209,7 @@ int nst_plan_timeline(nst_plan* plan, int enable, unsigned long long* out96, voi
 /* SM clock at the phase boundaries of the most recent L-BFGS controller launch (slots: csrc/lbfgs_ctl.h), 8 values:
    tuning aid, tools/ctl_phases.py */
 int nst_lbfgs_ctl_clocks(nst_plan* plan, long long* out8, void* stream);
-/* runs the forward (which = 0) or backward (1) chained convolution launch once on the plan's current buffers with wait
-   accounting: out[16 * cta + slot] SM cycles (slots: csrc/conv_chain.cu), then 4 counters per chain layer from
-   out[16 * n_ctas]; out holds 16 * max_ctas + 256 values; returns the number of CTAs: tools/chain_waits.py */
-int nst_plan_chain_waits(nst_plan* plan, int which, long long* out, int max_ctas, void* stream);
+#endif /* NST_INSTRUMENT */
 
 /* ---- host-buffer convenience (the e2e path: copies inside) ---------------------------------------
  * content_u8: [H,W,3] uint8 host; out_u8: [H,W,3] uint8 host (truncating, like ToPILImage).

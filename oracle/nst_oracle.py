@@ -92,8 +92,8 @@ def vgg19_random_weights(seed: int = 1234, n_conv: int = 13, dtype=torch.float32
 # ------------------------------------------------------------------------------------------------
 def normalize(img: torch.Tensor, mean, std) -> torch.Tensor:
     """style_transfer_losses.py:9-28 - per-channel z-score on a (b, c, h, w) tensor."""
-    m = torch.as_tensor(mean, dtype=img.dtype).reshape(1, -1, 1, 1)
-    s = torch.as_tensor(std, dtype=img.dtype).reshape(1, -1, 1, 1)
+    m = torch.as_tensor(mean, dtype=img.dtype, device=img.device).reshape(1, -1, 1, 1)
+    s = torch.as_tensor(std, dtype=img.dtype, device=img.device).reshape(1, -1, 1, 1)
     return (img - m) / s
 
 
@@ -359,6 +359,7 @@ class ClosureOracle:
                  content_layers=CONTENT_LAYERS, style_layers=STYLE_LAYERS, ca_seed: Optional[int] = 101,
                  emulate_reference_cost: bool = False):
         self.dtype = content.dtype
+        self.device = content.device
         self.mean, self.std = mean, std
         self.w = dict(style=w_style, content=w_content, tv=w_tv, edge=w_edge)
         self.content_layers, self.style_layers = list(content_layers), list(style_layers)
@@ -384,7 +385,7 @@ class ClosureOracle:
                 for name in self.content_layers:
                     w1, w2 = channel_attention_weights(cfeats[name].shape[1], seed=ca_seed if first else None)
                     first = False
-                    cfeats[name] = channel_attention(cfeats[name], w1.to(self.dtype), w2.to(self.dtype))
+                    cfeats[name] = channel_attention(cfeats[name], w1.to(self.device, self.dtype), w2.to(self.device, self.dtype))
             self.content_t = cfeats
 
     def evaluate(self, x: torch.Tensor, need_grad=True):
@@ -392,7 +393,7 @@ class ClosureOracle:
         xv = x.detach().clone().requires_grad_(need_grad)
         normed = normalize(xv, self.mean, self.std)
         feats = self.vgg(normed)
-        zero = torch.zeros((), dtype=self.dtype)
+        zero = torch.zeros((), dtype=self.dtype, device=self.device)
         c = self.w["content"] * content_loss(feats, self.content_t, self.content_layers) if self.w["content"] > 0 else zero
         per = []
         if self.w["style"] > 0:
@@ -408,7 +409,7 @@ class ClosureOracle:
             e = self.w["edge"] * edge_loss(self.edge_target, get_gradient_imgs(to_grayscale(xv)))
         else:
             e = zero
-        total = torch.zeros(1, dtype=self.dtype) + s + c + tv + e     # run_style_transfer.py:139
+        total = torch.zeros(1, dtype=self.dtype, device=self.device) + s + c + tv + e     # run_style_transfer.py:139
         grad = None
         if need_grad:
             total.backward()
@@ -422,16 +423,18 @@ class ClosureOracle:
 def run_oracle(weights, biases, content_u8: np.ndarray, style_u8: List[np.ndarray], num_steps: int, *,
                random_init=False, w_style, w_content, w_tv, w_edge, style_img_weight=0.5, channel_attention_on=False,
                mean=VGG_MEAN, std=VGG_STD, dtype=torch.float32, keep_iterates=False, max_evals=None,
-               emulate_reference_cost=False, on_eval=None) -> OracleResult:
-    """run_multi_style_transfer (run_style_transfer.py:27-159) on uint8 HWC arrays."""
+               emulate_reference_cost=False, on_eval=None, device="cpu") -> OracleResult:
+    """run_multi_style_transfer (run_style_transfer.py:27-159) on uint8 HWC arrays.  `device`: where the reference's
+    torch ops run - "cpu" for every parity use; bench.py's torch_eager_gpu leg passes "cuda" to time the reference's
+    own eager path (cuDNN / cuBLAS kernels picked by torch) on the B200 beside the CUDA path of this repo."""
     torch.manual_seed(101)                                                  # :52 seed_everything
     np.random.seed(101)
-    weights = [w.to(dtype) for w in weights]
-    biases = [b.to(dtype) for b in biases]
-    content = to_tensor_u8(content_u8, dtype)
-    styles = [to_tensor_u8(s, dtype) for s in style_u8]
+    weights = [w.to(device, dtype) for w in weights]
+    biases = [b.to(device, dtype) for b in biases]
+    content = to_tensor_u8(content_u8, dtype).to(device)                    # :59 .to(device)
+    styles = [to_tensor_u8(s, dtype).to(device) for s in style_u8]
     if random_init:
-        x0 = torch.randn(content.shape).to(dtype)                           # :84
+        x0 = torch.randn(content.shape).to(device, dtype)                   # :84
     else:
         x0 = content.clone()                                                # :87
     co = ClosureOracle(weights, biases, content, styles, w_style=w_style, w_content=w_content, w_tv=w_tv, w_edge=w_edge,

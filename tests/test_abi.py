@@ -12,10 +12,17 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
+def _header(instrumented=False):
     text = open(os.path.join(ROOT, "include", "nst_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(nst_[a-z0-9_]+)\s*\(", text)))
+    blocks = re.findall(r"#ifdef NST_INSTRUMENT(.*?)#endif", text, flags=re.S)
+    if instrumented:
+        return "\n".join(blocks)
+    return re.sub(r"#ifdef NST_INSTRUMENT.*?#endif", "", text, flags=re.S)
+
+
+def header_symbols(instrumented=False):
+    return sorted(set(re.findall(r"\b(nst_[a-z0-9_]+)\s*\(", _header(instrumented))))
 
 
 def test_library_exports_every_declared_symbol(built_libs):
@@ -26,6 +33,20 @@ def test_library_exports_every_declared_symbol(built_libs):
         assert hasattr(lib, n), n
     lib.nst_abi_version.restype = ctypes.c_int
     assert lib.nst_abi_version() == 1
+
+
+def test_product_library_has_no_instrumentation(built_libs):
+    """Tuning aids (phase stamps, launch spans, wrong-result timing experiments) live in the -DNST_INSTRUMENT build only."""
+    lib = ctypes.CDLL(built_libs[0])
+    names = header_symbols(instrumented=True)
+    assert names == ["nst_lbfgs_ctl_clocks", "nst_plan_conv_phases", "nst_plan_timeline"]
+    for n in names:
+        assert not hasattr(lib, n), n
+    pkg = importlib.import_module("text-based-image-style-transfer_b200")
+    assert set(pkg._lib.INSTR_PROTOTYPES) == set(names)
+    blob = open(built_libs[0], "rb").read()
+    for env in (b"NST_DBG_FLAGS", b"NST_DBG_CONV1", b"NST_CHAIN"):
+        assert env not in blob, env
 
 
 def test_binding_covers_the_header(built_libs):

@@ -432,10 +432,9 @@ def test_config5_video_frames_match_single_image_runs(nst, rst, oracle):
 
 # ------------------------------------------------------------------------------------------------ optional code paths
 @pytest.mark.parametrize("env", [
-    {"NST_CHAIN": "1"},                                    # chained launches with tile-level dataflow (conv_chain.cu)
     {"NST_DIRECT_STORES": "1", "NST_NO_SEED_FOLD": "1"},   # per-thread stores, Gram backward as separate 1x1 launches
     {"NST_NO_PDL": "1", "NST_NO_SIDE_STREAM": "1"},        # no programmatic dependent launch, single stream
-], ids=["chain", "direct-stores-unfolded", "no-pdl-single-stream"])
+], ids=["direct-stores-unfolded", "no-pdl-single-stream"])
 def test_optional_paths_stay_parity_green(env):
     """The schedule / epilogue variants that are switched by environment variables (read when the library or a plan is
     created, hence a fresh process) must give the same answers: __graft_entry__.smoke() checks step-0 losses and
@@ -649,3 +648,169 @@ def test_concurrent_frames_are_bit_identical_to_one_at_a_time(nst, oracle):
         finally:
             one.close()
             many.close()
+
+
+# ------------------------------------------------------------------------------------------------ run-level parity at full size
+LARGE_CASES = ["nat512", "syn512", "boat512", "nat512_mix_ca", "nat1024", "nat720p"]
+
+
+@pytest.mark.parametrize("name", LARGE_CASES)
+def test_full_run_against_reference_golden_large(nst, rst, oracle, name):
+    """Run-level parity on the configurations the performance is quoted on (BASELINE configs[1]..[4]), against goldens written
+    by the UNMODIFIED reference (tests/golden/make_golden_large.py -> /root/reference/multi_style_transfer/
+    run_style_transfer.py:27-159 on CPU): the loss of EVERY closure evaluation within 1e-2 relative, the final float image at
+    >= 40 dB - north_star's run-level tolerances - and the evaluation count.  Each golden carries the reference's own
+    self-noise (the same run with another CPU thread count); our deviation is printed beside it."""
+    path = os.path.join(GOLDEN_DIR, "large_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden %s not generated" % path)
+    O = oracle
+    g = np.load(path)
+    content = g["content_u8"]
+    styles = [g["style%d_u8" % i] for i in range(2) if "style%d_u8" % i in g.files]
+    steps, wgt, ca = int(g["num_steps"]), float(g["style_img_weight"]), bool(g["channel_attention"])
+    ref = g["loss_trace"]
+    s, c = session(rst, O, content, styles, mix_w=wgt)
+    s.prepare(c, channel_attention=ca, trace_capacity=len(ref) + 32)
+    n = s.run(steps)
+    assert n == int(g["n_evals"]) == len(ref)
+    tr = s.trace()[:, 0].double().numpy()
+    dev = np.abs(tr - ref) / np.abs(ref)
+    x = s.result().cpu()
+    p = O.psnr(x, torch.from_numpy(g["x_final"].astype(np.float32)))
+    mid = {}
+    print("\n[large golden %s] %d evals, loss %.5f -> %.5f (reference %.5f -> %.5f); max loss-curve deviation %.2e at eval %d "
+          "(reference self-noise %.2e); final image %.1f dB (reference self-noise %.1f dB)"
+          % (name, n, tr[0], tr[-1], ref[0], ref[-1], dev.max(), int(dev.argmax()), float(g["self_loss_dev"]), p, float(g["self_psnr"])))
+    assert dev.max() <= CURVE_TOL, (name, float(dev.max()), int(dev.argmax()))
+    assert p >= PSNR_MIN, (name, p)
+    st = s.status()
+    assert st.closure_calls == n and st.stop == 0
+    # drop-in form on the same inputs: PIL in, PIL out; bytes within the truncation noise of the float comparison above
+    u8 = O.to_u8(x)
+    d8 = np.abs(u8.astype(int) - g["final_u8"].astype(int))
+    assert d8.mean() < 1.0, (name, float(d8.mean()))
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ VGG-dominant regime (ADVICE r01)
+@pytest.mark.parametrize("weights", [dict(w_style=5e5, w_content=1.0, w_tv=0.0, w_edge=0.0),
+                                     dict(w_style=5e7, w_content=1e2, w_tv=2e1, w_edge=2e1)],
+                         ids=["pixel-terms-off", "vgg-terms-x100"])
+def test_vgg_dominated_gradient_and_short_trajectory(nst, rst, oracle, vgg_weights, weights):
+    """With random-init VGG weights and app.py's loss weights the fp32 TV / edge terms carry ~99 % of the gradient, which hides
+    the bf16 data-gradient error.  Here the VGG terms dominate (pixel terms off, or style / content weights x100 - the regime
+    ImageNet weights put the reference in): teacher-forced gradients at several iterates of the oracle's own trajectory and a
+    free-running 20-evaluation comparison.  The free run is only meaningful while the reference itself is stable: SURVEY A.3
+    measured 21 dB between two CPU thread counts at evaluation 20 with w_tv = w_edge = 0, so the curve is held to 1e-2 on the
+    evaluations before the reference's self-noise exceeds that and the gradient bound carries the weight of the test."""
+    O = oracle
+    ws, bs = vgg_weights
+    content, style = O.synth_image(96, 96, 0), O.synth_image(96, 96, 1)
+    ref = O.run_oracle(ws, bs, content, [style], 0, keep_iterates=True, **weights)
+    s, c = session(rst, O, content, [style], weights)
+    s.prepare(c, trace_capacity=64)
+    worst = 0.0
+    for k in (0, 3, 7, 12, 19):
+        xk = ref.iterates[k].cuda()
+        with torch.cuda.stream(s.stream):
+            losses, grad = s.plan.eval(xk)
+        assert float(losses[0]) == pytest.approx(ref.losses[k][0], rel=LOSS_TOL), k
+        worst = max(worst, rel(grad, ref.grads[k]))
+    print("\n[vgg-dominated %s] worst teacher-forced gradient error %.2e over 5 iterates" % (weights, worst))
+    assert worst < 2e-2, worst
+    assert s.run(0) == ref.evals == 20
+    tr = s.trace()[:, 0].double().numpy()
+    rl = np.array([l[0] for l in ref.losses])
+    assert np.all(np.abs(tr[:8] - rl[:8]) <= CURVE_TOL * np.abs(rl[:8])), np.abs(tr - rl) / rl
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ tutorial-style compat surface
+def test_compat_run_style_transfer_and_loss_modules(nst, rst, oracle, vgg_weights):
+    """north_star's run_style_transfer(cnn, norm_mean, norm_std, content_img, style_img, input_img, num_steps, style_weight,
+    content_weight) + ContentLoss / StyleLoss modules: the same device loop with the pixel terms off, started from input_img."""
+    O = oracle
+    ws, bs = vgg_weights
+    content, style = O.synth_image(64, 64, 0), O.synth_image(64, 64, 1)
+    c, st = O.to_tensor_u8(content).cuda(), O.to_tensor_u8(style).cuda()
+    x0 = noisy(c, seed=5)
+    wts = dict(w_style=1e6, w_content=1.0, w_tv=0.0, w_edge=0.0)
+    # oracle: the reference closure with those weights, started from x0
+    co = O.ClosureOracle(ws, bs, c.cpu(), [st.cpu()], **wts)
+    ref0 = co.evaluate(x0)
+    inp = x0.clone().cuda()
+    out = rst.run_style_transfer(None, O.VGG_MEAN, O.VGG_STD, c, st, inp, num_steps=0, style_weight=1e6, content_weight=1)
+    assert out.shape == c.shape and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    assert torch.equal(out, inp)                                            # the tutorial's parameter is updated in place
+    # a cnn given as a module: torchvision-style features built from the same weights
+    import torchvision
+    feats = torchvision.models.vgg19(weights=None).features
+    convs = [m for m in feats if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        for m, w, b in zip(convs, ws, bs):
+            m.weight.copy_(w)
+            m.bias.copy_(b)
+    out2 = rst.run_style_transfer(feats, O.VGG_MEAN, O.VGG_STD, c, st, x0.clone().cuda(), num_steps=0, style_weight=1e6, content_weight=1)
+    assert torch.equal(out, out2)
+    # the loss after 20 evaluations went down from the oracle's step-0 value
+    s, _ = session(rst, O, content, [style], wts)
+    s.prepare(c, x0.cuda())
+    with torch.cuda.stream(s.stream):
+        l0, _ = s.plan.eval(x0.cuda())
+        l1, _ = s.plan.eval(out)
+    assert float(l0[0]) == pytest.approx(ref0["total"], rel=LOSS_TOL)
+    assert float(l1[0]) < float(l0[0])
+    s.close()
+    # modules: transparent layers that record the per-layer terms
+    L = importlib.import_module("text-based-image-style-transfer_b200.multi_style_transfer.style_transfer_losses")
+    f_in = torch.randn(1, 64, 24, 20, generator=torch.Generator().manual_seed(1)).cuda()
+    f_t = torch.randn(1, 64, 24, 20, generator=torch.Generator().manual_seed(2)).cuda()
+    cl, sl = rst.ContentLoss(f_t), rst.StyleLoss(f_t)
+    assert cl(f_in) is f_in and sl(f_in) is f_in
+    assert float(cl.loss) == pytest.approx(float(torch.nn.functional.mse_loss(f_in, f_t)), rel=1e-5)
+    want = torch.nn.functional.mse_loss(O.gram_matrix(f_in.cpu()), O.gram_matrix(f_t.cpu()))
+    assert float(sl.loss) == pytest.approx(float(want), rel=5e-3)
+
+
+# ------------------------------------------------------------------------------------------------ apply_video_process mirror
+def test_apply_video_process_mirror(nst, rst, oracle, tmp_path):
+    """app.py:742-864 through the mirror: a tiny synthetic clip -> JPEG round trip -> FrameStyler -> device assembly; the final
+    BGR frame list equals (a) run_multi_style_transfer on every JPEG-round-tripped frame and (b) the cv2 assembly oracle."""
+    cv2 = pytest.importorskip("cv2")
+    from PIL import Image
+    from oracle import video_oracle as V
+    A = importlib.import_module("text-based-image-style-transfer_b200.app_video")
+    O = oracle
+    H, W, F = 48, 64, 3
+    path = str(tmp_path / "in.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 10.0, (W, H))
+    assert wr.isOpened()
+    for k in range(F):
+        wr.write(np.ascontiguousarray(O.synth_image(H, W, 200 + k)[:, :, ::-1]))
+    wr.release()
+    style = Image.fromarray(O.synth_image(40, 56, 1))
+    got = []
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out_path = A.apply_video_process(path, ["Style Transfer"], 0.5, 2, style, device="cuda", num_steps=20,
+                                         output_video_filepath=str(tmp_path / "out.mp4"), frame_sink=got.append)
+    assert out_path and os.path.exists(out_path) and os.path.getsize(out_path) > 0
+    assert "Finished processing frame: 3 out of" in buf.getvalue() and "Current output video temporarily saved at" in buf.getvalue()
+    final = got[0]
+    assert final.shape == ((F - 1) * 3 + 1, H, W, 3)
+    frames, fps, _ = A.read_frames(path, jpeg=True)
+    singles = []
+    for f in frames:
+        with contextlib.redirect_stdout(io.StringIO()):
+            singles.append(np.asarray(nst.run_multi_style_transfer(torch.tensor(O.VGG_MEAN), torch.tensor(O.VGG_STD), Image.fromarray(f), 20,
+                                                                   False, style_img1=style, device="cuda", **O.APP_WEIGHTS)))
+    want = np.stack(V.assemble_frames(singles, 2), 0)
+    assert np.array_equal(final, want)
+    cap = cv2.VideoCapture(out_path)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == final.shape[0]
+    assert cap.get(cv2.CAP_PROP_FPS) == pytest.approx(A.output_fps(fps, 2, 0.5), abs=0.5)
+    cap.release()
+    # effects outside the hot path raise instead of being skipped
+    with pytest.raises(nst.NstError):
+        A.apply_video_process(path, ["Pixel Art", "Style Transfer"], input_style=style, device="cuda")

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "nst_style_mix_tensors": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "nst_lbfgs_init": (C.c_int, [_P, _P, C.c_int, _P]),
     "nst_lbfgs_step": (C.c_int, [_P, _P]),
+    "nst_lbfgs_prepare_graph": (C.c_int, [_P, _P]),
     "nst_lbfgs_status": (C.c_int, [_P, C.POINTER(NstStatus), _P]),
     "nst_lbfgs_get_x": (C.c_int, [_P, _P, _P]),
     "nst_lbfgs_trace": (C.c_int, [_P, _P, C.c_int, _P]),
@@ -75,10 +76,6 @@ PROTOTYPES = {
     "nst_plan_eval_timed": (C.c_int, [_P, _P, _P, C.POINTER(NstLaunchTime), C.c_int, _P]),
     "nst_lbfgs_step_timed": (C.c_int, [_P, C.POINTER(NstLaunchTime), C.c_int, _P]),
     "nst_lbfgs_step_timed_grouped": (C.c_int, [_P, C.POINTER(NstLaunchTime), C.c_int, _P]),
-    "nst_plan_conv_phases": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_longlong), _P]),
-    "nst_plan_timeline": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong), _P]),
-    "nst_lbfgs_ctl_clocks": (C.c_int, [_P, C.POINTER(C.c_longlong), _P]),
-    "nst_plan_chain_waits": (C.c_int, [_P, C.c_int, C.POINTER(C.c_longlong), C.c_int, _P]),
     "nst_run_frames_host": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.POINTER(_P),
                                       C.POINTER(C.c_int)]),
     "nst_mask_composite": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
@@ -91,7 +88,32 @@ PROTOTYPES = {
     "nst_run_frame_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
 }
 
+# tuning aids exported by the instrumented build only (tools/build.py --instrument; -DNST_INSTRUMENT)
+INSTR_LIB_PATH = os.path.join(_HERE, "libnst_b200_instr.so")
+INSTR_PROTOTYPES = {
+    "nst_plan_conv_phases": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_longlong), _P]),
+    "nst_plan_timeline": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong), _P]),
+    "nst_lbfgs_ctl_clocks": (C.c_int, [_P, C.POINTER(C.c_longlong), _P]),
+}
+
 _lib = None
+
+
+def load_instrumented():
+    """tools/ only: binds the instrumented build (stamps, wait counters, timing experiments) in place of the product
+    library for this process.  Must be called before anything else loads the library."""
+    global _lib
+    if _lib is not None:
+        raise NstError("load_instrumented() must run before the product library is loaded")
+    if not os.path.exists(INSTR_LIB_PATH):
+        raise NstError("%s is missing: build it with `python tools/build.py --instrument`" % INSTR_LIB_PATH)
+    lib = C.CDLL(INSTR_LIB_PATH)
+    for name, (res, args) in list(PROTOTYPES.items()) + list(INSTR_PROTOTYPES.items()):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
 
 
 def load():

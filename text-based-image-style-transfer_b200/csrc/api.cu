@@ -21,7 +21,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "conv_chain.cuh"
 #include "conv_tc.cuh"
 #include "gram.cuh"
 #include "lbfgs.cuh"
@@ -74,7 +73,6 @@ extern "C" int nst_device_check(void) {
                 prop.major, prop.minor);
   if (g_num_sms == 0) {
     e = conv_tc_init();
-    if (e == cudaSuccess) e = conv_chain_init();
     if (e == cudaSuccess) e = conv1_tc_init();
     if (e == cudaSuccess) e = gram_init();
     if (e == cudaSuccess) e = lbfgs_init();
@@ -211,18 +209,10 @@ struct nst_plan {
   float* pooled_dev = nullptr;
   // seed_folded[i]: the Gram backward of style layer conv i runs inside the data gradient of conv i+1 (no launch of its own)
   bool seed_folded[NST_MAX_CONV] = {};
-  // chained convolution launches (conv_chain.cu): [0] forward conv1_2.., [1] Gram backward + data gradients
-  bool chain = false;
-  ChainLayer* chain_dev[2] = {};
-  int chain_layers[2] = {}, chain_items[2] = {};
-  int* chain_done = nullptr;
-  size_t chain_done_bytes = 0;
-  // the Gram-backward (1x1) layers of the shallower style layers as ONE launch of the chained kernel (no dependencies
-  // between them): five ~12 us launches of 2 GFLOP each were launch- and latency-bound
-  ChainLayer* seeds_dev = nullptr;
-  int seeds_layers = 0, seeds_items = 0;
-  unsigned long long* timeline = nullptr;  // [48][2] launch spans of the conv kernels (debug, nst_plan_timeline)
+#ifdef NST_INSTRUMENT
+  unsigned long long* timeline = nullptr;  // [48][2] launch spans of the conv kernels (nst_plan_timeline)
   bool timeline_on = false;
+#endif
 };
 
 static int plan_alloc(nst_plan* p, void** ptr, size_t bytes, bool zero) {
@@ -289,7 +279,9 @@ static int build_conv_params(nst_plan* p) {
     f.out_tap = p->tap[0];
     f.out_act = p->n_layers > 1 ? p->act[0] : nullptr;
     conv_finalize_params(f, CONV_FWD);
-    f.dbg_flags = getenv("NST_DBG_CONV1") ? atoi(getenv("NST_DBG_CONV1")) : 0;  // timing experiments only
+#ifdef NST_INSTRUMENT
+    f.dbg_flags = getenv("NST_DBG_CONV1") ? atoi(getenv("NST_DBG_CONV1")) : 0;  // timing experiments only (instrumented build)
+#endif
     if (tma_out && getenv("NST_CONV1_CUDA_CORES") == nullptr) {
       if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, p->H, p->W, 64, 64, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out 0)");
       if (f.out_act && make_tmap_out(&f.tmO1, f.out_act, p->H, p->W, 64, 64, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (act out 0)");
@@ -309,7 +301,7 @@ static int build_conv_params(nst_plan* p) {
     f.N = kCout[i];
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
-    f.block_n = p->chain ? chain_block_n(kCout[i]) : conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
+    f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
@@ -333,7 +325,7 @@ static int build_conv_params(nst_plan* p) {
     d.N = kCin[i];
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
-    d.block_n = p->chain ? chain_block_n(kCin[i]) : conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
+    d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
@@ -343,7 +335,10 @@ static int build_conv_params(nst_plan* p) {
       d.Hup = p->lh[kLevel[i - 1]];
       d.Wup = p->lw[kLevel[i - 1]];
     } else {
-      d.mask_act = p->act[i - 1];
+      // ReLU mask: act = relu(tap) rounded the same way, so (tap > 0) == (act > 0).  A style layer's data gradient already
+      // pulls that tap through L2 for the folded Gram backward; masking from it saves the DRAM read of the activation
+      // (33.5 MB at conv1_1 / 512^2, the slowest launch of the step).
+      d.mask_act = p->tap[i - 1] != nullptr ? p->tap[i - 1] : p->act[i - 1];
       d.addend = p->gadd[i - 1];
     }
     conv_finalize_params(d, CONV_DGRAD);
@@ -389,7 +384,7 @@ static int build_conv_params(nst_plan* p) {
     c.N = C;
     c.taps = 1;
     if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
-    c.block_n = p->chain ? chain_block_n(C) : conv_block_n(C, c.H, c.W, C, g_num_sms);
+    c.block_n = conv_block_n(C, c.H, c.W, C, g_num_sms);
     if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
     c.alpha = p->alpha + l;
     c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
@@ -403,7 +398,7 @@ static int build_conv_params(nst_plan* p) {
   // (conv_tc.cuh: seed_k).  Not for the deepest conv (its seed IS the first gradient), not when the layer is also a
   // content layer (that seed is accumulated by the content kernel), not with N tiles above 128 (tensor memory).
   for (int i = 0; i < NST_MAX_CONV; ++i) p->seed_folded[i] = false;
-  if (!p->chain && getenv("NST_NO_SEED_FOLD") == nullptr) {
+  if (getenv("NST_NO_SEED_FOLD") == nullptr) {
     for (int l = 0; l < p->n_style; ++l) {
       const int j = p->style_conv[l];      // style layer conv j; its gradient gpre[j] is produced by dgrad[j + 1]
       const int i = j + 1;
@@ -449,110 +444,6 @@ static int build_gram_params(nst_plan* p) {
   }
   return NST_OK;
 }
-
-// Work list of the shallow Gram-backward launch: every style layer except one on the deepest conv (that one is on the
-// critical path and runs on the main stream).
-static int build_seed_chain(nst_plan* p) {
-  if (!p->with_grad) return NST_OK;
-  const int last = p->n_layers - 1;
-  std::vector<ChainLayer> list;
-  size_t n_done = 0;
-  std::vector<size_t> off;
-  for (int l = p->n_style - 1; l >= 0; --l) {
-    const int i = p->style_conv[l];
-    if (i == last) continue;
-    ChainLayer L;
-    memset(&L, 0, sizeof(L));
-    L.c = p->scale[i];
-    const int C = kCout[i];
-    L.c.block_n = chain_block_n(C);
-    if (make_tmap_wgt(&L.c.tmB, p->dh[l], 1, C, C, L.c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, chained)", i);
-    conv_finalize_params(L.c, CONV_SCALE);
-    L.mode = CONV_SCALE;
-    L.dep_layer[0] = L.dep_layer[1] = -1;
-    L.item_base = list.empty() ? 0 : list.back().item_base + list.back().c.num_tiles;
-    off.push_back(n_done);
-    n_done += static_cast<size_t>(L.c.tiles_h) * L.c.tiles_w;
-    list.push_back(L);
-  }
-  if (list.empty()) return NST_OK;
-  int* done = nullptr;
-  CKI(plan_alloc_t(p, &done, n_done, true));
-  for (size_t k = 0; k < list.size(); ++k) list[k].done = done + off[k];
-  CKI(plan_alloc_t(p, &p->seeds_dev, list.size()));
-  CK(cudaMemcpy(p->seeds_dev, list.data(), list.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
-  p->seeds_layers = static_cast<int>(list.size());
-  p->seeds_items = list.back().item_base + list.back().c.num_tiles;
-  return NST_OK;
-}
-
-// Work lists of the two chained launches (conv_chain.cu).  Forward: conv1_2 .. the deepest conv.  Backward: the Gram
-// backward (1x1) layers of every style layer first - they depend on nothing inside the launch - then the data gradients
-// from the deepest conv down to conv1_2 (conv1_1's data gradient, N = 3, stays a launch of its own).
-static int build_chains(nst_plan* p) {
-  if (!p->chain) return NST_OK;
-  const int last = p->n_layers - 1;
-  std::vector<ChainLayer> lists[2];
-  std::vector<size_t> done_off[2];
-  size_t n_done = 0;
-  auto push = [&](int which, const ConvParams& c, int mode) -> int {
-    ChainLayer L;
-    memset(&L, 0, sizeof(L));
-    L.c = c;
-    L.c.dbg = nullptr;
-    L.c.tl = nullptr;
-    L.mode = mode;
-    L.dep_layer[0] = L.dep_layer[1] = -1;
-    L.item_base = lists[which].empty() ? 0 : lists[which].back().item_base + lists[which].back().c.num_tiles;
-    done_off[which].push_back(n_done);
-    n_done += static_cast<size_t>(c.tiles_h) * c.tiles_w;
-    lists[which].push_back(L);
-    return static_cast<int>(lists[which].size()) - 1;
-  };
-  auto dep = [&](ChainLayer& L, int k, int layer, int rpt, int cpt, int halo) {
-    L.dep_layer[k] = layer;
-    L.dep_rpt[k] = rpt;
-    L.dep_cpt[k] = cpt;
-    L.dep_halo[k] = halo;
-  };
-  for (int i = 1; i <= last; ++i) {
-    const int e = push(0, p->fwd[i], CONV_FWD);
-    // conv i reads the (pooled) output of conv i-1; conv1_1 is an earlier launch
-    if (i >= 2) dep(lists[0][e], 0, e - 1, kPoolAfter[i - 1] ? 8 : 16, kPoolAfter[i - 1] ? 4 : 8, 1);
-  }
-  if (p->with_grad) {
-    int scale_entry[NST_MAX_CONV];
-    for (int i = 0; i < NST_MAX_CONV; ++i) scale_entry[i] = -1;
-    for (int l = p->n_style - 1; l >= 0; --l) scale_entry[p->style_conv[l]] = push(1, p->scale[p->style_conv[l]], CONV_SCALE);
-    int prev = -1;
-    for (int i = last; i >= 1; --i) {
-      const int e = push(1, p->dgrad[i], CONV_DGRAD);
-      ChainLayer& L = lists[1][e];
-      // A operand = gpre[i]: written by the data gradient of conv i+1 (through the pool routing if conv i is pooled),
-      // or, for the deepest conv, by its Gram-backward layer (a content-only seed comes from an earlier launch)
-      if (i == last) {
-        if (scale_entry[last] >= 0) dep(L, 0, scale_entry[last], 16, 8, 1);
-      } else {
-        dep(L, 0, prev, kPoolAfter[i] ? 32 : 16, kPoolAfter[i] ? 16 : 8, 1);
-      }
-      // the epilogue adds the tap seed of conv i-1 (gadd[i-1]) when that is a style layer
-      if (L.c.addend != nullptr && scale_entry[i - 1] >= 0) dep(L, 1, scale_entry[i - 1], 16, 8, 0);
-      prev = e;
-    }
-  }
-  CKI(plan_alloc_t(p, &p->chain_done, n_done > 0 ? n_done : 1, true));
-  p->chain_done_bytes = n_done * sizeof(int);
-  for (int w = 0; w < 2; ++w) {
-    if (lists[w].empty()) continue;
-    for (size_t k = 0; k < lists[w].size(); ++k) lists[w][k].done = p->chain_done + done_off[w][k];
-    CKI(plan_alloc_t(p, &p->chain_dev[w], lists[w].size()));
-    CK(cudaMemcpy(p->chain_dev[w], lists[w].data(), lists[w].size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
-    p->chain_layers[w] = static_cast<int>(lists[w].size());
-    p->chain_items[w] = lists[w].back().item_base + lists[w].back().c.num_tiles;
-  }
-  return NST_OK;
-}
-
 
 extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
                                uint32_t content_mask, int with_grad) {
@@ -705,22 +596,7 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.ctl, 1, true));
     b.eval_loss = p->losses;
   }
-  {
-    // Opt-in (NST_CHAIN=1): one persistent launch per chain with tile-level dataflow between layers (conv_chain.cu).
-    // Measured at 512^2 (profiles/r01_chain_waits_512.log) it does not beat the per-layer launches: CTAs advance in
-    // lockstep, so almost every tile consumes what the previous wave just produced and pays the producer -> consumer
-    // latency (epilogue + fence + poll + first TMA, ~4.5 us) that a kernel boundary pays once per layer, and the Gram
-    // kernels can no longer hide on the side stream.  Kept for batches of independent frames, where other frames' tiles
-    // fill those waits.  A conv that is both a style and a content layer needs the content seed accumulated after its
-    // Gram seed, which only the per-layer path orders.
-    const bool want_chain = getenv("NST_CHAIN") != nullptr && getenv("NST_CHAIN")[0] == '1';
-    bool both = false;
-    for (int l = 0; l < p->n_content; ++l) both = both || style_index(p, p->content_conv[l]) >= 0;
-    p->chain = want_chain && !both && n_layers >= 2;
-  }
   PA(build_conv_params(p));
-  PA(build_chains(p));
-  PA(build_seed_chain(p));
 #undef PA
   *out = p;
   return NST_OK;
@@ -765,12 +641,7 @@ static cudaError_t conv1_forward(nst_plan* p, const float* x, cudaStream_t s) {
 
 static int forward_enqueue(nst_plan* p, const float* x, cudaStream_t s) {
   const nst_net* net = p->net;
-  if (p->chain) CK(cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s));
   CK(conv1_forward(p, x, s));
-  if (p->chain) {
-    CK(launch_conv_chain(p->chain_dev[0], p->chain_layers[0], p->chain_items[0], g_num_sms, s));
-    return NST_OK;
-  }
   for (int i = 1; i < p->n_layers; ++i) CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
   return NST_OK;
 }
@@ -999,126 +870,6 @@ struct LaunchTimer {
     if (tm && tm->begin(k) != 0) return fail(NST_ERR_CUDA, "event record failed");    \
   } while (0)
 
-// The same evaluation with the two chained launches (conv_chain.cu): main stream = conv1_1, forward chain, Gram of the
-// deepest style layer, backward chain (Gram backward + data gradients), conv1_1's data gradient; side stream = pixel
-// terms, Gram / style MSE of the shallower style layers, content loss, loss assembly.
-static int eval_enqueue_chain(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
-                              cudaStream_t s, LaunchTimer* tm) {
-  int nl = 0;
-  TB(NST_K_START);
-  TM(NST_K_START, -1);
-  const bool conc = tm == nullptr && p->side != nullptr;
-  cudaStream_t s2 = conc ? p->side : s;
-  enum { EV_FORK = 0, EV_TAPS = 1, EV_SEEDS = 4, EV_GRAM = 5, EV_JOIN = 6 };
-  auto edge = [&](int ev, cudaStream_t from, cudaStream_t to) -> cudaError_t {
-    if (!conc) return cudaSuccess;
-    cudaError_t e = cudaEventRecord(p->ev[ev], from);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(to, p->ev[ev], 0);
-    return e;
-  };
-  const int last = p->n_layers - 1;
-  const bool deep_style = p->n_style > 0 && p->style_conv[p->n_style - 1] == last;
-  auto content_launch = [&](int l, cudaStream_t st) -> cudaError_t {
-    const int i = p->content_conv[l];
-    const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
-    __nv_bfloat16* seed = grad != nullptr ? (i == last ? p->gpre[i] : p->gadd[i]) : nullptr;
-    const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
-    return launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel, gcoef, 0, st);
-  };
-  // ---- side: pixel-space terms
-  CK(edge(EV_FORK, s, s2));
-  TB(NST_K_PIXEL);
-  CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
-  ++nl;
-  TM(NST_K_PIXEL, -1);
-  // ---- main: VGG forward
-  CK(cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s));
-  CK(conv1_forward(p, x, s));
-  ++nl;
-  TM(NST_K_CONV1_FWD, 0);
-  CK(launch_conv_chain(p->chain_dev[0], p->chain_layers[0], p->chain_items[0], g_num_sms, s));
-  ++nl;
-  TM(NST_K_CONV_FWD, 100);
-  // ---- side: Gram, style MSE and backward operand of the shallower style layers; content loss (+ its seed)
-  CK(edge(EV_TAPS, s, s2));
-  if (p->gram_shallow.num_layers > 0) {
-    CK(launch_gram(p->gram_shallow, s2));
-    nl += 3;
-    TM(NST_K_GRAM, 0);
-  }
-  for (int l = 0; l < p->n_content; ++l) {
-    if (p->content_conv[l] == last) continue;
-    CK(content_launch(l, s2));
-    ++nl;
-    TM(NST_K_CONTENT, p->content_conv[l]);
-  }
-  if (grad != nullptr && conc) CK(cudaEventRecord(p->ev[EV_SEEDS], s2));
-  // ---- main: the deepest layer's targets
-  if (deep_style) {
-    CK(launch_gram(p->gram_deep, s));
-    nl += 3;
-    TM(NST_K_GRAM, last);
-  }
-  for (int l = 0; l < p->n_content; ++l) {
-    if (p->content_conv[l] != last) continue;
-    CK(content_launch(l, s));
-    ++nl;
-    TM(NST_K_CONTENT, last);
-  }
-  // ---- side: loss assembly
-  CK(edge(EV_GRAM, s, s2));
-  LossAssembleArgs a;
-  memset(&a, 0, sizeof(a));
-  a.tv_part = p->tv_part;
-  a.n_tv = pixel_blocks(p->H, p->W);
-  a.edge_part = p->edge_part;
-  a.n_edge = pixel_blocks(p->H, p->W);
-  a.content_part = p->content_part;
-  a.n_content = p->content_part_off[p->n_content];
-  a.style_layer_loss = p->style_loss;
-  a.num_style = p->n_style;
-  a.w_style = p->w_style;
-  a.w_content = p->w_content;
-  a.w_tv = p->w_tv;
-  a.w_edge = p->w_edge;
-  a.tv_norm = 1.0 / (3.0 * p->H * p->W);
-  a.edge_norm = (p->H > 2 && p->W > 2) ? 1.0 / (static_cast<double>(p->H - 2) * (p->W - 2)) : 0.0;
-  if (p->n_content > 0) {
-    const int i = p->content_conv[0];
-    const double numel = static_cast<double>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
-    a.content_norm = 1.0 / (numel * p->n_content);
-  }
-  a.out = p->losses;
-  a.counter = counter;
-  a.stop_flag = stop_flag;
-  a.trace = p->trace;
-  a.trace_cap = p->trace_cap;
-  TB(NST_K_ASSEMBLE);
-  CK(launch_loss_assemble(a, s2));
-  ++nl;
-  TM(NST_K_ASSEMBLE, -1);
-  if (conc) CK(cudaEventRecord(p->ev[EV_JOIN], s2));
-  // ---- main: backward chain
-  if (grad != nullptr) {
-    if (conc) CK(cudaStreamWaitEvent(s, p->ev[EV_SEEDS], 0));
-    CK(launch_conv_chain(p->chain_dev[1], p->chain_layers[1], p->chain_items[1], g_num_sms, s));
-    ++nl;
-    TM(NST_K_CONV_DGRAD, 100);
-    if (conc) CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
-    ConvParams d = p->dgrad[0];
-    d.out_pix = grad;
-    for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
-    CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
-    ++nl;
-    TM(NST_K_CONV1_DGRAD, 0);
-  } else if (conc) {
-    CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
-  }
-  if (launches) *launches += nl;
-  return NST_OK;
-}
-
-
 // Enqueues one closure evaluation.  With a side stream (p->side, default) the evaluation is a small DAG: the
 // critical path conv forward -> Gram of the deepest style layer -> data gradients runs on `s`; everything that
 // only feeds it sideways (pixel-space losses, Gram + finalize + Gram-backward seeds of the shallower style layers,
@@ -1129,7 +880,6 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   int nl = 0;
   const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
   if (grad != nullptr && !p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
-  if (p->chain && use_vgg) return eval_enqueue_chain(p, x, grad, counter, stop_flag, launches, s, tm);
   TB(NST_K_START);
   TM(NST_K_START, -1);
   const bool conc = tm == nullptr && p->side != nullptr && use_vgg;
@@ -1253,31 +1003,21 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   }
   // ---- side: Gram-backward seeds of the shallower style layers
   if (grad != nullptr && use_vgg) {
-    // opt-in: measured inside the step, the single persistent launch holds all SMs for ~25 us and delays the critical
-    // path (deepest Gram -> first data gradient) more than five short launches do
-    static const bool one_launch = getenv("NST_SEEDS_ONE_LAUNCH") != nullptr;
-    bool accumulate_after = false;
-    for (int l = 0; l < n_shallow; ++l) accumulate_after = accumulate_after || content_index(p, p->style_conv[l]) >= 0;
-    if (one_launch && tm == nullptr && p->seeds_layers > 0 && !accumulate_after) {
-      CK(launch_conv_chain(p->seeds_dev, p->seeds_layers, p->seeds_items, g_num_sms, s2));
+    // shallowest (largest, bandwidth-bound) first: it then overlaps the latency-bound Gram chain of the deepest layer on
+    // the main stream instead of the first data gradients; all seeds are awaited together before conv4_2's data gradient
+    for (int l = 0; l < n_shallow; ++l) {
+      const int i = p->style_conv[l];
+      if (p->seed_folded[i]) continue;  // computed inside the data gradient of conv i+1
+      TB(NST_K_GRAM_BWD);
+      CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
       ++nl;
-    } else {
-      // shallowest (largest, bandwidth-bound) first: it then overlaps the latency-bound Gram chain of the deepest layer on
-      // the main stream instead of the first data gradients; all seeds are awaited together before conv4_2's data gradient
-      for (int l = 0; l < n_shallow; ++l) {
-        const int i = p->style_conv[l];
-        if (p->seed_folded[i]) continue;  // computed inside the data gradient of conv i+1
-        TB(NST_K_GRAM_BWD);
-        CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
+      TM(NST_K_GRAM_BWD, i);
+      const int cl = content_index(p, i);
+      if (cl >= 0) {
+        TB(NST_K_CONTENT);
+        CK(content_launch(cl, 1, s2));
         ++nl;
-        TM(NST_K_GRAM_BWD, i);
-        const int cl = content_index(p, i);
-        if (cl >= 0) {
-          TB(NST_K_CONTENT);
-          CK(content_launch(cl, 1, s2));
-          ++nl;
-          TM(NST_K_CONTENT, i);
-        }
+        TM(NST_K_CONTENT, i);
       }
     }
     if (conc) CK(cudaEventRecord(p->ev[EV_SEEDS], s2));
@@ -1300,12 +1040,8 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   a.w_edge = p->w_edge;
   a.tv_norm = 1.0 / (3.0 * p->H * p->W);
   a.edge_norm = (p->H > 2 && p->W > 2) ? 1.0 / (static_cast<double>(p->H - 2) * (p->W - 2)) : 0.0;
-  if (p->n_content > 0) {
-    // all content layers are weighted equally by 1/(numel_l * n_content); with a single layer this is 1/numel
-    const int i = p->content_conv[0];
-    const double numel = static_cast<double>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
-    a.content_norm = 1.0 / (numel * p->n_content);
-  }
+  // mean over the content layers of the per-layer MSEs; each layer's partial sums are already divided by its own numel
+  if (p->n_content > 0) a.content_norm = 1.0 / p->n_content;
   a.out = p->losses;
   a.counter = counter;
   a.stop_flag = stop_flag;
@@ -1427,7 +1163,9 @@ extern "C" int nst_plan_eval_timed(nst_plan* p, const float* x, float* grad, nst
 
 // forward declaration (defined with the L-BFGS loop below)
 static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm);
+#ifdef NST_INSTRUMENT
 static void timeline_arm(nst_plan* p, bool on);
+#endif
 
 static int step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream, bool grouped);
 extern "C" int nst_lbfgs_step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stream) {
@@ -1451,6 +1189,7 @@ static int step_timed(nst_plan* p, nst_launch_time* out, int max_out, void* stre
   return timer_collect(tm, out, max_out, s);
 }
 
+#ifdef NST_INSTRUMENT
 // Debug / tuning aid: runs one convolution launch of the plan (mode 0 forward, 1 data gradient) with phase
 // timestamps of CTA 0 -> out[7] (SM clock): 0 start, 1 setup done, 2 first operands landed, 3 last MMA issued,
 // 4 accumulator complete, 5 epilogue done, 6 exit.
@@ -1493,26 +1232,6 @@ extern "C" int nst_lbfgs_ctl_clocks(nst_plan* p, long long* out8, void* stream) 
   return NST_OK;
 }
 
-// Debug / tuning aid: runs the forward (which = 0) or backward (1) chained launch once on the plan's current buffers and
-// returns the wait accounting of every CTA (16 counters per CTA, SM cycles; slot meaning: conv_chain.cu) followed by 4
-// counters per layer of the chain (64 layers): out must hold 16 * max_ctas + 256 values.
-extern "C" int nst_plan_chain_waits(nst_plan* p, int which, long long* out, int max_ctas, void* stream) {
-  if (!p || !out || which < 0 || which > 1 || max_ctas < g_num_sms) return fail(NST_ERR_ARG, "nst_plan_chain_waits: bad arguments");
-  if (!p->chain || p->chain_layers[which] == 0) return fail(NST_ERR_STATE, "plan has no chained launch %d", which);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  long long* d = nullptr;
-  const size_t bytes = (static_cast<size_t>(16) * g_num_sms + 256) * sizeof(long long);
-  CK(cudaMalloc(&d, bytes));
-  cudaError_t e = cudaMemsetAsync(d, 0, bytes, s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->chain_done, 0, p->chain_done_bytes, s);
-  if (e == cudaSuccess) e = launch_conv_chain(p->chain_dev[which], p->chain_layers[which], p->chain_items[which], g_num_sms, s, d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d);
-  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "nst_plan_chain_waits: %s", cudaGetErrorString(e));
-  return g_num_sms;
-}
-
 // Debug / tuning aid: where do the convolution launches sit inside the captured step?  enable = 1 gives every conv launch
 // of the plan a slot {earliest CTA start, latest CTA end} in %globaltimer ns (slot = conv for forward, 16 + conv for data
 // gradients, 32 + conv for Gram backward) and drops the captured graph so that the next step re-captures with the slots;
@@ -1536,6 +1255,8 @@ extern "C" int nst_plan_timeline(nst_plan* p, int enable, unsigned long long* ou
   drop_graph(p);
   return NST_OK;
 }
+
+#endif  // NST_INSTRUMENT
 
 // ------------------------------------------------------------------------------------------------
 // mask compositing (the step after the loop in six of the reference's call sites)
@@ -1692,6 +1413,15 @@ __global__ void clamp_copy_kernel(const float* __restrict__ in, float* __restric
     out[i] = fminf(fmaxf(in[i], 0.f), 1.f);
 }
 
+__global__ void lbfgs_ctl_reset_kernel(NstLbfgsCtl* c, int trace_cap) {
+  c->lr = 1.0;            // torch.optim.LBFGS defaults (lbfgs.py:246-271), run_style_transfer.py:90
+  c->tol_grad = 1e-7;
+  c->tol_change = 1e-9;
+  c->history_size = NST_LBFGS_HISTORY;
+  c->H_diag = 1.0;
+  c->trace_cap = trace_cap;
+}
+
 extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, void* stream) {
   if (!p || !x0) return fail(NST_ERR_ARG, "nst_lbfgs_init: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
@@ -1703,16 +1433,11 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
     CKI(plan_alloc_t(p, &p->trace, static_cast<size_t>(trace_capacity) * 5, true));
     p->trace_cap = trace_capacity;
   }
-  NstLbfgsCtl h;
-  memset(&h, 0, sizeof(h));
-  h.lr = 1.0;
-  h.tol_grad = 1e-7;
-  h.tol_change = 1e-9;
-  h.history_size = NST_LBFGS_HISTORY;
-  h.H_diag = 1.0;
-  h.trace_cap = p->trace_cap;
-  CK(cudaMemcpyAsync(b.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // `h` lives on this stack frame
+  // the control block is reset on the device (torch defaults: lr 1, tolerance_grad 1e-7, tolerance_change 1e-9, history 100):
+  // no host staging, hence no host synchronisation per frame
+  CK(cudaMemsetAsync(b.ctl, 0, sizeof(NstLbfgsCtl), s));
+  lbfgs_ctl_reset_kernel<<<1, 1, 0, s>>>(b.ctl, p->trace_cap);
+  CK(cudaGetLastError());
   CK(cudaMemsetAsync(b.R, 0, NST_CTL_MAT_DOUBLES * sizeof(double), s));
   CK(cudaMemsetAsync(b.YY, 0, NST_CTL_MAT_DOUBLES * sizeof(double), s));
   CK(cudaMemsetAsync(b.x, 0, b.n_pad * sizeof(float), s));
@@ -1728,6 +1453,7 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
 // One optimizer.step(closure).  max_evals < 20 truncates the step after that many evaluations (used to time an
 // exact number of evaluations; the optimizer state stays valid - it looks like a step that ended early).
 // arms (or disarms) the launch-span slots of every convolution launch of the plan; see nst_plan_timeline
+#ifdef NST_INSTRUMENT
 static void timeline_arm(nst_plan* p, bool on) {
   for (int i = 0; i < p->n_layers; ++i) {
     p->fwd[i].tl = on ? p->timeline + 2 * i : nullptr;
@@ -1735,6 +1461,7 @@ static void timeline_arm(nst_plan* p, bool on) {
     p->scale[i].tl = on ? p->timeline + 2 * (32 + i) : nullptr;
   }
 }
+#endif
 
 static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm) {
   LbfgsBuffers& b = p->lb;
@@ -1766,7 +1493,9 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
     }
     nl += 4;
     if (k != max_iter) {
+#ifdef NST_INSTRUMENT
       if (p->timeline_on) timeline_arm(p, evals == 10);  // the spans of ONE evaluation in the middle of the step
+#endif
       CKI(eval_enqueue(p, b.x, b.g, &b.ctl->closure_calls, &b.ctl->stop, &nl, s, tm));  // lbfgs.py:493-502
       ++evals;
     }
@@ -1783,6 +1512,35 @@ extern "C" int nst_lbfgs_partial_step(nst_plan* p, int n_evals, void* stream) {
   return nl;
 }
 
+// Captures and instantiates the CUDA graph of one optimizer.step() (about 800 kernel nodes) if the plan has none.
+static int ensure_step_graph(nst_plan* p, cudaStream_t s) {
+  if (p->step_graph) return NST_OK;
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  const int rc = step_enqueue(p, &p->launches_per_step, s, 20, nullptr);
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != NST_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&p->step_graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  e = cudaGraphUpload(p->step_graph, s);  // the first launch then costs what every later launch costs
+  if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaGraphUpload: %s", cudaGetErrorString(e));
+  return NST_OK;
+}
+
+extern "C" int nst_lbfgs_prepare_graph(nst_plan* p, void* stream) {
+  if (!p) return fail(NST_ERR_ARG, "nst_lbfgs_prepare_graph: null plan");
+  if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool no_graph = getenv("NST_NO_GRAPH") != nullptr;
+  if (no_graph || s == nullptr) return NST_OK;  // steps are enqueued directly: nothing to prepare
+  return ensure_step_graph(p, s);
+}
+
 extern "C" int nst_lbfgs_step(nst_plan* p, void* stream) {
   if (!p) return fail(NST_ERR_ARG, "nst_lbfgs_step: null plan");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
@@ -1792,20 +1550,7 @@ extern "C" int nst_lbfgs_step(nst_plan* p, void* stream) {
     // legacy default stream cannot be captured: enqueue directly
     return step_enqueue(p, &p->launches_per_step, s, 20, nullptr);
   }
-  if (!p->step_graph) {
-    cudaGraph_t graph = nullptr;
-    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int rc = step_enqueue(p, &p->launches_per_step, s, 20, nullptr);
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
-    if (rc != NST_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&p->step_graph, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(NST_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-  }
+  CKI(ensure_step_graph(p, s));
   CK(cudaGraphLaunch(p->step_graph, s));
   return NST_OK;
 }

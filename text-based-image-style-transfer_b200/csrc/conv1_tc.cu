@@ -204,7 +204,7 @@ conv1_tc_kernel(const __grid_constant__ ConvParams p, const float* __restrict__ 
     const int stride = gridDim.x;
     // builds the rows of `tile` from patch buffer `buf`, then stashes `next_regs` (the patch of tile + stride) into the
     // other buffer and starts fetching tile + 2 * stride into `far_regs`' place... (the caller orders the register sets)
-    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && t == 0;
+    const bool dbg = NST_DBG_PTR(p) != nullptr && blockIdx.x == 0 && t == 0;
     long long acc_build = 0, acc_wait = 0, acc_write = 0, acc_sync = 0;
     auto build = [&](int buf) {
       const long long c0 = dbg ? clock64() : 0;
@@ -271,10 +271,10 @@ conv1_tc_kernel(const __grid_constant__ ConvParams p, const float* __restrict__ 
       asm volatile("bar.sync 3, 128;" ::: "memory");
     }
     if (dbg) {
-      p.dbg[0] = acc_build;   // patch -> split rows (registers)
-      p.dbg[1] = acc_wait;    // waiting for a free operand stage
-      p.dbg[2] = acc_write;   // swizzled shared-memory writes + proxy fence + arrive
-      p.dbg[3] = acc_sync;    // stash of the prefetched patch + builder barrier (even steps only)
+      NST_DBG_PTR(p)[0] = acc_build;   // patch -> split rows (registers)
+      NST_DBG_PTR(p)[1] = acc_wait;    // waiting for a free operand stage
+      NST_DBG_PTR(p)[2] = acc_write;   // swizzled shared-memory writes + proxy fence + arrive
+      NST_DBG_PTR(p)[3] = acc_sync;    // stash of the prefetched patch + builder barrier (even steps only)
     }
   } else if (warp >= 8) {
     // ===================== epilogue =====================
@@ -291,16 +291,16 @@ conv1_tc_kernel(const __grid_constant__ ConvParams p, const float* __restrict__ 
     const int et = threadIdx.x - 256;
     if (et < C1_N) sbias[et] = __ldg(p.bias + et);
     asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32) : "memory");
-    const bool skip = (p.dbg_flags & 1) != 0;
+    const bool skip = NST_DBG_FLAG(p, 1);
     int k = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
       if ((k & 1) != g) continue;
       const int th = tile / tiles_w, tw = tile - th * tiles_w;
-      const long long e0 = (p.dbg != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0) ? clock64() : 0;
+      const long long e0 = (NST_DBG_PTR(p) != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0) ? clock64() : 0;
       mbar_wait(&tfull_bar[g], tphase);
       tphase ^= 1u;
       tc_fence_after();
-      if (e0) p.dbg[4] += clock64() - e0;  // epilogue group 0: waiting for the accumulator
+      if (e0) NST_DBG_PTR(p)[4] += clock64() - e0;  // epilogue group 0: waiting for the accumulator
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * C1_N);
       uint32_t r0[32], r1[32];
       tmem_ld32(taddr, r0);

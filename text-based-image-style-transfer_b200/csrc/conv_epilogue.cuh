@@ -173,9 +173,9 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
       pack_h32(v, u);
       uint8_t* b = epi_acquire(*st, false);
       stage_row64(b, lane, u);
-      epi_submit(*st, b, &p.tmO0, n, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+      epi_submit(*st, b, &p.tmO0, n, st->w0, st->h0, NST_DBG_FLAG(p, 1));
     }
-  } else if (p.out_tap != nullptr && valid && !(p.dbg_flags & 1)) {
+  } else if (p.out_tap != nullptr && valid && !NST_DBG_FLAG(p, 1)) {
     store_h32(p.out_tap + pix * p.N + n, v);
   }
 #pragma unroll
@@ -187,9 +187,9 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
         pack_h32(v, u);
         uint8_t* b = epi_acquire(*st, false);
         stage_row64(b, lane, u);
-        epi_submit(*st, b, &p.tmO1, n, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+        epi_submit(*st, b, &p.tmO1, n, st->w0, st->h0, NST_DBG_FLAG(p, 1));
       }
-    } else if (p.out_act != nullptr && valid && !(p.dbg_flags & 1)) {
+    } else if (p.out_act != nullptr && valid && !NST_DBG_FLAG(p, 1)) {
       store_h32(p.out_act + pix * p.N + n, v);
     }
     return;
@@ -240,7 +240,7 @@ struct DgradAux {
   uint4 a[2];  // tap seed (bf16) added to the gradient
 };
 __device__ __forceinline__ void dgrad_aux_load(const ConvParams& p, DgradAux& x, int h, int w, int n, bool valid) {
-  if (!valid || (p.dbg_flags & 2)) return;
+  if (!valid || NST_DBG_FLAG(p, 2)) return;
   const size_t pix = static_cast<size_t>(h) * p.W + w;
   if (p.route == nullptr) {
     ld_global_nc_256(p.mask_act + pix * p.N + n, x.m[0], x.m[1]);
@@ -298,8 +298,8 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[D
       uint4* row = reinterpret_cast<uint4*>(st->cur + st->lane * 64);
       row[(2 * half) ^ x] = u[0];
       row[(2 * half + 1) ^ x] = u[1];
-      if (half == 1) epi_submit(*st, st->cur, &p.tmO0, n - DG_CH, st->w0, st->h0, (p.dbg_flags & 1) != 0);
-    } else if (!(p.dbg_flags & 1)) {
+      if (half == 1) epi_submit(*st, st->cur, &p.tmO0, n - DG_CH, st->w0, st->h0, NST_DBG_FLAG(p, 1));
+    } else if (!NST_DBG_FLAG(p, 1)) {
       store_bf<DG_CH>(p.out_grad + pix * p.N + n, v);
     }
   } else {
@@ -324,10 +324,10 @@ __device__ __forceinline__ void epilogue_dgrad(const ConvParams& p, float (&v)[D
         stage_row32(b, row, u);
       } else {
         const size_t upix = static_cast<size_t>(2 * h + (pos >> 1)) * p.Wup + (2 * w + (pos & 1));
-        if (!(p.dbg_flags & 1)) store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
+        if (!NST_DBG_FLAG(p, 1)) store_bf<DG_CH>(p.out_grad + upix * p.N + n, o);
       }
     }
-    if (st != nullptr) epi_submit(*st, b, &p.tmO0, n, 2 * st->w0, 2 * st->h0, (p.dbg_flags & 1) != 0);
+    if (st != nullptr) epi_submit(*st, b, &p.tmO0, n, 2 * st->w0, 2 * st->h0, NST_DBG_FLAG(p, 1));
   }
 }
 
@@ -341,7 +341,7 @@ __device__ __forceinline__ void epilogue_scale(const ConvParams& p, float (&v)[3
     pack_bf<32>(v, u);
     uint8_t* b = epi_acquire(*st, false);
     stage_row64(b, st->lane, u);
-    epi_submit(*st, b, &p.tmO0, n, st->w0, st->h0, (p.dbg_flags & 1) != 0);
+    epi_submit(*st, b, &p.tmO0, n, st->w0, st->h0, NST_DBG_FLAG(p, 1));
     return;
   }
   const size_t pix = static_cast<size_t>(h) * p.W + w;

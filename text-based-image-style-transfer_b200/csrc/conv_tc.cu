@@ -98,11 +98,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
-  const long long life0 = p.dbg != nullptr ? clock64() : 0;
+  const bool dbg = NST_DBG_PTR(p) != nullptr && blockIdx.x == 0;
+  const long long life0 = NST_DBG_PTR(p) != nullptr ? clock64() : 0;
 #define NST_STAMP(slot, cond)                                        \
   do {                                                               \
-    if (dbg && (cond)) p.dbg[slot] = clock64();                      \
+    if (dbg && (cond)) NST_DBG_PTR(p)[slot] = clock64();                      \
   } while (0)
   // wait accounting of CTA 0 (debug): slot 8 MMA waits for the patch, 9 for weights, 10 for a free accumulator stage,
   // 11 epilogue (warp 4) waits for the accumulator, 12 producer waits for a free patch stage, 13 for a free weight stage
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     }                                         \
   } while (0)
   NST_STAMP(0, threadIdx.x == 0);
-  if (p.tl != nullptr && threadIdx.x == 0) atomicMin(&p.tl[0], globaltimer_ns());
+  if (NST_TL_PTR(p) != nullptr && threadIdx.x == 0) atomicMin(&NST_TL_PTR(p)[0], globaltimer_ns());
   // Programmatic dependent launch: let the next kernel in the stream get scheduled as soon as CTAs of this grid retire
   // (its CTAs run their own setup, then block in griddepcontrol.wait until this grid has completed and flushed).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   // dbg_flags bit 2 (timing experiment, wrong results): never re-stream the weights - how fast is the main loop without
   // the TMA writes of the B operand competing with the tensor core's shared-memory reads?
   const bool b_resident = p.taps == 9 && 9 / Cfg::TPS <= Cfg::B_STAGES && !seed &&
-                          ((k_slices == 1 && p.tiles_n == 1) || (p.dbg_flags & 4));
+                          ((k_slices == 1 && p.tiles_n == 1) || NST_DBG_FLAG(p, 4));
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         }
       }
       if (dbg) {
-        p.dbg[12] = wacc0;
-        p.dbg[13] = wacc1;
+        NST_DBG_PTR(p)[12] = wacc0;
+        NST_DBG_PTR(p)[13] = wacc1;
       }
     }
   } else if (warp == 1 && elect_one()) {
@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
     }
     if (dbg) {
-      p.dbg[8] = wacc0;
-      p.dbg[9] = wacc1;
-      p.dbg[10] = wacc2;
+      NST_DBG_PTR(p)[8] = wacc0;
+      NST_DBG_PTR(p)[9] = wacc1;
+      NST_DBG_PTR(p)[10] = wacc2;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     }
   }
 
-  if (dbg && threadIdx.x == 128) p.dbg[11] = wacc0;
+  if (dbg && threadIdx.x == 128) NST_DBG_PTR(p)[11] = wacc0;
   if (TMA_OUT && warp >= 4 && lane == 0) bulk_wait_all();  // the staging buffers must outlive the stores reading them
   tc_fence_before();
   __syncthreads();
@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     tmem_dealloc(tmem_base, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
   }
   NST_STAMP(6, threadIdx.x == 64);
-  if (p.dbg != nullptr && threadIdx.x == 64) p.dbg[16 + blockIdx.x] = clock64() - life0;  // lifetime of every CTA
-  if (p.tl != nullptr && threadIdx.x == 64) atomicMax(&p.tl[1], globaltimer_ns());
+  if (NST_DBG_PTR(p) != nullptr && threadIdx.x == 64) NST_DBG_PTR(p)[16 + blockIdx.x] = clock64() - life0;  // lifetime of every CTA
+  if (NST_TL_PTR(p) != nullptr && threadIdx.x == 64) atomicMax(&NST_TL_PTR(p)[1], globaltimer_ns());
 #undef NST_STAMP
 #undef NST_WAIT
 }

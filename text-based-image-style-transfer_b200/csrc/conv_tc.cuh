@@ -6,6 +6,19 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+// Instrumentation accessors: in the product build they are compile-time constants, so every stamp, wait counter and
+// wrong-result experiment below folds away; -DNST_INSTRUMENT (tools/build.py --instrument) turns them into the fields of
+// ConvParams above.
+#ifdef NST_INSTRUMENT
+#define NST_DBG_PTR(p) ((p).dbg)
+#define NST_TL_PTR(p) ((p).tl)
+#define NST_DBG_FLAG(p, bit) ((((p).dbg_flags) & (bit)) != 0)
+#else
+#define NST_DBG_PTR(p) (static_cast<long long*>(nullptr))
+#define NST_TL_PTR(p) (static_cast<unsigned long long*>(nullptr))
+#define NST_DBG_FLAG(p, bit) (false)
+#endif
+
 namespace nst {
 
 // output-pixel tile of one CTA (M = 128): activation tensor maps use a (64, W+2, H+2) box for 3x3, (64, W, H) for 1x1
@@ -64,13 +77,17 @@ struct ConvParams {
   const float* grad_pix;  // [3,H,W] gradient of the TV + edge terms, or nullptr
   float* out_pix;         // [3,H,W] fp32 gradient w.r.t. the raw image
   float inv_std[3];       // d normalize / d x
-  // ---- phase timestamps of CTA 0 (debug; nullptr in production): see tools/conv_phases.py
+#ifdef NST_INSTRUMENT
+  // ---- instrumented build only (libnst_b200_instr.so, tools/): never part of the product library
+  // phase timestamps of CTA 0: see tools/conv_phases.py
   long long* dbg;
-  // ---- launch span inside a captured step (debug; nullptr in production): tl[0] = earliest CTA start, tl[1] = latest CTA
-  // end, both %globaltimer ns (atomicMin / atomicMax by every CTA): tools/conv_timeline.py
+  // launch span inside a captured step: tl[0] = earliest CTA start, tl[1] = latest CTA end, both %globaltimer ns
+  // (atomicMin / atomicMax by every CTA): tools/conv_timeline.py
   unsigned long long* tl;
-  // ---- debug experiments (0 in production): bit 0 = skip the epilogue's global stores, bit 1 = skip its global loads
+  // timing experiments that produce WRONG results: bit 0 = skip the epilogue's global stores, bit 1 = skip its global
+  // loads, bit 2 = never re-stream the weights
   int dbg_flags;
+#endif
 };
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)

@@ -274,7 +274,9 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
   w.ro = w.yq + NST_LBFGS_SLOTS;
   w.red = w.ro + NST_LBFGS_SLOTS;
   uint64_t* bar = reinterpret_cast<uint64_t*>(w.red + 2);
+#ifdef NST_INSTRUMENT
   if (threadIdx.x == 0) b.ctl->clk[0] = clock64();
+#endif
   const bool stage = b.ctl->stop == NST_RUN && b.ctl->n_iter > 0;
   if (stage && threadIdx.x == 0) {
     // stage the persistent dot-product matrices in shared memory with two bulk copies (2 x 80 KB, L2 resident):

@@ -91,7 +91,11 @@ struct NstCtlWork {
 #define NST_CTL_WORK_DOUBLES (2 * NST_CTL_MAT_DOUBLES + 6 * NST_LBFGS_SLOTS + 4)
 
 #if defined(__CUDA_ARCH__)
+#if defined(NST_INSTRUMENT)
 #define NST_CLK(k) do { if (NST_TID == 0) c->clk[k] = clock64(); } while (0)
+#else
+#define NST_CLK(k) do { } while (0)
+#endif
 #define NST_HD __device__
 #define NST_TID (static_cast<int>(threadIdx.x))
 #define NST_NT (static_cast<int>(blockDim.x))

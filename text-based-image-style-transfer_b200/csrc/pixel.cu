@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(CL_THREADS) content_loss_kernel(const __half* 
                                                                   const float* __restrict__ yc,
                                                                   __nv_bfloat16* __restrict__ addend,
                                                                   double* __restrict__ part, size_t numel,
-                                                                  float gcoef, int accumulate) {
+                                                                  float gcoef, int accumulate, double part_scale) {
   __shared__ double scratch[CL_THREADS / 32];
   float acc = 0.f;
   const size_t nvec = numel / 8;
@@ -458,13 +458,16 @@ __global__ void __launch_bounds__(CL_THREADS) content_loss_kernel(const __half* 
     }
   }
   const double tot = block_sum(static_cast<double>(acc), scratch);
-  if (threadIdx.x == 0) part[blockIdx.x] = tot;
+  // every layer's partial sums carry that layer's own 1 / numel: the assembled value is the mean over the content layers
+  // of the per-layer MSEs (style_transfer_losses.py:53-65) also when the layers differ in size
+  if (threadIdx.x == 0) part[blockIdx.x] = tot * part_scale;
 }
 
 cudaError_t launch_content_loss(const __half* y, const float* yc, __nv_bfloat16* addend, double* part, size_t numel,
                                 float gcoef, int accumulate, cudaStream_t s) {
   if (numel % 8 != 0) return cudaErrorInvalidValue;  // C is a multiple of 64
-  content_loss_kernel<<<content_blocks(numel), CL_THREADS, 0, s>>>(y, yc, addend, part, numel, gcoef, accumulate);
+  content_loss_kernel<<<content_blocks(numel), CL_THREADS, 0, s>>>(y, yc, addend, part, numel, gcoef, accumulate,
+                                                                   1.0 / static_cast<double>(numel));
   return cudaGetLastError();
 }
 

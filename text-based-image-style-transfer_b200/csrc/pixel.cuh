@@ -58,7 +58,7 @@ struct LossAssembleArgs {
   float w_style, w_content, w_tv, w_edge;
   double tv_norm;       // 1 / (3 H W)
   double edge_norm;     // 1 / ((H-2)(W-2))
-  double content_norm;  // 1 / (numel * num_content_layers)
+  double content_norm;  // 1 / num_content_layers (the per-block partial sums already carry 1 / numel of their layer)
   float* out;           // [16]: 0 total, 1..4 weighted c/s/tv/e, 5..9 per-layer Gram MSE, 10..13 unweighted c/s/tv/e
   // closure bookkeeping (run_style_transfer.py:143): *counter += 1 and one trace row per evaluation,
   // unless *stop_flag != 0 (the L-BFGS step already terminated; the evaluation is a no-op replay)

@@ -199,6 +199,11 @@ class Plan:
         with torch.cuda.device(self.device):
             check(self.lib.nst_lbfgs_step(self.handle, _stream_ptr(self.device)))
 
+    def lbfgs_prepare_graph(self):
+        """Captures the CUDA graph of optimizer.step() now instead of inside the first lbfgs_step()."""
+        with torch.cuda.device(self.device):
+            check(self.lib.nst_lbfgs_prepare_graph(self.handle, _stream_ptr(self.device)))
+
     def lbfgs_status(self) -> NstStatus:
         st = NstStatus()
         with torch.cuda.device(self.device):

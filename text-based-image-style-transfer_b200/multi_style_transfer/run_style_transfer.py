@@ -56,23 +56,41 @@ def channel_attention_weights(channels, reduction_ratio=2):
     return fc1.weight.detach(), fc2.weight.detach()
 
 
+CA_SEED = 101   # seed_everything(101), run_style_transfer.py:52
+
+
+def channel_attention_gate_weights(channel_counts, seed=CA_SEED):
+    """Gate weights of channel_att_per_chosen_layers (run_style_transfer.py:13-25): one fresh ChannelAttention per content
+    layer, drawn in layer order from the CPU generator as it stands right after seed_everything(101) - the reference
+    reseeds at the top of every call (:52) and, on a CUDA device, draws nothing from the CPU generator before the modules
+    (its random_init randn is a device draw, :84).  The draw happens inside fork_rng, so it neither depends on nor disturbs
+    the caller's generator: identical inputs give identical gates on every call and on every path (session, frames, planes).
+    With downloaded ImageNet weights the reference's generator has additionally been advanced by torchvision's VGG
+    constructor (random init before load_state_dict); that advance is not emulated - the gate is an untrained random
+    module either way and the golden vectors of tests/golden pin the first-draw convention."""
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        return [channel_attention_weights(c) for c in channel_counts]
+
+
 class StyleTransferSession:
     """VGG trunk + style targets + plan for one (content resolution, style set, weights) configuration."""
 
     def __init__(self, vgg_mean, vgg_std, content_hw, style_imgs: List[torch.Tensor], w_style, w_content, w_tv, w_edge,
                  style_img_weight=0.5, device="cuda", content_layers=CONTENT_LAYERS, style_layers=STYLE_LAYERS,
-                 style_targets: Optional[dict] = None):
+                 style_targets: Optional[dict] = None, net=None):
         self.device = _require_cuda(device)
         self.mean = _as_tensor3(vgg_mean, "vgg_mean")
         self.std = _as_tensor3(vgg_std, "vgg_std")
         self.content_layers = list(content_layers)
         self.style_layers = list(style_layers)
         self.weights = (float(w_style), float(w_content), float(w_tv), float(w_edge))
-        self.net = get_net(self.device)
+        self.net = net if net is not None else get_net(self.device)
         # high priority: the library's side stream (pixel terms, shallow Gram work) is created with the lowest priority, so
         # that when an SM frees up the block scheduler gives it to the critical path (conv chain, optimizer) first
         self.stream = torch.cuda.Stream(self.device, priority=-1)
         H, W = int(content_hw[0]), int(content_hw[1])
+        self._sync_with_caller()
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.plan = Plan(self.net, H, W, self.content_layers + self.style_layers, self.style_layers,
                              self.content_layers, with_grad=True, mean=self.mean, std=self.std)
@@ -84,8 +102,19 @@ class StyleTransferSession:
                 self.plan.set_style_target(name, self.style_targets[name])
             self.stream.synchronize()
 
+    def _sync_with_caller(self, *tensors):
+        """The session works on its own non-blocking stream; inputs were produced on the caller's current stream.  Make
+        the session stream wait for everything enqueued there so far and tell the caching allocator that `tensors` are in
+        use on the session stream."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(self.stream)
+
     def compute_style_targets(self, style_imgs, style_img_weight):
         """Gram targets of style_loss (style_transfer_losses.py:122-135), once instead of once per evaluation."""
+        if torch.cuda.current_stream(self.device) != self.stream:
+            self._sync_with_caller(*style_imgs)
         plans = []
         for img in style_imgs:
             h, w = int(img.shape[2]), int(img.shape[3])
@@ -110,19 +139,26 @@ class StyleTransferSession:
     def prepare(self, content: torch.Tensor, x0: Optional[torch.Tensor] = None, channel_attention=False,
                 trace_capacity=0):
         """Content / edge targets from the content image and optimizer reset (run_style_transfer.py:71-96)."""
+        self._sync_with_caller(content, x0)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             plan = self.plan
             plan.features(content)
-            for name in self.content_layers:
+            gates = None
+            if channel_attention:
+                gates = channel_attention_gate_weights([plan.tap_shape(name)[0] for name in self.content_layers])   # :13-25
+            for k, name in enumerate(self.content_layers):
                 gate = None
-                if channel_attention:
-                    c, _, _ = plan.tap_shape(name)
-                    w1, w2 = channel_attention_weights(c)      # :13-25, fresh module per layer
-                    gate = plan.channel_gate(name, w1, w2)
+                if gates is not None:
+                    gate = plan.channel_gate(name, *gates[k])
                 plan.set_content_target(name, plan, gate)
             if self.weights[3] > 0:
                 plan.set_edge_target(content)
             plan.lbfgs_init(content if x0 is None else x0, trace_capacity)
+
+    def prepare_graph(self):
+        """Captures the CUDA graph of optimizer.step() now (otherwise the first step() does)."""
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.plan.lbfgs_prepare_graph()
 
     def step(self):
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
@@ -200,3 +236,92 @@ def run_multi_style_transfer(vgg_mean, vgg_std, content_img, num_steps, random_i
     finally:
         session.close()
     return tensor_to_PIL(out[0])                                           # :157
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Tutorial-style compatibility surface named by BASELINE.json's north_star.  The reference itself only carries a
+# commented-out import of it (basic.py:12: `from style_transfer.run_style_transfer import run_style_transfer`); SURVEY.md
+# section 0 / 8(b) lists it as optional sugar over run_multi_style_transfer.  It maps onto the SAME device loop with the
+# pixel-space terms switched off (w_tv = w_edge = 0) and the reference's layer set and loss definitions
+# (style_transfer_losses.py: per-layer MSEs averaged over the layers).
+# ------------------------------------------------------------------------------------------------------------------
+def _net_from_cnn(cnn, device):
+    """`cnn`: None (the installed VGG-19 provider), a helper_functions.Vgg19 mirror, an engine.Net, or a torchvision-style
+    `vgg19().features` module (its Conv2d parameters, in order, are handed to the library)."""
+    from ..engine import Net
+    from .helper_functions import Vgg19
+    if cnn is None:
+        return get_net(device)
+    if isinstance(cnn, Net):
+        return cnn
+    if isinstance(cnn, Vgg19):
+        return cnn.net
+    convs = [m for m in cnn.modules() if isinstance(m, torch.nn.Conv2d)]
+    if len(convs) < 13:
+        raise ValueError("cnn must contain the first 13 convolutions of VGG-19 `features` (found %d Conv2d)" % len(convs))
+    return Net([c.weight.detach() for c in convs[:16]], [c.bias.detach() for c in convs[:16]], device)
+
+
+class ContentLoss(torch.nn.Module):
+    """Transparent layer of the tutorial contract: forward(input) stores `self.loss` = MSE(input, target) - the per-layer
+    term of content_loss (style_transfer_losses.py:53-65) - and returns its input unchanged.  `self.loss` is a plain CUDA
+    scalar computed by the library (no autograd graph: the optimisation loop differentiates inside the fused closure)."""
+
+    def __init__(self, target):
+        super().__init__()
+        self.target = target.detach()
+        self.loss = None
+
+    def forward(self, input):
+        from . import style_transfer_losses as L
+        self.loss = L._mse(input, self.target)
+        return input
+
+
+class StyleLoss(torch.nn.Module):
+    """Transparent layer of the tutorial contract: the target is the Gram matrix of `target_feature`
+    (gram_matrix, style_transfer_losses.py:70-95); forward(input) stores `self.loss` = MSE(gram(input), target) - the
+    per-layer term of style_loss (:138-144) - and returns its input unchanged."""
+
+    def __init__(self, target_feature):
+        super().__init__()
+        from . import style_transfer_losses as L
+        self.target = L.gram_matrix(target_feature).detach()
+        self.loss = None
+
+    def forward(self, input):
+        from . import style_transfer_losses as L
+        self.loss = L._mse(L.gram_matrix(input), self.target)
+        return input
+
+
+def run_style_transfer(cnn, normalization_mean, normalization_std, content_img, style_img, input_img, num_steps=300,
+                       style_weight=1000000, content_weight=1):
+    """run_style_transfer(cnn, norm_mean, norm_std, content_img, style_img, input_img, num_steps, style_weight,
+    content_weight) -> the optimised image tensor (1,3,H,W), clamped to [0,1].
+
+    Tensors in, tensor out (CUDA).  Equivalent to run_multi_style_transfer (run_style_transfer.py:27-159) with
+    w_style = style_weight, w_content = content_weight, w_tv = w_edge = 0, a single style, no channel attention, and the
+    optimisation started from `input_img` instead of the content image / randn (:83-87); `num_steps` counts closure
+    evaluations between optimizer.step() calls exactly as there (:99-100).  `input_img` is updated in place, like the
+    parameter the tutorial optimises."""
+    dev = _require_cuda(content_img.device)
+    if content_img.dim() != 4 or content_img.shape[0] != 1 or content_img.shape[1] != 3:
+        raise ValueError("content_img must be a (1,3,H,W) tensor")
+    if tuple(input_img.shape) != tuple(content_img.shape):
+        raise ValueError("input_img must have the shape of content_img")
+    session = StyleTransferSession(normalization_mean, normalization_std, content_img.shape[2:], [style_img.to(dev)],
+                                   float(style_weight), float(content_weight), 0.0, 0.0, device=dev, net=_net_from_cnn(cnn, dev))
+    try:
+        evals = 20 * (int(num_steps) // 20 + 1)
+        session.prepare(content_img, input_img.to(dev), False, trace_capacity=evals + 32)
+        session.run(int(num_steps))
+        out = session.result()
+    finally:
+        session.close()
+    with torch.no_grad():
+        if isinstance(input_img, torch.Tensor) and input_img.is_cuda and not input_img.requires_grad:
+            input_img.copy_(out)
+        elif isinstance(input_img, torch.Tensor) and input_img.is_cuda:
+            input_img.data.copy_(out)
+    return out

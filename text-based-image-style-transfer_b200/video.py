@@ -86,7 +86,7 @@ class FrameStyler:
 
     def __init__(self, vgg_mean, vgg_std, frame_hw, style_imgs: List[torch.Tensor], w_style, w_content, w_tv, w_edge,
                  num_steps: int, style_img_weight=0.5, channel_attention=False, device="cuda", concurrent: int = 1):
-        from .multi_style_transfer.run_style_transfer import StyleTransferSession, STYLE_LAYERS, channel_attention_weights
+        from .multi_style_transfer.run_style_transfer import StyleTransferSession, STYLE_LAYERS, channel_attention_gate_weights
         from .engine import _require_cuda
         self.device = _require_cuda(device)
         dist = _dist()
@@ -107,8 +107,7 @@ class FrameStyler:
         if channel_attention:
             # ChannelAttention is re-created (re-seeded, run_style_transfer.py:52) for every call of the reference:
             # the gate weights are the same for every frame
-            torch.manual_seed(101)
-            w1, w2 = channel_attention_weights(512)
+            (w1, w2), = channel_attention_gate_weights([512])
             self.ca = (w1.to(self.device).contiguous(), w2.to(self.device).contiguous())
         H, W = int(frame_hw[0]), int(frame_hw[1])
         self._in = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import nst_b200  # noqa: E402
+nst_b200._lib.load_instrumented()  # tools/build.py --instrument: the product library has no stamps / timing experiments
 from nst_b200 import synth  # noqa: E402
 from importlib import import_module  # noqa: E402
 
