@@ -630,12 +630,13 @@ def run_b200(args, rank, world, local_rank):
         roofline_small[k] = dict(bound="hbm", ms=by_kind[k], bytes=nbytes, achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
                                  on_critical_path=on_critical_path[k])
     roofline_small["gram"]["tensor_tflops"] = sum(synth.gram_flops(i, S, S) for i in synth._STYLE) / (by_kind["gram"] * 1e-3) / 1e12
-    it_ms = sum(by_kind[k] for k in lb_kinds)
+    it_ms = sum(by_kind.get(k, 0.0) for k in lb_kinds)
     roofline_small["lbfgs_iteration"] = dict(bound="hbm", ms=it_ms, bytes=synth.lbfgs_bytes(S, S, m_avg), unit="GB/s", peak=pk["hbm"],
                                              achieved=synth.lbfgs_bytes(S, S, m_avg) / (it_ms * 1e-3) / 1e9,
                                              frac=synth.lbfgs_bytes(S, S, m_avg) / (it_ms * 1e-3) / 1e9 / pk["hbm"],
-                                             serial_ms=by_kind["lbfgs_reduce"] + by_kind["lbfgs_control"], on_critical_path=True,
-                                             what="pass 1 + reduction + controller + pass 2 at %d stored pairs; serial_ms = reduction + one-block controller" % m_avg)
+                                             serial_ms=by_kind.get("lbfgs_reduce", 0.0) + by_kind["lbfgs_control"], on_critical_path=True,
+                                             what="pass 1 + controller (reduces pass 1's per-block partials, then the recursion on coefficients) + pass 2 at %d stored pairs; "
+                                                  "serial_ms = the one-block controller" % m_avg)
 
     # ---- next rows of the scope table: kernels right behind the loop, measured the same way
     mask_row = assemble_row = mip_row = None

@@ -175,11 +175,19 @@ struct nst_plan {
   int n_style = 0;
   int style_conv[GRAM_MAX_LAYERS] = {};
   float* style_target[GRAM_MAX_LAYERS] = {};
-  float* gdiff[GRAM_MAX_LAYERS] = {};
   __half* dh[GRAM_MAX_LAYERS] = {};
   float* alpha = nullptr;       // [GRAM_MAX_LAYERS]
-  float* style_loss = nullptr;  // [GRAM_MAX_LAYERS]
+  float* dh_scale = nullptr;    // [GRAM_MAX_LAYERS] power-of-two scale of the fp16 Gram-backward operand (from the target)
+  const float* style_fin[GRAM_MAX_LAYERS] = {};   // per style layer: per-block sums of (G - T)^2 inside a set's fin_part
+  int style_fin_n[GRAM_MAX_LAYERS] = {};
   GramParams gram_shallow;  // every style layer except a style layer on the deepest conv (side stream)
+  // The same layers planned for the SMs the convolution chain leaves idle while this launch runs beside it (conv4_2 ..
+  // conv5_1 and the first data gradients have 128 work items on 148 SMs at 512^2): a persistent launch on that many CTAs
+  // never takes an SM a convolution tile is waiting for.  r01's 148-CTA launch pushed conv4_4 into a second wave (+15 us
+  // on the critical path).  num_layers == 0: no idle SMs at this resolution, the wide plan is used.
+  GramParams gram_shallow_narrow;
+  const float* style_fin_narrow[GRAM_MAX_LAYERS] = {};
+  int style_fin_n_narrow[GRAM_MAX_LAYERS] = {};
   GramParams gram_deep;     // the style layer on the deepest conv, if any (critical path)
   float* gram_ws = nullptr;
   cudaStream_t side = nullptr;
@@ -261,8 +269,20 @@ static int content_index(const nst_plan* p, int conv) {
   return -1;
 }
 
+// workspace + rendezvous words of a split-K layer (conv_tc.cuh)
+static int alloc_split(nst_plan* p, ConvParams& c) {
+  if (c.splits <= 1) {
+    c.splits = 1;
+    return NST_OK;
+  }
+  CKI(plan_alloc_t(p, &c.split_ws, static_cast<size_t>(c.num_tiles) * 128 * c.block_n));
+  CKI(plan_alloc_t(p, &c.split_sync, static_cast<size_t>(2) * c.num_tiles, true));
+  return NST_OK;
+}
+
 static int build_conv_params(nst_plan* p) {
   const nst_net* net = p->net;
+  const bool no_split = getenv("NST_NO_SPLIT_K") != nullptr;   // measurement switch: every layer as one work item per tile
   // epilogue outputs through shared memory + TMA stores (conv_epilogue.cuh); NST_DIRECT_STORES=1 keeps the per-thread stores
   const bool tma_out = getenv("NST_DIRECT_STORES") == nullptr;
   {
@@ -302,6 +322,7 @@ static int build_conv_params(nst_plan* p) {
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
     f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
+    f.splits = no_split ? 1 : conv_pick_splits(kCout[i], H, W, kCin[i], 9, g_num_sms, &f.block_n);
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
@@ -310,6 +331,7 @@ static int build_conv_params(nst_plan* p) {
     f.out_route = p->route[i];
     f.pool = pooled ? 1 : 0;
     conv_finalize_params(f, CONV_FWD);
+    CKI(alloc_split(p, f));
     if (tma_out) {
       if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out %d)", i);
       if (!pooled && f.out_act && make_tmap_out(&f.tmO1, f.out_act, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (act out %d)", i);
@@ -326,6 +348,13 @@ static int build_conv_params(nst_plan* p) {
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
     d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
+    {
+      // a data gradient that will carry a folded Gram backward (second accumulator, see below) is not split
+      const int j = i - 1;
+      const bool fold_candidate = getenv("NST_NO_SEED_FOLD") == nullptr && style_index(p, j) >= 0 && !kPoolAfter[j] &&
+                                  content_index(p, j) < 0 && j != p->n_layers - 1;
+      d.splits = (no_split || fold_candidate) ? 1 : conv_pick_splits(kCin[i], H, W, kCout[i], 9, g_num_sms, &d.block_n);
+    }
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
@@ -342,6 +371,7 @@ static int build_conv_params(nst_plan* p) {
       d.addend = p->gadd[i - 1];
     }
     conv_finalize_params(d, CONV_DGRAD);
+    CKI(alloc_split(p, d));
     if (tma_out) {
       const int rc = prev_pooled ? make_tmap_out(&d.tmO0, d.out_grad, d.Hup, d.Wup, kCin[i], 16, 2 * CONV_TILE_W, 8)
                                  : make_tmap_out(&d.tmO0, d.out_grad, H, W, kCin[i], 32, CONV_TILE_W, 4);
@@ -404,7 +434,7 @@ static int build_conv_params(nst_plan* p) {
       const int i = j + 1;
       if (j == p->n_layers - 1 || i >= p->n_layers || kPoolAfter[j] || content_index(p, j) >= 0) continue;
       ConvParams& d = p->dgrad[i];
-      if (d.block_n > 128 || d.route != nullptr) continue;
+      if (d.block_n > 128 || d.route != nullptr || d.splits > 1) continue;
       const int C = kCout[j];
       if (make_tmap_act(&d.tmA2, p->tap[j], d.H, d.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d, folded)", j);
       if (make_tmap_wgt(&d.tmB2, p->dh[l], 1, C, C, d.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
@@ -433,14 +463,63 @@ static int build_gram_params(nst_plan* p) {
     L.HW = p->lh[lv] * p->lw[lv];
     L.inv_norm = 1.f / (static_cast<float>(L.C) * static_cast<float>(L.HW));
     L.target = p->style_target[l];
-    L.gram_out = p->gdiff[l];
+    L.gram_out = nullptr;   // only G - T's fp16 image (dh) and its sum of squares are consumed
     L.dh = p->dh[l];
+    L.dh_scale = p->dh_scale + l;
     L.alpha = p->alpha + l;
-    L.loss = p->style_loss + l;
     // d/dF of w_s/n_style * mean((G-T)^2), G = F F^T / (C HW): 4 w_s (G-T) F / (n_style C^3 HW)
     L.grad_coef = 4.f * p->w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) *
                                       static_cast<float>(L.C) * static_cast<float>(L.C) * static_cast<float>(L.HW));
     if (make_tmap_feat(&g.tm[k], p->tap[i], L.HW, L.C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
+  }
+  return NST_OK;
+}
+
+static int conv_grid(const ConvParams& c) {
+  const int items = c.num_tiles * (c.splits > 1 ? c.splits : 1);
+  return items < g_num_sms ? items : g_num_sms;
+}
+
+// Plans the shallow style layers' Gram launch for the SMs that stay idle beside the deeper convolutions (nst_plan).
+static int build_gram_narrow(nst_plan* p) {
+  memset(&p->gram_shallow_narrow, 0, sizeof(GramParams));
+  for (int l = 0; l < GRAM_MAX_LAYERS; ++l) {
+    p->style_fin_narrow[l] = p->style_fin[l];
+    p->style_fin_n_narrow[l] = p->style_fin_n[l];
+  }
+  const GramParams& wide = p->gram_shallow;
+  if (wide.num_layers == 0 || p->side == nullptr || getenv("NST_GRAM_WIDE") != nullptr) return NST_OK;
+  const int last = p->n_layers - 1;
+  int max_shallow = -1;
+  for (int l = 0; l < p->n_style; ++l)
+    if (p->style_conv[l] != last) max_shallow = p->style_conv[l];
+  // launches that run while the shallow Gram work is in flight: forward convolutions behind its last tap, the deepest
+  // layer's Gram + Gram backward, and the data gradients down to the one that consumes its results
+  int busiest = 0;
+  for (int i = max_shallow + 1; i <= last; ++i) {
+    if (conv_grid(p->fwd[i]) > busiest) busiest = conv_grid(p->fwd[i]);
+    if (p->with_grad && i >= max_shallow + 2 && conv_grid(p->dgrad[i]) > busiest) busiest = conv_grid(p->dgrad[i]);
+  }
+  if (max_shallow + 1 > last) return NST_OK;   // nothing runs beside it
+  const int idle = g_num_sms - busiest;
+  if (idle < 8) return NST_OK;
+  GramParams& g = p->gram_shallow_narrow;
+  g = wide;
+  const size_t ws = gram_plan(g, idle);
+  g.max_ctas = idle;
+  float* wsp = nullptr;
+  float* fin = nullptr;
+  CKI(plan_alloc_t(p, &wsp, ws));
+  CKI(plan_alloc_t(p, &fin, static_cast<size_t>(g.num_fin_blocks), true));
+  g.ws = wsp;
+  g.fin_part = fin;
+  for (int j = 0; j < g.num_layers; ++j) {
+    const GramLayer& L = g.L[j];
+    for (int q = 0; q < p->n_style; ++q)
+      if (p->dh[q] == L.dh) {
+        p->style_fin_narrow[q] = fin + L.fin_blk0;
+        p->style_fin_n_narrow[q] = L.fused ? L.pairs : L.fin_blocks;
+      }
   }
   return NST_OK;
 }
@@ -524,12 +603,18 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
   }
   // ---- style / content / pixel state
   PA(plan_alloc_t(p, &p->alpha, GRAM_MAX_LAYERS, true));
-  PA(plan_alloc_t(p, &p->style_loss, GRAM_MAX_LAYERS, true));
+  PA(plan_alloc_t(p, &p->dh_scale, GRAM_MAX_LAYERS, true));
+  {
+    const float ones[GRAM_MAX_LAYERS] = {1.f, 1.f, 1.f, 1.f, 1.f};   // until nst_plan_set_style_target derives it from the target
+    if (cudaMemcpy(p->dh_scale, ones, sizeof(ones), cudaMemcpyHostToDevice) != cudaSuccess) {
+      nst_plan_destroy(p);
+      return fail(NST_ERR_CUDA, "cudaMemcpy (operand scales)");
+    }
+  }
   PA(plan_alloc_t(p, &p->losses, NST_LOSS_COUNT, true));
   for (int l = 0; l < p->n_style; ++l) {
     const size_t cc = static_cast<size_t>(kCout[p->style_conv[l]]) * kCout[p->style_conv[l]];
     PA(plan_alloc_t(p, &p->style_target[l], cc, true));
-    PA(plan_alloc_t(p, &p->gdiff[l], cc, true));
     PA(plan_alloc_t(p, &p->dh[l], cc, true));
   }
   int cpart = 0;
@@ -558,9 +643,18 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
       float* wsp = nullptr;
       float* fin = nullptr;
       PA(plan_alloc_t(p, &wsp, ws));
-      PA(plan_alloc_t(p, &fin, static_cast<size_t>(2) * sets[k]->num_fin_blocks));
+      PA(plan_alloc_t(p, &fin, static_cast<size_t>(sets[k]->num_fin_blocks), true));
       sets[k]->ws = wsp;
       sets[k]->fin_part = fin;
+      // where the loss assembly finds each style layer's per-block sums
+      for (int j = 0; j < sets[k]->num_layers; ++j) {
+        const GramLayer& L = sets[k]->L[j];
+        int l = 0;
+        for (int q = 0; q < p->n_style; ++q)
+          if (p->dh[q] == L.dh) l = q;
+        p->style_fin[l] = fin + L.fin_blk0;
+        p->style_fin_n[l] = L.fused ? L.pairs : L.fin_blocks;
+      }
     }
   }
   {
@@ -589,14 +683,13 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.hist, lbfgs_hist_floats(b), true));
     PA(plan_alloc_t(p, &b.part, static_cast<size_t>(b.nblocks) * LB_PART_STRIDE, true));
     PA(plan_alloc_t(p, &b.td_part, b.nblocks, true));
-    PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * NST_LBFGS_NDOT, true));
-    PA(plan_alloc_t(p, &b.scal, NST_LBFGS_NSCAL, true));
     PA(plan_alloc_t(p, &b.R, NST_CTL_MAT_DOUBLES, true));
     PA(plan_alloc_t(p, &b.YY, NST_CTL_MAT_DOUBLES, true));
     PA(plan_alloc_t(p, &b.ctl, 1, true));
     b.eval_loss = p->losses;
   }
   PA(build_conv_params(p));
+  PA(build_gram_narrow(p));
 #undef PA
   *out = p;
   return NST_OK;
@@ -618,8 +711,8 @@ extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content,
   p->w_content = w_content;
   p->w_tv = w_tv;
   p->w_edge = w_edge;
-  GramParams* sets[2] = {&p->gram_shallow, &p->gram_deep};
-  for (int k = 0; k < 2; ++k)
+  GramParams* sets[3] = {&p->gram_shallow, &p->gram_deep, &p->gram_shallow_narrow};
+  for (int k = 0; k < 3; ++k)
     for (int l = 0; l < sets[k]->num_layers; ++l) {
       GramLayer& L = sets[k]->L[l];
       L.grad_coef = 4.f * w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) * static_cast<float>(L.C) *
@@ -682,7 +775,7 @@ static int gram_of(const __half* feat, int HW, int C, int c_true, float* out, cu
   float* wsp = nullptr;
   float* fin = nullptr;
   CK(cudaMalloc(&wsp, ws * sizeof(float)));
-  cudaError_t e = cudaMalloc(&fin, static_cast<size_t>(2) * g.num_fin_blocks * sizeof(float));
+  cudaError_t e = cudaMalloc(&fin, static_cast<size_t>(g.num_fin_blocks) * sizeof(float));
   if (e != cudaSuccess) {
     cudaFree(wsp);
     return fail(NST_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
@@ -789,6 +882,8 @@ extern "C" int nst_plan_set_style_target(nst_plan* p, int conv, const float* gra
   const size_t cc = static_cast<size_t>(kCout[conv]) * kCout[conv];
   CK(cudaMemcpyAsync(p->style_target[l], gram, cc * sizeof(float), cudaMemcpyDeviceToDevice,
                      static_cast<cudaStream_t>(stream)));
+  // scale of the fp16 backward operand (G - T) * s: a function of the target alone (gram.cuh)
+  CK(launch_gram_target_scale(p->style_target[l], static_cast<int>(cc), p->dh_scale + l, static_cast<cudaStream_t>(stream)));
   return NST_OK;
 }
 
@@ -915,6 +1010,10 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   const int at_shallow = grouped && max_shallow > 0 ? last : late_at;
   const int at_content = grouped && max_content > 0 ? last : max_content;
 
+  // beside the convolution chain the shallow layers' Gram launch keeps to the idle SMs; alone (timing, single stream) it
+  // takes the whole GPU
+  const bool narrow = conc && p->gram_shallow_narrow.num_layers > 0;
+  const GramParams& gram_shallow = narrow ? p->gram_shallow_narrow : p->gram_shallow;
   auto content_launch = [&](int l, int accumulate, cudaStream_t st) -> cudaError_t {
     const int i = p->content_conv[l];
     const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
@@ -948,8 +1047,8 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
         // ---- side: Gram, style MSE and backward operand of the shallower style layers
         CK(edge(EV_TAPS, s, s2));
         TB(NST_K_GRAM);
-        CK(launch_gram(p->gram_shallow, s2));
-        nl += 3;
+        CK(launch_gram(gram_shallow, s2));
+        nl += gram_launches(gram_shallow);
         TM(NST_K_GRAM, 0);
       }
       if (i == at_content) {
@@ -967,8 +1066,8 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     nl += p->n_layers;
     if (max_shallow == 0) {
       TB(NST_K_GRAM);
-      CK(launch_gram(p->gram_shallow, s2));
-      nl += 3;
+      CK(launch_gram(gram_shallow, s2));
+      nl += gram_launches(gram_shallow);
       TM(NST_K_GRAM, 0);
     }
     if (max_content == 0) {
@@ -983,14 +1082,14 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     if (deep_style) {
       TB(NST_K_GRAM);
       CK(launch_gram(p->gram_deep, s));
-      nl += 3;
+      nl += gram_launches(p->gram_deep);
       TM(NST_K_GRAM, last);
     }
     if (shallow_after_deep) {
       CK(edge(EV_TAPS, s, s2));
       TB(NST_K_GRAM);
-      CK(launch_gram(p->gram_shallow, s2));
-      nl += 3;
+      CK(launch_gram(gram_shallow, s2));
+      nl += gram_launches(gram_shallow);
       TM(NST_K_GRAM, 0);
     }
     for (int l = 0; l < p->n_content; ++l) {
@@ -1032,8 +1131,13 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   a.n_edge = pixel_blocks(p->H, p->W);
   a.content_part = p->content_part;
   a.n_content = use_vgg ? p->content_part_off[p->n_content] : 0;
-  a.style_layer_loss = p->style_loss;
   a.num_style = use_vgg ? p->n_style : 0;
+  for (int l = 0; l < p->n_style; ++l) {
+    const double c = kCout[p->style_conv[l]];
+    a.style_fin[l] = narrow ? p->style_fin_narrow[l] : p->style_fin[l];
+    a.style_fin_n[l] = narrow ? p->style_fin_n_narrow[l] : p->style_fin_n[l];
+    a.style_inv_cc[l] = static_cast<float>(1.0 / (c * c));
+  }
   a.w_style = p->w_style;
   a.w_content = p->w_content;
   a.w_tv = p->w_tv;
@@ -1481,9 +1585,6 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
       TB(NST_K_LBFGS_PASS1);
       CK(launch_lbfgs_pass1(b, s));
       TM(NST_K_LBFGS_PASS1, -1);
-      TB(NST_K_LBFGS_REDUCE);
-      CK(launch_lbfgs_reduce(b, s));
-      TM(NST_K_LBFGS_REDUCE, -1);
       TB(NST_K_LBFGS_CONTROL);
       CK(launch_lbfgs_control(b, mode, s));
       TM(NST_K_LBFGS_CONTROL, -1);
@@ -1491,7 +1592,7 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
       CK(launch_lbfgs_pass2(b, s));
       TM(NST_K_LBFGS_PASS2, -1);
     }
-    nl += 4;
+    nl += 3;
     if (k != max_iter) {
 #ifdef NST_INSTRUMENT
       if (p->timeline_on) timeline_arm(p, evals == 10);  // the spans of ONE evaluation in the middle of the step

@@ -5,8 +5,10 @@
 //   style_loss    multi_style_transfer/style_transfer_losses.py:98-146  (MSELoss(mean) per layer, / #layers)
 // The feature map is NHWC fp16, i.e. a [HW x C] matrix with C contiguous, so F^T F contracts over rows:
 // both MMA operands are "MN-major" views of the same 128B-swizzled tile (64 pixels x 64 channels per
-// TMA box).  Split-K partial tiles go to a workspace; two small kernels reduce them in a fixed order
-// (deterministic), form G - T, the per-layer MSE and the scaled fp16 operand of the backward GEMM.
+// TMA box).  Layers with few K chunks are finished by the Gram kernel itself (one CTA per block pair: G - T, the fp16
+// operand of the backward GEMM and the sum of squares straight from tensor memory); for the others split-K partial tiles
+// go to a workspace and one small kernel reduces them in a fixed order (deterministic).  The per-layer MSE is summed from
+// the per-block sums by the loss assembly (pixel.cu).
 #include "gram.cuh"
 #include <stdlib.h>
 #include "common.cuh"
@@ -24,7 +26,8 @@ static constexpr int G_STAGES = 5;
 // reads whatever follows the first one (those accumulator rows are never stored); behind the last packed chunk of the last
 // stage that must still be inside the allocation
 static constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + G_BOX_BYTES + 1024 + 256;
-static constexpr int G_TMEM_COLS = 128;
+static constexpr int G_TMEM_COLS = 256;                       // two accumulator stages of 128 columns
+static constexpr int GRAM_FUSED_MAX_CHUNKS = 32;            // up to 2048 pixels: one CTA per block pair, finished in place
 
 __device__ __forceinline__ int gram_find_layer_by_item(const GramParams& p, int item) {
   int l = 0;
@@ -51,6 +54,35 @@ __device__ __forceinline__ void gram_pair_to_blocks(int pair, int nblk, int& bi,
   bj = bi + pair;
 }
 
+// What one work item (block pair x K split of one layer) is
+struct GramItem {
+  int l, local, pair, bi, bj, c_begin, c_end, a_boxes, b_boxes, nb, kmul;
+};
+__device__ __forceinline__ GramItem gram_item(const GramParams& p, int item) {
+  GramItem it;
+  it.l = gram_find_layer_by_item(p, item);
+  const GramLayer& L = p.L[it.l];
+  it.local = item - L.item0;
+  it.pair = it.local / L.splits;
+  const int split = it.local - it.pair * L.splits;
+  gram_pair_to_blocks(it.pair, L.nblk, it.bi, it.bj);
+  it.c_begin = static_cast<int>((static_cast<long long>(split) * L.chunks) / L.splits);
+  it.c_end = static_cast<int>((static_cast<long long>(split + 1) * L.chunks) / L.splits);
+  it.a_boxes = L.C >= 128 ? 2 : 1;
+  it.b_boxes = it.bi == it.bj ? 0 : L.bn / 64;
+  // A stage holds 32 KB: four 64-pixel x 64-channel boxes.  An off-diagonal block of a >= 128-channel layer needs all four
+  // for one 64-pixel K chunk (A: 2, B: 2); a diagonal block needs two and conv1_1 (64 channels) one - those pack two / four
+  // consecutive K chunks into a stage, so that every kind of item keeps the same number of bytes in flight (conv1_1's Gram
+  // is a pure 33 MB read; with one 8 KB box per stage it was latency bound and set the duration of the whole launch).
+  it.nb = it.a_boxes + it.b_boxes;   // boxes per 64-pixel chunk
+  it.kmul = 4 / it.nb;               // chunks per stage: 4, 2 or 1
+  return it;
+}
+
+// Persistent: CTA b takes items b, b + gridDim.x, ...  With gridDim.x = num_items (a launch that has the GPU to itself) every
+// CTA runs one item; a launch that shares the GPU with the convolution chain is given only as many CTAs as that chain leaves
+// idle (GramParams::max_ctas) and walks the item list, so that it never takes an SM a convolution tile is waiting for.
+// Two accumulator stages in tensor memory: the epilogue of item i overlaps the main loop of item i + 1.
 __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid_constant__ GramParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -58,33 +90,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES + G_BOX_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + G_STAGES;
-  uint64_t* done_bar = bars + 2 * G_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint64_t* tfull_bar = bars + 2 * G_STAGES;   // [2] accumulator stage complete
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator stage read out by the four epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_sq = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int item = blockIdx.x;
-  const int l = gram_find_layer_by_item(p, item);
-  const GramLayer& L = p.L[l];
-  const int local = item - L.item0;
-  const int pair = local / L.splits;
-  const int split = local - pair * L.splits;
-  int bi, bj;
-  gram_pair_to_blocks(pair, L.nblk, bi, bj);
-  const int c_begin = static_cast<int>((static_cast<long long>(split) * L.chunks) / L.splits);
-  const int c_end = static_cast<int>((static_cast<long long>(split + 1) * L.chunks) / L.splits);
-  const int a_boxes = L.C >= 128 ? 2 : 1;
-  const int b_boxes = bi == bj ? 0 : L.bn / 64;
-  const CUtensorMap* tm = &p.tm[l];
-
-  if (warp == 0 && lane == 0) tma_prefetch_desc(tm);
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < p.num_layers; ++l) tma_prefetch_desc(&p.tm[l]);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(done_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -99,82 +124,166 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // A stage holds 32 KB: four 64-pixel x 64-channel boxes.  An off-diagonal block of a >= 128-channel layer needs all four
-  // for one 64-pixel K chunk (A: 2, B: 2); a diagonal block needs two and conv1_1 (64 channels) one - those pack two / four
-  // consecutive K chunks into a stage, so that every kind of item keeps the same number of bytes in flight (conv1_1's Gram
-  // is a pure 33 MB read; with one 8 KB box per stage it was latency bound and set the duration of the whole launch).
-  const int nb = a_boxes + b_boxes;        // boxes per 64-pixel chunk
-  const int kmul = 4 / nb;                 // chunks per stage: 4, 2 or 1
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int c = c_begin; c < c_end; c += kmul) {
-        const int n = c_end - c < kmul ? c_end - c : kmul;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(n * nb * G_BOX_BYTES));
-        for (int j = 0; j < n; ++j) {
-          uint8_t* sa = smem + stage * G_STAGE_BYTES + j * nb * G_BOX_BYTES;
-          uint8_t* sb = sa + a_boxes * G_BOX_BYTES;
-          for (int b = 0; b < a_boxes; ++b)
-            tma_load_2d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], bi * 128 + b * 64, (c + j) * G_KCHUNK);
-          for (int b = 0; b < b_boxes; ++b)
-            tma_load_2d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], bj * 128 + b * 64, (c + j) * G_KCHUNK);
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const GramItem it = gram_item(p, item);
+        const CUtensorMap* tm = &p.tm[it.l];
+        for (int c = it.c_begin; c < it.c_end; c += it.kmul) {
+          const int n = it.c_end - c < it.kmul ? it.c_end - c : it.kmul;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(n * it.nb * G_BOX_BYTES));
+          for (int j = 0; j < n; ++j) {
+            uint8_t* sa = smem + stage * G_STAGE_BYTES + j * it.nb * G_BOX_BYTES;
+            uint8_t* sb = sa + it.a_boxes * G_BOX_BYTES;
+            for (int b = 0; b < it.a_boxes; ++b)
+              tma_load_2d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], it.bi * 128 + b * 64, (c + j) * G_KCHUNK);
+            for (int b = 0; b < it.b_boxes; ++b)
+              tma_load_2d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], it.bj * 128 + b * 64, (c + j) * G_KCHUNK);
+          }
+          if (++stage == G_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0, ts = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const GramItem it = gram_item(p, item);
+      const GramLayer& L = p.L[it.l];
+      const uint32_t idesc = umma_idesc_f16(128, L.bn, 0, 1, 1);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * 128);
+      mbar_wait(&tempty_bar[ts], tphase ^ 1u);
+      tc_fence_after();
+      for (int c = it.c_begin; c < it.c_end; c += it.kmul) {
+        const int n = it.c_end - c < it.kmul ? it.c_end - c : it.kmul;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int j = 0; j < n; ++j) {
+            const uint32_t a_addr = smem_u32(smem + stage * G_STAGE_BYTES + j * it.nb * G_BOX_BYTES);
+            const uint32_t b_addr = it.bi == it.bj ? a_addr : a_addr + it.a_boxes * G_BOX_BYTES;
+#pragma unroll
+            for (int k = 0; k < G_KCHUNK / 16; ++k) {
+              // MN-major: LBO = distance between the two 64-channel boxes, SBO = 8 pixel rows
+              const uint64_t da = umma_desc_sw128(a_addr + k * 16 * 128, G_BOX_BYTES, 1024);
+              const uint64_t db = umma_desc_sw128(b_addr + k * 16 * 128, G_BOX_BYTES, 1024);
+              umma_f16(d_tmem, da, db, idesc, (c > it.c_begin || j > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (c + it.kmul >= it.c_end) umma_commit(&tfull_bar[ts]);
+        }
+        __syncwarp();
         if (++stage == G_STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-    }
-  } else if (warp == 1) {
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t idesc = umma_idesc_f16(128, L.bn, 0, 1, 1);
-    for (int c = c_begin; c < c_end; c += kmul) {
-      const int n = c_end - c < kmul ? c_end - c : kmul;
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        for (int j = 0; j < n; ++j) {
-          const uint32_t a_addr = smem_u32(smem + stage * G_STAGE_BYTES + j * nb * G_BOX_BYTES);
-          const uint32_t b_addr = bi == bj ? a_addr : a_addr + a_boxes * G_BOX_BYTES;
-#pragma unroll
-          for (int k = 0; k < G_KCHUNK / 16; ++k) {
-            // MN-major: LBO = distance between the two 64-channel boxes, SBO = 8 pixel rows
-            const uint64_t da = umma_desc_sw128(a_addr + k * 16 * 128, G_BOX_BYTES, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 16 * 128, G_BOX_BYTES, 1024);
-            umma_f16(tmem_base, da, db, idesc, (c > c_begin || j > 0 || k > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(&empty_bar[stage]);
-        if (c + kmul >= c_end) umma_commit(done_bar);
-      }
-      __syncwarp();
-      if (++stage == G_STAGES) {
-        stage = 0;
-        phase ^= 1u;
+      if (++ts == 2) {
+        ts = 0;
+        tphase ^= 1u;
       }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-    float* dst = p.ws + L.ws_off + (static_cast<size_t>(local) * 128 + row) * L.bn;
-    const bool row_ok = bi * 128 + row < L.C;
+    int ts = 0;
+    uint32_t tphase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const GramItem it = gram_item(p, item);
+      const GramLayer& L = p.L[it.l];
+      const int bi = it.bi, bj = it.bj;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * 128);
+      const bool row_ok = bi * 128 + row < L.C;
+      if (L.fused && L.target != nullptr) {
+        // ---- the layer is finished here: d = G - T, fp16 backward operand d * dh_scale (both triangles), sum of d^2.
+        // Everything that does not depend on the accumulator is fetched before waiting for it.
+        const int gi = bi * 128 + row;
+        const float scale = L.dh_scale != nullptr ? __ldg(L.dh_scale) : 1.f;
+        const float* trow = L.target + static_cast<size_t>(row_ok ? gi : 0) * L.C + bj * 128;
+        float sq = 0.f;
+        const float w = bi == bj ? 1.f : 2.f;   // an off-diagonal block stands for its mirror image too
+        mbar_wait(&tfull_bar[ts], tphase);
+        tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < L.bn / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        // 32-byte stores: the lanes of a warp are whole rows apart, so a 16-byte store would write half sectors
+        for (int c = 0; c < L.bn / 32; ++c) {
+          float4 t4[8];
+          if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c * 32 + 8 * j), "r"(r[8 * j]), "r"(r[8 * j + 1]),
-                       "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]), "r"(r[8 * j + 6]), "r"(r[8 * j + 7])
-                       : "memory");
+            for (int j = 0; j < 8; ++j) t4[j] = __ldg(reinterpret_cast<const float4*>(trow + c * 32) + j);
+          }
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            const float* tt = reinterpret_cast<const float*>(t4);
+            __align__(16) __half hv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int gj = bj * 128 + c * 32 + j;
+              float d = __uint_as_float(r[j]) * L.inv_norm - tt[j];
+              if (gj >= L.C) d = 0.f;
+              sq = fmaf(w * d, d, sq);
+              hv[j] = __float2half_rn(d * scale);
+            }
+            if (L.dh != nullptr) {
+              __half* drow = L.dh + static_cast<size_t>(gi) * L.C + bj * 128 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *(reinterpret_cast<uint4*>(drow) + j) = *(reinterpret_cast<const uint4*>(hv) + j);
+              if (bi != bj) {
+                // mirror image: consecutive lanes are consecutive rows gi, so every store instruction of the warp is contiguous
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int gj = bj * 128 + c * 32 + j;
+                  if (gj < L.C) L.dh[static_cast<size_t>(gj) * L.C + gi] = hv[j];
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        sq = warp_sum(sq);
+        if (lane == 0) {
+          mbar_arrive(&tempty_bar[ts]);
+          s_sq[q] = sq;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+        if (warp == 4 && lane == 0) {
+          p.fin_part[L.fin_blk0 + it.pair] = ((s_sq[0] + s_sq[1]) + s_sq[2]) + s_sq[3];
+          if (it.pair == 0 && L.alpha != nullptr) *L.alpha = L.grad_coef / scale;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_sq is rewritten by the next item
+      } else {
+        mbar_wait(&tfull_bar[ts], tphase);
+        tc_fence_after();
+        float* dst = p.ws + L.ws_off + (static_cast<size_t>(it.local) * 128 + row) * L.bn;
+#pragma unroll 1
+        for (int c = 0; c < L.bn / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            // 32-byte stores: the lanes of a warp are whole rows apart, so a 16-byte store would write half sectors
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c * 32 + 8 * j), "r"(r[8 * j]), "r"(r[8 * j + 1]),
+                           "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]), "r"(r[8 * j + 6]), "r"(r[8 * j + 7])
+                           : "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[ts]);
+      }
+      if (++ts == 2) {
+        ts = 0;
+        tphase ^= 1u;
       }
     }
   }
@@ -243,76 +352,55 @@ __device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const Gram
   return e;
 }
 
-// pass 1: reduce split-K partials, G or G - T, per-block (sum of squares, max abs)
-__global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize1_kernel(const __grid_constant__ GramParams p) {
+// Split-K layers: reduce the partial tiles in a fixed order, G (no target) or d = G - T, the fp16 backward operand
+// d * dh_scale (both triangles) and the per-block sum of d^2.  Fused layers (GramLayer::fused) have nothing left to do.
+__global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize_kernel(const __grid_constant__ GramParams p) {
   __shared__ float scratch[GRAM_FIN_THREADS / 32];
   __shared__ float s_part[GRAM_FIN_THREADS];
   const int l = gram_find_layer_by_finblk(p, blockIdx.x);
   const GramLayer& L = p.L[l];
+  const float scale = (L.dh_scale != nullptr && !L.fused) ? __ldg(L.dh_scale) : 1.f;  // set with the target: not written by the previous launch
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (L.fused && L.target != nullptr) return;
   FinElem e = gram_fin_elem(p, L, blockIdx.x - L.fin_blk0, s_part);
-  float sq = 0.f, mx = 0.f;
+  float sq = 0.f;
   if (e.ok) {
     float d = e.g;
     if (L.target != nullptr) d -= L.target[static_cast<size_t>(e.gi) * L.C + e.gj];
-    L.gram_out[static_cast<size_t>(e.gi) * L.C + e.gj] = d;
-    if (e.offdiag) L.gram_out[static_cast<size_t>(e.gj) * L.C + e.gi] = d;
+    if (L.gram_out != nullptr) {
+      L.gram_out[static_cast<size_t>(e.gi) * L.C + e.gj] = d;
+      if (e.offdiag) L.gram_out[static_cast<size_t>(e.gj) * L.C + e.gi] = d;
+    }
+    if (L.dh != nullptr) {
+      const __half h = __float2half_rn(d * scale);
+      L.dh[static_cast<size_t>(e.gi) * L.C + e.gj] = h;
+      if (e.offdiag) L.dh[static_cast<size_t>(e.gj) * L.C + e.gi] = h;
+    }
     sq = e.offdiag ? 2.f * d * d : d * d;
-    mx = fabsf(d);
   }
   sq = block_sum(sq, scratch);
-  mx = block_max(mx, scratch);
   if (threadIdx.x == 0) {
-    p.fin_part[2 * blockIdx.x] = sq;
-    p.fin_part[2 * blockIdx.x + 1] = mx;
+    p.fin_part[blockIdx.x] = sq;
+    if (blockIdx.x == L.fin_blk0 && L.alpha != nullptr) *L.alpha = L.grad_coef / scale;
   }
 }
 
-// pass 2: per-layer loss, scale, fp16 backward operand
-__global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize2_kernel(const __grid_constant__ GramParams p) {
-  __shared__ float scratch[GRAM_FIN_THREADS / 32];
-  __shared__ float s_bcast[2];
-  const int l = gram_find_layer_by_finblk(p, blockIdx.x);
-  const GramLayer& L = p.L[l];
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (L.target == nullptr) return;
-  float sq = 0.f, mx = 0.f;
-  for (int b = threadIdx.x; b < L.fin_blocks; b += GRAM_FIN_THREADS) {
-    sq += p.fin_part[2 * (L.fin_blk0 + b)];
-    mx = fmaxf(mx, p.fin_part[2 * (L.fin_blk0 + b) + 1]);
-  }
-  sq = block_sum(sq, scratch);
-  mx = block_max(mx, scratch);
+// dh_scale of a target: largest power of two s with max|T| * s <= 64 (1 for an all-zero target)
+__global__ void __launch_bounds__(256) gram_target_scale_kernel(const float* __restrict__ t, int cc, float* __restrict__ out) {
+  __shared__ float scratch[8];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < cc; i += 256) m = fmaxf(m, fabsf(t[i]));
+  m = block_max(m, scratch);
   if (threadIdx.x == 0) {
-    s_bcast[0] = sq;
-    s_bcast[1] = mx;
+    float s = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      int e;
+      frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(6 - e) in [32, 64)
+      s = ldexpf(1.f, 6 - e);
+    }
+    *out = s;
   }
-  __syncthreads();
-  sq = s_bcast[0];
-  mx = s_bcast[1];
-  if (blockIdx.x == L.fin_blk0 && threadIdx.x == 0) {
-    *L.loss = sq / (static_cast<float>(L.C) * static_cast<float>(L.C));
-    *L.alpha = L.grad_coef * mx;
-  }
-  if (L.dh == nullptr) return;
-  const float inv = mx > 0.f ? 1.f / mx : 0.f;
-  const int tile = 128 * L.bn;
-  const int FIN_ELEMS = GRAM_FIN_THREADS / L.fin_q;
-  if (threadIdx.x >= FIN_ELEMS) return;
-  const int id = (blockIdx.x - L.fin_blk0) * FIN_ELEMS + threadIdx.x;
-  if (id >= L.pairs * tile) return;
-  const int pair = id / tile;
-  const int rem = id - pair * tile;
-  const int li = rem / L.bn, lj = rem - li * L.bn;
-  int bi, bj;
-  gram_pair_to_blocks(pair, L.nblk, bi, bj);
-  const int gi = bi * 128 + li, gj = bj * 128 + lj;
-  if (gi >= L.C || gj >= L.C) return;
-  const float d = L.gram_out[static_cast<size_t>(gi) * L.C + gj] * inv;
-  L.dh[static_cast<size_t>(gi) * L.C + gj] = __float2half_rn(d);
-  if (bi != bj) L.dh[static_cast<size_t>(gj) * L.C + gi] = __float2half_rn(d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -362,12 +450,19 @@ size_t gram_plan(GramParams& p, int target_ctas) {
     long long s = (layer_boxes[l] + per_cta * L.pairs - 1) / ((per_cta > 0 ? per_cta : 1) * L.pairs);
     if (s < 1) s = 1;
     if (s > L.chunks) s = L.chunks;
+    // Few K chunks (deep layers at moderate resolution: conv5_1 at 512^2 has 16): splitting them ~15 ways made every CTA run
+    // four MMAs and then write a 64 KB partial tile for a finalize launch to gather again.  One CTA per block pair instead
+    // keeps the accumulator in tensor memory to the end and finishes the layer in the same launch (GramLayer::fused).
+    if (L.chunks <= GRAM_FUSED_MAX_CHUNKS) s = 1;
     L.splits = static_cast<int>(s);
+    L.fused = L.splits == 1 ? 1 : 0;
     L.item0 = item;
     item += L.pairs * L.splits;
     L.fin_blk0 = fin;
     L.fin_q = L.splits >= 16 ? 4 : 1;
     const int fin_elems = GRAM_FIN_THREADS / L.fin_q;
+    // a fused layer with a target needs one sum-of-squares slot per block pair; without a target (nst_plan_tap_gram: G itself
+    // is wanted) it goes through the workspace and the finalize kernel like a split layer with one split
     L.fin_blocks = (L.pairs * 128 * L.bn + fin_elems - 1) / fin_elems;
     fin += L.fin_blocks;
     L.ws_off = ws;
@@ -401,12 +496,23 @@ static cudaError_t launch_pdl(void (*kernel)(Args...), int grid, int block, size
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
+static bool gram_needs_finalize(const GramParams& p) {
+  for (int l = 0; l < p.num_layers; ++l)
+    if (!(p.L[l].fused && p.L[l].target != nullptr)) return true;
+  return false;
+}
+int gram_launches(const GramParams& p) { return gram_needs_finalize(p) ? 2 : 1; }
+
 cudaError_t launch_gram(const GramParams& p, cudaStream_t stream) {
-  cudaError_t e = launch_pdl(gram_partial_kernel, p.num_items, G_THREADS, G_SMEM_BYTES, stream, p);
-  if (e != cudaSuccess) return e;
-  e = launch_pdl(gram_finalize1_kernel, p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream, p);
-  if (e != cudaSuccess) return e;
-  return launch_pdl(gram_finalize2_kernel, p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream, p);
+  const int grid = (p.max_ctas > 0 && p.max_ctas < p.num_items) ? p.max_ctas : p.num_items;
+  cudaError_t e = launch_pdl(gram_partial_kernel, grid, G_THREADS, G_SMEM_BYTES, stream, p);
+  if (e != cudaSuccess || !gram_needs_finalize(p)) return e;
+  return launch_pdl(gram_finalize_kernel, p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream, p);
+}
+
+cudaError_t launch_gram_target_scale(const float* target, int cc, float* scale_out, cudaStream_t stream) {
+  gram_target_scale_kernel<<<1, 256, 0, stream>>>(target, cc, scale_out);
+  return cudaGetLastError();
 }
 
 }  // namespace nst

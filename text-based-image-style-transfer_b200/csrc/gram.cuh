@@ -24,13 +24,18 @@ struct GramLayer {
   int fin_blk0;   // first finalize block of this layer
   int fin_blocks; // finalize blocks of this layer
   int fin_q;      // threads that share the split-K sum of one element in finalize1: 4 when there are many splits, else 1
+  int fused;      // splits == 1: the Gram kernel finishes the layer itself (G - T, backward operand, sum of squares) straight
+                  // from tensor memory - no workspace round trip, no finalize launch; its fin blocks are its block pairs
   size_t ws_off;  // float offset of this layer's partial tiles in the workspace
   // finalize inputs / outputs
   const float* target;  // [C,C] target Gram or nullptr (then `gram_out` receives G itself)
   float* gram_out;      // [C,C] G (if target == nullptr) or G - T
-  __half* dh;           // [C,C] (G - T) / max|G - T| as fp16 (backward operand), or nullptr
-  float* alpha;         // device scalar: coefficient of the backward 1x1 convolution
-  float* loss;          // device scalar: mean((G - T)^2)
+  __half* dh;           // [C,C] (G - T) * dh_scale as fp16 (backward operand), or nullptr
+  // Device scalar: the power of two that maps max|T| to 64 (gram_target_scale).  It depends on the TARGET only, so the
+  // operand can be written in the same pass that forms G - T (r01 normalised by max|G - T|, which needs a second pass over
+  // the matrix and a launch of its own).  fp16 keeps 10 bits for every |G - T| between 1e-6 and 1e3 times max|T|.
+  const float* dh_scale;
+  float* alpha;         // device scalar: coefficient of the backward 1x1 convolution = grad_coef / dh_scale
   float grad_coef;      // 4 * w_style / (num_layers * C^3 * HW)
 };
 
@@ -39,15 +44,20 @@ struct GramParams {
   GramLayer L[GRAM_MAX_LAYERS];
   int num_layers;
   int num_items;
+  int max_ctas;     // 0: one CTA per item; else the Gram kernel runs persistent on at most this many CTAs (see gram.cu)
   int num_fin_blocks;
   float* ws;        // split-K partial tiles [item][128][bn]
-  float* fin_part;  // [num_fin_blocks][2] partial (sum sq, max abs)
+  float* fin_part;  // [num_fin_blocks] partial sums of (G - T)^2; summed per layer in a fixed order by the loss assembly
 };
 
 int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C);
 // fills nblk/pairs/bn/splits/chunks/item0/fin_* /ws_off and the totals; returns workspace floats needed
 size_t gram_plan(GramParams& p, int target_ctas);
 cudaError_t launch_gram(const GramParams& p, cudaStream_t stream);
+// number of kernels launch_gram enqueues for this parameter set (1 when every layer is fused, else 2)
+int gram_launches(const GramParams& p);
+// dh_scale of a [C,C] target: 2^(6 - ceil(log2(max|T|))), 1 for an all-zero target (device scalar out)
+cudaError_t launch_gram_target_scale(const float* target, int cc, float* scale_out, cudaStream_t stream);
 // sets the kernel attributes (opt-in shared memory); call once per process before any capture
 cudaError_t gram_init();
 

@@ -240,59 +240,37 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     // lbfgs.py:432-435: for k newest..oldest: al_k = ro_k (s_k . q); q -= al_k y_k.  Column oriented: once al_k is
     // known every older row i subtracts al_k (s_i . y_k) from its running s_i . q - no reduction on the dependent chain.
 #if defined(__CUDA_ARCH__)
-    // Device: blocked back-substitution.  The recurrence is a triangular solve; 32 pairs at a time, warp 0 runs the
-    // dependent chain with everything in registers (lane l owns one row, its 32 matrix entries of the diagonal block
-    // are preloaded, al_k travels by one 64-bit shuffle: a step is shuffle + multiply-add), then the whole block applies
-    // the 32 new al_k to all older rows in parallel.  Same arithmetic as the loop below up to the fp64 summation order.
-    // Warp b owns diagonal block b (at most four: len <= 100).  All four preload their 32 x 32 piece of the matrix into
-    // registers at once, up front - the entries do not depend on the recurrence; preloading block after block inside
-    // the loop put 1.4 us of shared-memory latency in front of every 1.2 us chain.
-    const int my_blk = tid >> 5, lane_c = tid & 31;
-    double rr[32];
-    {
-      const int hi_b = len - 32 * my_blk;
-      const int lo_b = hi_b > 32 ? hi_b - 32 : 0, nb_b = hi_b > 0 ? hi_b - lo_b : 0;
-      const bool own_b = my_blk < 4 && lane_c < nb_b;
-      const int pa_b = nst_ctl_slot(head, own_b ? lo_b + lane_c : 0);
+    // Device: ONE warp runs the whole dependent chain, no block barrier inside it.  Lane l owns rows l, l + 32, l + 64, l + 96
+    // (age order) with their running values s_i . q in registers; a step is: the owner lane of row k forms al_k, one 64-bit
+    // shuffle broadcasts it, every lane applies it to its (at most four) older rows.  The matrix entries a step needs do not
+    // depend on the chain, so their shared-memory loads are issued ahead of it (the loop is unrolled).  r01 ran the chain in
+    // 32-row blocks with a block-wide update and two __syncthreads() per block: 9.8 us for 100 pairs; this form is bound by
+    // ~50 cycles per step.
+    if (tid < 32) {
+      const int lane = tid;
+      double cv[4], rov[4];
+      int prow[4];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) rr[j] = (own_b && j < nb_b) ? w.R[pa_b * TOT + nst_ctl_slot(head, lo_b + (j < nb_b ? j : 0))] : 0.0;
-    }
-    int blk = 0;
-    for (int hi = len; hi > 0; hi -= 32, ++blk) {
-      const int lo = hi > 32 ? hi - 32 : 0, nb = hi - lo;
-      if (my_blk == blk) {
-        const bool own = lane_c < nb;
-        const int pa = nst_ctl_slot(head, own ? lo + lane_c : lo);
-        double run = own ? w.c[pa] : 0.0;
-        const double rok = own ? w.ro[pa] : 0.0;
-        double mine = 0.0;
+      for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        prow[j] = nst_ctl_slot(head, i < len ? i : 0);
+        cv[j] = i < len ? w.c[prow[j]] : 0.0;
+        rov[j] = i < len ? w.ro[prow[j]] : 0.0;
+      }
+#pragma unroll 4
+      for (int k = len - 1; k >= 0; --k) {
+        const int pk = nst_ctl_slot(head, k);
+        const int jk = k >> 5, lk = k & 31;
+        double r4[4];
 #pragma unroll
-        for (int kk = 31; kk >= 0; --kk) {
-          if (kk < nb) {
-            const double al = __shfl_sync(0xffffffffu, rok * run, kk);
-            if (lane_c < kk) run -= al * rr[kk];
-            if (lane_c == kk) mine = al;
-          }
-        }
-        if (own) w.al[pa] = mine;
+        for (int j = 0; j < 4; ++j) r4[j] = w.R[prow[j] * TOT + pk];
+        const double mine = jk == 0 ? rov[0] * cv[0] : (jk == 1 ? rov[1] * cv[1] : (jk == 2 ? rov[2] * cv[2] : rov[3] * cv[3]));
+        const double al = __shfl_sync(0xffffffffu, mine, lk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lane + 32 * j < k) cv[j] -= al * r4[j];
+        if (lane == lk) w.al[pk] = al;
       }
-      NST_BLOCK_SYNC();
-      // rows older than the block: c_i -= sum_k al_k (s_i . y_k); four threads per row, eight columns each
-      {
-        const int row = tid >> 2, part = tid & 3;
-        double acc = 0.0;
-        const int pi = nst_ctl_slot(head, row < lo ? row : 0);
-        if (row < lo) {
-          for (int j = part; j < nb; j += 4) {
-            const int pk = nst_ctl_slot(head, lo + j);
-            acc += w.al[pk] * w.R[pi * TOT + pk];
-          }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (row < lo && part == 0) w.c[pi] -= acc;
-      }
-      NST_BLOCK_SYNC();
     }
 #else
     if (tid < NST_CTL_NL) {
@@ -325,52 +303,34 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     // lbfgs.py:439-442: r = H q; for k oldest..newest: be_k = ro_k (y_k . r); r += (al_k - be_k) s_k.  Once c_k is known
     // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
 #if defined(__CUDA_ARCH__)
-    // device: the same blocking, forward
-    {
-      // preload, all four warps at once (see loop 1): warp b takes the block that starts at 32 b
-      const int lo_b = 32 * my_blk;
-      const int hi_b = lo_b + 32 < len ? lo_b + 32 : len, nb_b = hi_b > lo_b ? hi_b - lo_b : 0;
-      const bool own_b = my_blk < 4 && lane_c < nb_b;
-      const int pa_b = nst_ctl_slot(head, own_b ? lo_b + lane_c : 0);
+    // device: the same single-warp form, forward
+    if (tid < 32) {
+      const int lane = tid;
+      double yv[4], rov[4], alv[4];
+      int prow[4];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) rr[j] = (own_b && j < nb_b) ? w.R[nst_ctl_slot(head, lo_b + (j < nb_b ? j : 0)) * TOT + pa_b] : 0.0;
-    }
-    blk = 0;
-    for (int lo = 0; lo < len; lo += 32, ++blk) {
-      const int hi = lo + 32 < len ? lo + 32 : len, nb = hi - lo;
-      if (my_blk == blk) {
-        const bool own = lane_c < nb;
-        const int pa = nst_ctl_slot(head, own ? lo + lane_c : lo);
-        double run = own ? w.yq[pa] : 0.0;
-        const double rok = own ? w.ro[pa] : 0.0, alk = own ? w.al[pa] : 0.0;
-        double mine = 0.0;
+      for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        prow[j] = nst_ctl_slot(head, i < len ? i : 0);
+        yv[j] = i < len ? w.yq[prow[j]] : 0.0;
+        rov[j] = i < len ? w.ro[prow[j]] : 0.0;
+        alv[j] = i < len ? w.al[prow[j]] : 0.0;
+      }
+#pragma unroll 4
+      for (int k = 0; k < len; ++k) {
+        const int pk = nst_ctl_slot(head, k);
+        const int jk = k >> 5, lk = k & 31;
+        double r4[4];
 #pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          if (kk < nb) {
-            const double ck = __shfl_sync(0xffffffffu, alk - rok * run, kk);
-            if (lane_c > kk) run += ck * rr[kk];
-            if (lane_c == kk) mine = ck;
-          }
-        }
-        if (own) w.c[pa] = mine;
+        for (int j = 0; j < 4; ++j) r4[j] = w.R[pk * TOT + prow[j]];
+        const double mine = jk == 0 ? alv[0] - rov[0] * yv[0]
+                                    : (jk == 1 ? alv[1] - rov[1] * yv[1] : (jk == 2 ? alv[2] - rov[2] * yv[2] : alv[3] - rov[3] * yv[3]));
+        const double ck = __shfl_sync(0xffffffffu, mine, lk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lane + 32 * j > k) yv[j] += ck * r4[j];
+        if (lane == lk) w.c[pk] = ck;
       }
-      NST_BLOCK_SYNC();
-      // rows younger than the block: (y_i . r) += sum_k c_k (s_k . y_i)
-      {
-        const int row = hi + (tid >> 2), part = tid & 3;
-        double acc = 0.0;
-        const int pi = nst_ctl_slot(head, row < len ? row : 0);
-        if (row < len) {
-          for (int j = part; j < nb; j += 4) {
-            const int pk = nst_ctl_slot(head, lo + j);
-            acc += w.c[pk] * w.R[pk * TOT + pi];
-          }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (row < len && part == 0) w.yq[pi] += acc;
-      }
-      NST_BLOCK_SYNC();
     }
 #else
     if (tid < NST_CTL_NL) {

@@ -483,12 +483,20 @@ __global__ void __launch_bounds__(256) loss_assemble_kernel(LossAssembleArgs a) 
   tv = block_sum(tv, scratch);
   ed = block_sum(ed, scratch);
   ct = block_sum(ct, scratch);
+  // per-layer Gram MSE (style_transfer_losses.py:138-144): the Gram kernels leave per-block sums of (G - T)^2
+  __shared__ float s_style[5];
+  for (int l = 0; l < a.num_style; ++l) {
+    double sq = 0.0;
+    for (int i = threadIdx.x; i < a.style_fin_n[l]; i += 256) sq += static_cast<double>(a.style_fin[l][i]);
+    sq = block_sum(sq, scratch);
+    if (threadIdx.x == 0) s_style[l] = static_cast<float>(sq * static_cast<double>(a.style_inv_cc[l]));
+  }
   if (threadIdx.x != 0) return;
   // run_style_transfer.py:115-139: each term is formed in fp32, weighted, then summed s + c + tv + e
   float style = 0.f;
   for (int l = 0; l < a.num_style; ++l) {
-    style += a.style_layer_loss[l];
-    a.out[5 + l] = a.style_layer_loss[l];
+    style += s_style[l];
+    a.out[5 + l] = s_style[l];
   }
   if (a.num_style > 0) style /= static_cast<float>(a.num_style);
   const float content = static_cast<float>(ct * a.content_norm);

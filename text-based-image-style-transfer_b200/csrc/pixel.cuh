@@ -53,7 +53,10 @@ struct LossAssembleArgs {
   int n_edge;
   const double* content_part;
   int n_content;
-  const float* style_layer_loss;  // [num_style]
+  // per style layer: per-block sums of (G - T)^2 written by the Gram kernels (gram.cu); MSE_l = sum / C_l^2
+  const float* style_fin[5];
+  int style_fin_n[5];
+  float style_inv_cc[5];
   int num_style;
   float w_style, w_content, w_tv, w_edge;
   double tv_norm;       // 1 / (3 H W)
