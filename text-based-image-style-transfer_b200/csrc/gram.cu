@@ -121,7 +121,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   tc_fence_after();
   // programmatic dependent launch: everything above touched only on-chip state; the taps come from the previous launch
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // A launch that has the GPU to itself lets its dependent start scheduling right away.  A launch that runs beside the
+  // convolution chain (max_ctas > 0, side stream) must not: its dependent is the finalize kernel, whose thousands of small
+  // blocks would sit in griddepcontrol.wait on every SM for as long as this kernel runs - and a convolution CTA needs a whole
+  // SM's registers, so the chain's next layer could not be scheduled (measured: conv4_4 100 us instead of 18).  There the
+  // dependent is released at the end.
+  if (p.max_ctas == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -290,6 +295,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (p.max_ctas != 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, G_TMEM_COLS);

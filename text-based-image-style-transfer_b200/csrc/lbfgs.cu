@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   }
   __syncthreads();
   // cross-warp sums in a fixed order -> per-block partials
-  float* out = b.part + static_cast<size_t>(blockIdx.x) * LB_PART_STRIDE;
+  // per-block partials, output-major: part[o][block] - the controller sums one output with coalesced loads
+  float* out = b.part + blockIdx.x;
+  const size_t ostride = static_cast<size_t>(b.nblocks);
   for (int idx = threadIdx.x; idx < len * NST_LBFGS_NDOT; idx += LB_THREADS) {
     const int i = idx / NST_LBFGS_NDOT, q = idx - NST_LBFGS_NDOT * i;
     int p = head + i;
@@ -216,14 +218,14 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < LB_THREADS / 32; ++w) acc += wpart[w][p][q];
-    out[p * NST_LBFGS_NDOT + q] = acc;
+    out[static_cast<size_t>(p * NST_LBFGS_NDOT + q) * ostride] = acc;
   }
   if (threadIdx.x < NST_LBFGS_NSCAL) {
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < LB_THREADS / 32; ++w)
       acc = threadIdx.x == 6 ? fmaxf(acc, wscal[w][threadIdx.x]) : acc + wscal[w][threadIdx.x];
-    out[NST_LBFGS_SLOTS * NST_LBFGS_NDOT + threadIdx.x] = acc;
+    out[static_cast<size_t>(NST_LBFGS_SLOTS * NST_LBFGS_NDOT + threadIdx.x) * ostride] = acc;
   }
 }
 
@@ -265,36 +267,34 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // Reduction of pass 1's per-block partials, folded in (r01: a kernel of its own, 8 us + a launch boundary on the critical
-  // path of every evaluation): thread o sums output o over the blocks in block order (fixed order -> deterministic), fp64;
-  // consecutive threads read consecutive floats, sixteen independent loads in flight per thread.  It overlaps the bulk copy.
+  // path of every evaluation): one warp per output, the lanes stride over the blocks (coalesced: the partials are stored
+  // output-major), fp64, fixed order (lane-strided sums, then a shuffle tree) -> deterministic.  Overlaps the bulk copy.
   if (b.ctl->stop == NST_RUN) {
     const int hist_len = b.ctl->hist_len, hist_head = b.ctl->hist_head;
-    for (int o = threadIdx.x; o < LB_PART_STRIDE; o += LB_CTL_THREADS) {
+    const int lane = threadIdx.x & 31;
+    for (int o = threadIdx.x >> 5; o < LB_PART_STRIDE; o += LB_CTL_THREADS / 32) {
       const bool is_scal = o >= NST_LBFGS_SLOTS * NST_LBFGS_NDOT;
-      bool live = true;
       if (!is_scal) {
         int rel = o / NST_LBFGS_NDOT - hist_head;   // slots that hold no stored pair are skipped
         if (rel < 0) rel += NST_LBFGS_SLOTS;
-        live = rel < hist_len;
+        if (rel >= hist_len) continue;
       }
-      if (!live) continue;
       const bool is_max = o == NST_LBFGS_SLOTS * NST_LBFGS_NDOT + 6;
-      const float* src = b.part + o;
+      const float* src = b.part + static_cast<size_t>(o) * b.nblocks;
       double acc = 0.0;
-      int blk = 0;
-      for (; blk + 16 <= b.nblocks; blk += 16) {
-        float v[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + static_cast<size_t>(blk + u) * LB_PART_STRIDE);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) acc = is_max ? fmax(acc, static_cast<double>(v[u])) : acc + static_cast<double>(v[u]);
-      }
-      for (; blk < b.nblocks; ++blk) {
-        const double val = static_cast<double>(__ldcg(src + static_cast<size_t>(blk) * LB_PART_STRIDE));
+      for (int blk = lane; blk < b.nblocks; blk += 32) {
+        const double val = static_cast<double>(__ldcg(src + blk));
         acc = is_max ? fmax(acc, val) : acc + val;
       }
-      if (is_scal) s_scal[o - NST_LBFGS_SLOTS * NST_LBFGS_NDOT] = acc;
-      else s_dots[o] = acc;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, acc, sh);
+        acc = is_max ? fmax(acc, other) : acc + other;
+      }
+      if (lane == 0) {
+        if (is_scal) s_scal[o - NST_LBFGS_SLOTS * NST_LBFGS_NDOT] = acc;
+        else s_dots[o] = acc;
+      }
     }
   }
   __syncthreads();

@@ -27,7 +27,7 @@ struct LbfgsBuffers {
   // (~1 MB) instead of touching 2 x 101 vectors that are megabytes apart: the 0.64 GB history otherwise thrashes the
   // TLB once more than ~60 pairs are stored (measured: pass 1 took 381 us at m = 100 against 75 us at m = 57).
   float* hist;      // s = torch old_stps, y = torch old_dirs
-  float* part;      // [nblocks][LB_PART_STRIDE] pass-1 per-block partial dots
+  float* part;      // [LB_PART_STRIDE][nblocks] pass-1 per-block partial dots, output-major
   float* td_part;   // [nblocks] pass-2 per-block max|t d|
   double* R;        // [SLOTS][SLOTS] s_i . y_j (upper triangle in age order)
   double* YY;       // [SLOTS][SLOTS] y_i . y_j

@@ -246,16 +246,19 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     // depend on the chain, so their shared-memory loads are issued ahead of it (the loop is unrolled).  r01 ran the chain in
     // 32-row blocks with a block-wide update and two __syncthreads() per block: 9.8 us for 100 pairs; this form is bound by
     // ~50 cycles per step.
+    // The chain itself is one shuffle and one multiply-add per step: the rows carry z_i = ro_i (s_i . q) instead of s_i . q, so
+    // al_k is the owner's z_k as it stands, and the update z_i -= al_k (ro_i R_ik) takes its factor ro_i R_ik from a product
+    // that does not depend on the chain.  (fp64 latency is what bounds this loop: ~50 cycles per dependent operation.)
     if (tid < 32) {
       const int lane = tid;
-      double cv[4], rov[4];
+      double zv[4], rov[4];
       int prow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = lane + 32 * j;
         prow[j] = nst_ctl_slot(head, i < len ? i : 0);
-        cv[j] = i < len ? w.c[prow[j]] : 0.0;
         rov[j] = i < len ? w.ro[prow[j]] : 0.0;
+        zv[j] = i < len ? rov[j] * w.c[prow[j]] : 0.0;
       }
 #pragma unroll 4
       for (int k = len - 1; k >= 0; --k) {
@@ -263,12 +266,12 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         const int jk = k >> 5, lk = k & 31;
         double r4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r4[j] = w.R[prow[j] * TOT + pk];
-        const double mine = jk == 0 ? rov[0] * cv[0] : (jk == 1 ? rov[1] * cv[1] : (jk == 2 ? rov[2] * cv[2] : rov[3] * cv[3]));
+        for (int j = 0; j < 4; ++j) r4[j] = rov[j] * w.R[prow[j] * TOT + pk];
+        const double mine = jk == 0 ? zv[0] : (jk == 1 ? zv[1] : (jk == 2 ? zv[2] : zv[3]));
         const double al = __shfl_sync(0xffffffffu, mine, lk);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (lane + 32 * j < k) cv[j] -= al * r4[j];
+          if (lane + 32 * j < k) zv[j] -= al * r4[j];
         if (lane == lk) w.al[pk] = al;
       }
     }
@@ -304,17 +307,17 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
 #if defined(__CUDA_ARCH__)
     // device: the same single-warp form, forward
+    // rows carry t_i = al_i - ro_i (y_i . r): c_k is the owner's t_k, the update is t_i -= c_k (ro_i R_ki)
     if (tid < 32) {
       const int lane = tid;
-      double yv[4], rov[4], alv[4];
+      double tv[4], rov[4];
       int prow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = lane + 32 * j;
         prow[j] = nst_ctl_slot(head, i < len ? i : 0);
-        yv[j] = i < len ? w.yq[prow[j]] : 0.0;
         rov[j] = i < len ? w.ro[prow[j]] : 0.0;
-        alv[j] = i < len ? w.al[prow[j]] : 0.0;
+        tv[j] = i < len ? w.al[prow[j]] - rov[j] * w.yq[prow[j]] : 0.0;
       }
 #pragma unroll 4
       for (int k = 0; k < len; ++k) {
@@ -322,13 +325,12 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         const int jk = k >> 5, lk = k & 31;
         double r4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r4[j] = w.R[pk * TOT + prow[j]];
-        const double mine = jk == 0 ? alv[0] - rov[0] * yv[0]
-                                    : (jk == 1 ? alv[1] - rov[1] * yv[1] : (jk == 2 ? alv[2] - rov[2] * yv[2] : alv[3] - rov[3] * yv[3]));
+        for (int j = 0; j < 4; ++j) r4[j] = rov[j] * w.R[pk * TOT + prow[j]];
+        const double mine = jk == 0 ? tv[0] : (jk == 1 ? tv[1] : (jk == 2 ? tv[2] : tv[3]));
         const double ck = __shfl_sync(0xffffffffu, mine, lk);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (lane + 32 * j > k) yv[j] += ck * r4[j];
+          if (lane + 32 * j > k) tv[j] -= ck * r4[j];
         if (lane == lk) w.c[pk] = ck;
       }
     }
