@@ -191,6 +191,8 @@ struct nst_plan {
   GramParams gram_deep;     // the style layer on the deepest conv, if any (critical path)
   float* gram_ws = nullptr;
   cudaStream_t side = nullptr;
+  cudaStream_t side2 = nullptr;  // the shallow layers' Gram launch when it runs on the idle SMs: ~100 us long, so the short side work
+                                 // (content loss and its seed, loss assembly) must not queue behind it
   cudaEvent_t ev[8] = {};
   // content
   int n_content = 0;
@@ -251,6 +253,7 @@ extern "C" void nst_plan_destroy(nst_plan* p) {
   if (!p) return;
   drop_graph(p);
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->side2) cudaStreamDestroy(p->side2);
   for (int k = 0; k < 8; ++k)
     if (p->ev[k]) cudaEventDestroy(p->ev[k]);
   for (void* a : p->allocs) cudaFree(a);
@@ -269,20 +272,8 @@ static int content_index(const nst_plan* p, int conv) {
   return -1;
 }
 
-// workspace + rendezvous words of a split-K layer (conv_tc.cuh)
-static int alloc_split(nst_plan* p, ConvParams& c) {
-  if (c.splits <= 1) {
-    c.splits = 1;
-    return NST_OK;
-  }
-  CKI(plan_alloc_t(p, &c.split_ws, static_cast<size_t>(c.num_tiles) * 128 * c.block_n));
-  CKI(plan_alloc_t(p, &c.split_sync, static_cast<size_t>(2) * c.num_tiles, true));
-  return NST_OK;
-}
-
 static int build_conv_params(nst_plan* p) {
   const nst_net* net = p->net;
-  const bool no_split = getenv("NST_NO_SPLIT_K") != nullptr;   // measurement switch: every layer as one work item per tile
   // epilogue outputs through shared memory + TMA stores (conv_epilogue.cuh); NST_DIRECT_STORES=1 keeps the per-thread stores
   const bool tma_out = getenv("NST_DIRECT_STORES") == nullptr;
   {
@@ -322,7 +313,6 @@ static int build_conv_params(nst_plan* p) {
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
     f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
-    f.splits = no_split ? 1 : conv_pick_splits(kCout[i], H, W, kCin[i], 9, g_num_sms, &f.block_n);
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
@@ -331,7 +321,6 @@ static int build_conv_params(nst_plan* p) {
     f.out_route = p->route[i];
     f.pool = pooled ? 1 : 0;
     conv_finalize_params(f, CONV_FWD);
-    CKI(alloc_split(p, f));
     if (tma_out) {
       if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out %d)", i);
       if (!pooled && f.out_act && make_tmap_out(&f.tmO1, f.out_act, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (act out %d)", i);
@@ -348,13 +337,6 @@ static int build_conv_params(nst_plan* p) {
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
     d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
-    {
-      // a data gradient that will carry a folded Gram backward (second accumulator, see below) is not split
-      const int j = i - 1;
-      const bool fold_candidate = getenv("NST_NO_SEED_FOLD") == nullptr && style_index(p, j) >= 0 && !kPoolAfter[j] &&
-                                  content_index(p, j) < 0 && j != p->n_layers - 1;
-      d.splits = (no_split || fold_candidate) ? 1 : conv_pick_splits(kCin[i], H, W, kCout[i], 9, g_num_sms, &d.block_n);
-    }
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
@@ -371,7 +353,6 @@ static int build_conv_params(nst_plan* p) {
       d.addend = p->gadd[i - 1];
     }
     conv_finalize_params(d, CONV_DGRAD);
-    CKI(alloc_split(p, d));
     if (tma_out) {
       const int rc = prev_pooled ? make_tmap_out(&d.tmO0, d.out_grad, d.Hup, d.Wup, kCin[i], 16, 2 * CONV_TILE_W, 8)
                                  : make_tmap_out(&d.tmO0, d.out_grad, H, W, kCin[i], 32, CONV_TILE_W, 4);
@@ -434,7 +415,7 @@ static int build_conv_params(nst_plan* p) {
       const int i = j + 1;
       if (j == p->n_layers - 1 || i >= p->n_layers || kPoolAfter[j] || content_index(p, j) >= 0) continue;
       ConvParams& d = p->dgrad[i];
-      if (d.block_n > 128 || d.route != nullptr || d.splits > 1) continue;
+      if (d.block_n > 128 || d.route != nullptr) continue;
       const int C = kCout[j];
       if (make_tmap_act(&d.tmA2, p->tap[j], d.H, d.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d, folded)", j);
       if (make_tmap_wgt(&d.tmB2, p->dh[l], 1, C, C, d.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
@@ -475,10 +456,7 @@ static int build_gram_params(nst_plan* p) {
   return NST_OK;
 }
 
-static int conv_grid(const ConvParams& c) {
-  const int items = c.num_tiles * (c.splits > 1 ? c.splits : 1);
-  return items < g_num_sms ? items : g_num_sms;
-}
+static int conv_grid(const ConvParams& c) { return c.num_tiles < g_num_sms ? c.num_tiles : g_num_sms; }
 
 // Plans the shallow style layers' Gram launch for the SMs that stay idle beside the deeper convolutions (nst_plan).
 static int build_gram_narrow(nst_plan* p) {
@@ -661,6 +639,7 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     cudaError_t e = cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_least);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->side2, cudaStreamNonBlocking, prio_least);
     for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
       nst_plan_destroy(p);
@@ -669,6 +648,8 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     if (getenv("NST_NO_SIDE_STREAM") != nullptr) {
       cudaStreamDestroy(p->side);
       p->side = nullptr;
+      if (p->side2) cudaStreamDestroy(p->side2);
+      p->side2 = nullptr;
     }
   }
   // ---- optimizer
@@ -683,6 +664,8 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     PA(plan_alloc_t(p, &b.hist, lbfgs_hist_floats(b), true));
     PA(plan_alloc_t(p, &b.part, static_cast<size_t>(b.nblocks) * LB_PART_STRIDE, true));
     PA(plan_alloc_t(p, &b.td_part, b.nblocks, true));
+    PA(plan_alloc_t(p, &b.dots, NST_LBFGS_SLOTS * NST_LBFGS_NDOT, true));
+    PA(plan_alloc_t(p, &b.scal, NST_LBFGS_NSCAL, true));
     PA(plan_alloc_t(p, &b.R, NST_CTL_MAT_DOUBLES, true));
     PA(plan_alloc_t(p, &b.YY, NST_CTL_MAT_DOUBLES, true));
     PA(plan_alloc_t(p, &b.ctl, 1, true));
@@ -979,7 +962,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   TM(NST_K_START, -1);
   const bool conc = tm == nullptr && p->side != nullptr && use_vgg;
   cudaStream_t s2 = conc ? p->side : s;
-  enum { EV_FORK = 0, EV_TAPS = 1, EV_CONTENT_IN = 2, EV_CONTENT = 3, EV_SEEDS = 4, EV_GRAM = 5, EV_JOIN = 6 };
+  enum { EV_FORK = 0, EV_TAPS = 1, EV_CONTENT_IN = 2, EV_CONTENT = 3, EV_SEEDS = 4, EV_GRAM = 5, EV_JOIN = 6, EV_GRAM_SHALLOW = 7 };
   // record on `from`, make `to` wait
   auto edge = [&](int ev, cudaStream_t from, cudaStream_t to) -> cudaError_t {
     if (!conc) return cudaSuccess;
@@ -1012,8 +995,22 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
 
   // beside the convolution chain the shallow layers' Gram launch keeps to the idle SMs; alone (timing, single stream) it
   // takes the whole GPU
-  const bool narrow = conc && p->gram_shallow_narrow.num_layers > 0;
+  const bool narrow = conc && p->gram_shallow_narrow.num_layers > 0 && p->side2 != nullptr;
   const GramParams& gram_shallow = narrow ? p->gram_shallow_narrow : p->gram_shallow;
+  cudaStream_t s3 = narrow ? p->side2 : s2;   // stream of the shallow layers' Gram launch
+  // its results (fp16 operands, alpha, per-block sums) are consumed on s2 (seed launches, loss assembly) and, through
+  // EV_SEEDS, on the main stream
+  auto gram_shallow_launch = [&]() -> cudaError_t {
+    cudaError_t e = cudaSuccess;
+    if (conc) {
+      e = cudaEventRecord(p->ev[EV_TAPS], s);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s3, p->ev[EV_TAPS], 0);
+    }
+    if (e == cudaSuccess) e = launch_gram(gram_shallow, s3);
+    if (e == cudaSuccess && narrow) e = cudaEventRecord(p->ev[EV_GRAM_SHALLOW], s3);
+    return e;
+  };
+  bool shallow_joined = !narrow;   // s2 has waited for the shallow Gram launch
   auto content_launch = [&](int l, int accumulate, cudaStream_t st) -> cudaError_t {
     const int i = p->content_conv[l];
     const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
@@ -1037,7 +1034,6 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     TB(NST_K_CONV1_FWD);
     CK(conv1_forward(p, x, s));
     TM(NST_K_CONV1_FWD, 0);
-    if (max_shallow == 0) CK(edge(EV_TAPS, s, s2));
     if (max_content == 0) CK(edge(EV_CONTENT_IN, s, s2));
     for (int i = 1; i < p->n_layers; ++i) {
       TB(NST_K_CONV_FWD);
@@ -1045,9 +1041,8 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       TM(NST_K_CONV_FWD, i);
       if (i == at_shallow) {
         // ---- side: Gram, style MSE and backward operand of the shallower style layers
-        CK(edge(EV_TAPS, s, s2));
         TB(NST_K_GRAM);
-        CK(launch_gram(gram_shallow, s2));
+        CK(gram_shallow_launch());
         nl += gram_launches(gram_shallow);
         TM(NST_K_GRAM, 0);
       }
@@ -1066,7 +1061,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     nl += p->n_layers;
     if (max_shallow == 0) {
       TB(NST_K_GRAM);
-      CK(launch_gram(gram_shallow, s2));
+      CK(gram_shallow_launch());
       nl += gram_launches(gram_shallow);
       TM(NST_K_GRAM, 0);
     }
@@ -1086,9 +1081,8 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       TM(NST_K_GRAM, last);
     }
     if (shallow_after_deep) {
-      CK(edge(EV_TAPS, s, s2));
       TB(NST_K_GRAM);
-      CK(launch_gram(gram_shallow, s2));
+      CK(gram_shallow_launch());
       nl += gram_launches(gram_shallow);
       TM(NST_K_GRAM, 0);
     }
@@ -1102,6 +1096,10 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   }
   // ---- side: Gram-backward seeds of the shallower style layers
   if (grad != nullptr && use_vgg) {
+    if (!shallow_joined && n_shallow > 0) {
+      CK(cudaStreamWaitEvent(s2, p->ev[EV_GRAM_SHALLOW], 0));
+      shallow_joined = true;
+    }
     // shallowest (largest, bandwidth-bound) first: it then overlaps the latency-bound Gram chain of the deepest layer on
     // the main stream instead of the first data gradients; all seeds are awaited together before conv4_2's data gradient
     for (int l = 0; l < n_shallow; ++l) {
@@ -1122,6 +1120,10 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     if (conc) CK(cudaEventRecord(p->ev[EV_SEEDS], s2));
   }
   // ---- side: loss assembly (needs the deepest layer's Gram MSE / content partials from main)
+  if (!shallow_joined && n_shallow > 0) {
+    CK(cudaStreamWaitEvent(s2, p->ev[EV_GRAM_SHALLOW], 0));
+    shallow_joined = true;
+  }
   CK(edge(EV_GRAM, s, s2));
   LossAssembleArgs a;
   memset(&a, 0, sizeof(a));
@@ -1585,6 +1587,9 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
       TB(NST_K_LBFGS_PASS1);
       CK(launch_lbfgs_pass1(b, s));
       TM(NST_K_LBFGS_PASS1, -1);
+      TB(NST_K_LBFGS_REDUCE);
+      CK(launch_lbfgs_reduce(b, s));
+      TM(NST_K_LBFGS_REDUCE, -1);
       TB(NST_K_LBFGS_CONTROL);
       CK(launch_lbfgs_control(b, mode, s));
       TM(NST_K_LBFGS_CONTROL, -1);
@@ -1592,7 +1597,7 @@ static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_eval
       CK(launch_lbfgs_pass2(b, s));
       TM(NST_K_LBFGS_PASS2, -1);
     }
-    nl += 3;
+    nl += 4;
     if (k != max_iter) {
 #ifdef NST_INSTRUMENT
       if (p->timeline_on) timeline_arm(p, evals == 10);  // the spans of ONE evaluation in the middle of the step

@@ -119,9 +119,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   } while (0)
   NST_STAMP(0, threadIdx.x == 0);
   if (NST_TL_PTR(p) != nullptr && threadIdx.x == 0) atomicMin(&NST_TL_PTR(p)[0], globaltimer_ns());
-  // Programmatic dependent launch: let the next kernel in the stream get scheduled as soon as CTAs of this grid retire
-  // (its CTAs run their own setup, then block in griddepcontrol.wait until this grid has completed and flushed).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Programmatic dependent launch: the next kernel in the stream may be scheduled once every CTA of this grid has said so
+  // (its CTAs run their own setup, then block in griddepcontrol.wait until this grid has completed and flushed).  A CTA says
+  // so when its MMA thread has issued the main loop of its LAST tile - not at kernel entry: a dependent CTA needs a whole SM
+  // (shared memory, registers), so released early it could only land on SMs this grid leaves idle (20 of 148 for the
+  // 128-tile layers at 512^2) and would sit there in griddepcontrol.wait for the whole launch, keeping the side stream's
+  // Gram work off exactly the SMs it is planned for (gram.cu, GramParams::max_ctas).
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -161,8 +164,6 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   const uint32_t a_tx = p.taps == 9 ? HALO_TX_BYTES : FLAT_TX_BYTES;
   const int sp_tiles = p.tiles_w * p.tiles_h;
   const int tps = p.taps == 9 ? Cfg::TPS : 1;              // taps per weight stage (the weight tensor map's box depth)
-  const int splits = p.splits > 1 ? p.splits : 1;          // split-K over the slices (conv_tc.cuh)
-  const int num_items = p.num_tiles * splits;
   // A layer with 64 input channels has ONE 64-channel slice: its whole weight set (nine taps) fits the weight ring.  It
   // is then loaded once per CTA and stays resident - re-streaming it for every tile (72 KB next to a 23 KB patch at
   // N = 64) made the 64-channel layers L2-bandwidth bound (148 SMs x ~96 KB per microsecond).  All tiles of a launch
@@ -172,23 +173,20 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   // dbg_flags bit 2 (timing experiment, wrong results): never re-stream the weights - how fast is the main loop without
   // the TMA writes of the B operand competing with the tensor core's shared-memory reads?
   const bool b_resident = p.taps == 9 && 9 / Cfg::TPS <= Cfg::B_STAGES && !seed &&
-                          ((k_slices == 1 && p.tiles_n == 1 && splits == 1) || NST_DBG_FLAG(p, 4));
+                          ((k_slices == 1 && p.tiles_n == 1) || NST_DBG_FLAG(p, 4));
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item / splits;
-        const int split = item - tile * splits;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile / sp_tiles;
         const int sp = tile - nt * sp_tiles;
         const int th = sp / p.tiles_w;
         const int tw = sp - th * p.tiles_w;
         const int h0 = th * TILE_H, w0 = tw * TILE_W, n0 = nt * BLOCK_N;
-        const int ks_begin = split * k_slices / splits, ks_end = (split + 1) * k_slices / splits;
-        for (int ks = ks_begin; ks < ks_end; ++ks) {
+        for (int ks = 0; ks < k_slices; ++ks) {
           NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
           mbar_arrive_expect_tx(&afull_bar[as], a_tx);
           tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA, &afull_bar[as], ks * BLOCK_K, w0 - pad, h0 - pad);
@@ -196,7 +194,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             as = 0;
             aphase ^= 1u;
           }
-          if (b_resident && (item != static_cast<int>(blockIdx.x) || ks > 0)) continue;
+          if (b_resident && (tile != static_cast<int>(blockIdx.x) || ks > 0)) continue;
           for (int tap = 0; tap < p.taps; tap += tps) {
             NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
             mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
@@ -247,16 +245,14 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     const uint32_t b_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, 1024) >> 32);
     const uint32_t lbo_lo = static_cast<uint32_t>(umma_desc_sw128(0, 16, 0) & 0xffffffffu);  // LBO field, address 0
     const bool conv3x3 = p.taps == 9;
-    for (int tile = blockIdx.x; tile < num_items; tile += gridDim.x) {   // `tile` = work item (tile x split) in this role
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       NST_WAIT(wacc2, mbar_wait(&tempty_bar[ts], tphase ^ 1u));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
       uint32_t accumulate = 0;
-      const int split = tile % splits;
-      const int ks_begin = split * k_slices / splits, ks_end = (split + 1) * k_slices / splits;
-      for (int ks = ks_begin; ks < ks_end; ++ks) {
+      for (int ks = 0; ks < k_slices; ++ks) {
         NST_WAIT(wacc0, mbar_wait(&afull_bar[as], aphase));
-        NST_STAMP(2, ks == ks_begin && tile == blockIdx.x);
+        NST_STAMP(2, ks == 0 && tile == blockIdx.x);
         const uint32_t a_lo0 = lbo_lo | (smem_u32(sA + as * HALO_STAGE_BYTES) >> 4);
         if (conv3x3) {
           // nine taps = nine row shifts of the patch: (dr * 10 + ds) rows of 128 B = (dr * 10 + ds) * 8 descriptor units
@@ -352,6 +348,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         tphase ^= 1u;
       }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (dbg) {
       NST_DBG_PTR(p)[8] = wacc0;
       NST_DBG_PTR(p)[9] = wacc1;
@@ -416,11 +413,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
     };
     if constexpr (XT) {
-      if (static_cast<int>(blockIdx.x) < num_items) request(blockIdx.x / splits, aux, gp);
+      if (static_cast<int>(blockIdx.x) < p.num_tiles) request(blockIdx.x, aux, gp);
     }
-    int* const s_role = reinterpret_cast<int*>(tmem_slot + 2);   // split-K: 0 = first arrival of the tile, 1 = second
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item / splits;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int h, w, n0;
       bool valid;
       coords(tile, h, w, n0, valid);
@@ -431,73 +426,15 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
       }
       if constexpr (XT) {
-        if (item + static_cast<int>(gridDim.x) < num_items) request((item + gridDim.x) / splits, aux_x, gp_x);
+        if (tile + static_cast<int>(gridDim.x) < p.num_tiles) request(tile + gridDim.x, aux_x, gp_x);
       } else if constexpr (MODE == CONV_DGRAD) {
         request(tile, aux, gp);
       }
       NST_WAIT(wacc0, mbar_wait(&tfull_bar[ts], tphase));
       tc_fence_after();
-      NST_STAMP(4, threadIdx.x == 128 && item == blockIdx.x);
+      NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * BLOCK_N + col0);
-      // ---- split-K rendezvous (conv_tc.cuh): who is first at this tile?
-      int role = 2;   // 2 = the tile is not split
-      float* ws_row = nullptr;
-      if constexpr (MODE == CONV_FWD || MODE == CONV_DGRAD) {
-        if (splits > 1) {
-          if (et == 0) *s_role = atomicAdd(p.split_sync + 2 * tile, 1);
-          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
-          role = *s_role == 0 ? 0 : 1;
-          ws_row = p.split_ws + (static_cast<size_t>(tile) * BLOCK_M + t) * BLOCK_N + col0;
-          if (role == 0) {
-            // first arrival: the raw fp32 partial goes to the workspace, the partner finishes the tile
-#pragma unroll 1
-            for (int c = 0; c < COLS / 32; ++c) {
-              uint32_t r[32];
-              tmem_ld32(taddr + c * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ws_row + c * 32 + 8 * j), "r"(r[8 * j]),
-                             "r"(r[8 * j + 1]), "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]),
-                             "r"(r[8 * j + 6]), "r"(r[8 * j + 7])
-                             : "memory");
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
-            if (et == 0) asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p.split_sync + 2 * tile + 1), "r"(1) : "memory");
-          } else {
-            // second arrival: wait for the partner's partial (it is being written right now: the partner took the counter
-            // before us, so it is resident and past its main loop)
-            if (et == 0) {
-              int f = 0;
-              const long long t0 = clock64();
-              do {
-                asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(f) : "l"(p.split_sync + 2 * tile + 1) : "memory");
-                if (f == 0 && clock64() - t0 > 4000000000ll) __trap();
-              } while (f == 0);
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
-          }
-        }
-      }
-      auto add_partial = [&](float* v_, int ncol, int coff) {
-        // second arrival: v += partner's partial (L2-coherent loads: the lines were written by another SM moments ago)
-#pragma unroll
-        for (int j = 0; j < ncol; j += 8) {
-          uint4 a, b;
-          ld_global_cg_256(ws_row + coff + j, a, b);
-          v_[j + 0] += __uint_as_float(a.x);
-          v_[j + 1] += __uint_as_float(a.y);
-          v_[j + 2] += __uint_as_float(a.z);
-          v_[j + 3] += __uint_as_float(a.w);
-          v_[j + 4] += __uint_as_float(b.x);
-          v_[j + 5] += __uint_as_float(b.y);
-          v_[j + 6] += __uint_as_float(b.z);
-          v_[j + 7] += __uint_as_float(b.w);
-        }
-      };
-      if (role != 0) {
       if constexpr (MODE == CONV_DGRAD_PIX) {
         // conv1_1: 3 of the 16 accumulator columns are image channels
         uint32_t r[16];
@@ -522,7 +459,6 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             float v[DG_CH];
 #pragma unroll
             for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-            if (role == 1) add_partial(v, DG_CH, c * DG_CH);
             if (seed) {
               uint32_t r2[DG_CH];
               tmem_ld16(taddr + 2 * BLOCK_N + c * DG_CH, r2);
@@ -545,7 +481,6 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
             float v[DG_CH];
 #pragma unroll
             for (int j = 0; j < DG_CH; ++j) v[j] = __uint_as_float(r[j]);
-            if (role == 1) add_partial(v, DG_CH, c * DG_CH);
             if (seed) {
               uint32_t r2[DG_CH];
               tmem_ld16(taddr + 2 * BLOCK_N + c * DG_CH, r2);
@@ -569,19 +504,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (role == 1) add_partial(v, 32, c * 32);
           const int n = n0 + col0 + c * 32;
           if constexpr (MODE == CONV_FWD) epilogue_fwd(p, v, h, w, n, valid, lane, sbias + ts * BLOCK_N + col0 + c * 32, st);
           if constexpr (MODE == CONV_SCALE) epilogue_scale(p, v, h, w, n, valid, alpha, st);
-        }
-      }
-      }  // role != 0
-      if (role == 1) {
-        // every thread has read its part of the partner's partial: leave the tile's counter and flag at 0 for the next launch
-        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
-        if (et == 0) {
-          p.split_sync[2 * tile] = 0;
-          p.split_sync[2 * tile + 1] = 0;
         }
       }
       if constexpr (XT) {
@@ -592,7 +517,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
       tc_fence_before();
       __syncwarp();
-      NST_STAMP(5, threadIdx.x == 128 && item == blockIdx.x);
+      NST_STAMP(5, threadIdx.x == 128 && tile == blockIdx.x);
       if (lane == 0) mbar_arrive(&tempty_bar[ts]);
       if (++ts == 2) {
         ts = 0;
@@ -705,24 +630,6 @@ int conv_block_n(int N, int H, int W, int k_total, int num_sms) {
   return best;
 }
 
-// Split-K policy (conv_tc.cuh): returns 2 and may widen *block_n when the layer has at most half as many tiles as SMs and
-// a long reduction; 1 otherwise.  64-channel tiles of a layer that could use 128 are widened first: two CTAs per 128-wide
-// tile run half the reduction each at the 128-wide tile's better operand reuse (conv4_1's data gradient at 512^2:
-// 128 tiles x 288 MMAs of N = 64 -> 128 work items x 144 MMAs of N = 128).
-int conv_pick_splits(int N, int H, int W, int K, int taps, int num_sms, int* block_n) {
-  const int sp = ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
-  const int k_slices = K / BLOCK_K;
-  if (taps != 9 || k_slices < 4) return 1;
-  if (num_sms < 1) num_sms = 148;
-  const int tiles = sp * (N / *block_n);
-  if (2 * tiles <= num_sms) return 2;
-  if (*block_n == 64 && N % 128 == 0 && 2 * sp * (N / 128) <= num_sms) {
-    *block_n = 128;
-    return 2;
-  }
-  return 1;
-}
-
 void conv_finalize_params(ConvParams& p, int mode) {
   const int bn = p.block_n;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
@@ -735,8 +642,7 @@ void conv_finalize_params(ConvParams& p, int mode) {
 template <int BLOCK_N, int MODE, bool TMA_OUT>
 static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
-  const int items = p.num_tiles * (p.splits > 1 ? p.splits : 1);
-  const int grid = items < num_sms ? items : num_sms;
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   static const bool pdl = getenv("NST_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -803,9 +709,6 @@ cudaError_t launch_conv_tc(const ConvParams& p, int mode, int num_sms, cudaStrea
     return launch_one<16, CONV_DGRAD_PIX>(p, num_sms, stream);
   }
   if (p.K % BLOCK_K != 0 || p.N % 64 != 0 || p.num_tiles <= 0) return cudaErrorInvalidValue;
-  if (p.splits > 1 && (p.splits != 2 || p.split_ws == nullptr || p.split_sync == nullptr || p.seed_k > 0 || mode == CONV_SCALE ||
-                       p.K / BLOCK_K < 2))
-    return cudaErrorInvalidValue;
   switch (mode) {
     case CONV_FWD: return launch_mode<CONV_FWD>(p, num_sms, stream);
     case CONV_DGRAD: return launch_mode<CONV_DGRAD>(p, num_sms, stream);

@@ -59,14 +59,6 @@ struct ConvParams {
   int block_n;     // N tile: 64, 128 or 256 (conv_block_n)
   int tiles_w, tiles_h, tiles_n, num_tiles;
   uint32_t idesc;
-  // Split-K over the 64-channel slices of the reduction (splits = 1 or 2): a layer with fewer tiles than half the SMs and a
-  // long reduction (conv5_1 at 512^2: 64 tiles x K = 4608) runs as tiles x 2 work items.  The two CTAs of a tile meet at a
-  // per-tile counter when their accumulators are complete: the first to arrive writes its fp32 partial tile to `split_ws`
-  // and raises the tile's flag, the second adds that partial to its own accumulator (a + b = b + a: the result does not
-  // depend on who came first) and runs the epilogue.  Not combined with the folded Gram backward (seed_k).
-  int splits;
-  float* split_ws;   // [num_tiles][128][block_n] fp32
-  int* split_sync;   // [num_tiles][2]: arrival counter, "partial written" flag; both left at 0 by the second arrival
   // ---- CONV_FWD
   const float* bias;   // [N]
   __half* out_tap;     // [H,W,N] pre-ReLU or nullptr
@@ -108,8 +100,6 @@ int conv_taps_per_stage(int block_n, int taps);
 
 // picks the N tile for a layer of N output channels on an H x W pixel grid contracting k_total = taps * K values
 int conv_block_n(int N, int H, int W, int k_total, int num_sms);
-// split-K factor (1 or 2) for a layer; may widen *block_n from 64 to 128 (see conv_tc.cu)
-int conv_pick_splits(int N, int H, int W, int K, int taps, int num_sms, int* block_n);
 // fills tiles_* / idesc from H, W, K, N, taps and mode
 void conv_finalize_params(ConvParams& p, int mode);
 // sets the kernel attributes (opt-in shared memory) of every instantiation; call once per process

@@ -214,14 +214,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
         const float* trow = L.target + static_cast<size_t>(row_ok ? gi : 0) * L.C + bj * 128;
         float sq = 0.f;
         const float w = bi == bj ? 1.f : 2.f;   // an off-diagonal block stands for its mirror image too
+        // target row, one 32-column chunk ahead of its use: the first chunk is requested before the accumulator is waited for
+        float4 t4[8], t4n[8];
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t4n[j] = __ldg(reinterpret_cast<const float4*>(trow) + j);
+        }
         mbar_wait(&tfull_bar[ts], tphase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < L.bn / 32; ++c) {
-          float4 t4[8];
-          if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t4[j] = __ldg(reinterpret_cast<const float4*>(trow + c * 32) + j);
+          for (int j = 0; j < 8; ++j) t4[j] = t4n[j];
+          if (row_ok && c + 1 < L.bn / 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t4n[j] = __ldg(reinterpret_cast<const float4*>(trow + (c + 1) * 32) + j);
           }
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);

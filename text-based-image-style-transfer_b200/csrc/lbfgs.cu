@@ -229,6 +229,44 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_pass1_kernel(const LbfgsBuff
   }
 }
 
+// One warp per output: sums the per-block partials of pass 1 in fp64 in a fixed order (lane-strided sums, then a shuffle tree).
+// A kernel of its own on purpose: every load of a warp is independent, so the whole reduction is ONE round trip to L2 spread over
+// ~50 SMs (6 us).  Folded into the one-block controller the same 0.5 MB take tens of microseconds: right after the streaming
+// pass a load batch comes back after ~2 us, and one block needs many dependent batches (measured: 49 - 88 us for three
+// variants of the folded form, profiles/r02_lbfgs_controller_experiments.md).
+__global__ void __launch_bounds__(256) lbfgs_pass1_reduce_kernel(const LbfgsBuffers b) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const NstLbfgsCtl* ctl = b.ctl;
+  if (ctl->stop != NST_RUN) return;
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= LB_PART_STRIDE) return;
+  const bool is_scal = o >= NST_LBFGS_SLOTS * NST_LBFGS_NDOT;
+  if (!is_scal) {
+    // skip slots that hold no stored pair
+    int rel = o / NST_LBFGS_NDOT - ctl->hist_head;
+    if (rel < 0) rel += NST_LBFGS_SLOTS;
+    if (rel >= ctl->hist_len) return;
+  }
+  const bool is_max = o == NST_LBFGS_SLOTS * NST_LBFGS_NDOT + 6;
+  const float* src = b.part + static_cast<size_t>(o) * b.nblocks;   // output-major: the lanes read consecutive floats
+  double acc = 0.0;
+  for (int blk = lane; blk < b.nblocks; blk += 32) {
+    const double val = static_cast<double>(src[blk]);
+    acc = is_max ? fmax(acc, val) : acc + val;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, acc, s);
+    acc = is_max ? fmax(acc, other) : acc + other;
+  }
+  if (lane == 0) {
+    if (is_scal) b.scal[o - NST_LBFGS_SLOTS * NST_LBFGS_NDOT] = acc;
+    else b.dots[o] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const LbfgsBuffers b, int mode) {
   extern __shared__ double ctl_smem[];
   NstCtlWork w;
@@ -241,9 +279,7 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
   w.yq = w.c + NST_LBFGS_SLOTS;
   w.ro = w.yq + NST_LBFGS_SLOTS;
   w.red = w.ro + NST_LBFGS_SLOTS;
-  double* s_dots = w.red + 4;                         // [SLOTS * NDOT] dot products of pass 1, reduced below
-  double* s_scal = s_dots + NST_LBFGS_SLOTS * NST_LBFGS_NDOT;   // [NSCAL]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_scal + NST_LBFGS_NSCAL);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(w.red + 4);
 #ifdef NST_INSTRUMENT
   if (threadIdx.x == 0) b.ctl->clk[0] = clock64();
 #endif
@@ -262,45 +298,14 @@ __global__ void __launch_bounds__(LB_CTL_THREADS) lbfgs_control_kernel(const Lbf
                  "l"(b.YY), "r"(BYTES), "r"(smem_u32(bar))
                  : "memory");
   }
-  // the matrices staged above are written by this kernel only (previous iteration); the per-block partial dot products come
-  // from pass 1: wait for it here, after the 160 KB copy has been issued
+  // the matrices staged above are written by this kernel only (previous iteration); the dot products come from the
+  // reduction kernel: wait for it here, after the 160 KB copy has been issued
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // Reduction of pass 1's per-block partials, folded in (r01: a kernel of its own, 8 us + a launch boundary on the critical
-  // path of every evaluation): one warp per output, the lanes stride over the blocks (coalesced: the partials are stored
-  // output-major), fp64, fixed order (lane-strided sums, then a shuffle tree) -> deterministic.  Overlaps the bulk copy.
-  if (b.ctl->stop == NST_RUN) {
-    const int hist_len = b.ctl->hist_len, hist_head = b.ctl->hist_head;
-    const int lane = threadIdx.x & 31;
-    for (int o = threadIdx.x >> 5; o < LB_PART_STRIDE; o += LB_CTL_THREADS / 32) {
-      const bool is_scal = o >= NST_LBFGS_SLOTS * NST_LBFGS_NDOT;
-      if (!is_scal) {
-        int rel = o / NST_LBFGS_NDOT - hist_head;   // slots that hold no stored pair are skipped
-        if (rel < 0) rel += NST_LBFGS_SLOTS;
-        if (rel >= hist_len) continue;
-      }
-      const bool is_max = o == NST_LBFGS_SLOTS * NST_LBFGS_NDOT + 6;
-      const float* src = b.part + static_cast<size_t>(o) * b.nblocks;
-      double acc = 0.0;
-      for (int blk = lane; blk < b.nblocks; blk += 32) {
-        const double val = static_cast<double>(__ldcg(src + blk));
-        acc = is_max ? fmax(acc, val) : acc + val;
-      }
-#pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) {
-        const double other = __shfl_xor_sync(0xffffffffu, acc, sh);
-        acc = is_max ? fmax(acc, other) : acc + other;
-      }
-      if (lane == 0) {
-        if (is_scal) s_scal[o - NST_LBFGS_SLOTS * NST_LBFGS_NDOT] = acc;
-        else s_dots[o] = acc;
-      }
-    }
-  }
   __syncthreads();
   if (stage) mbar_wait(bar, 0);
   __syncthreads();
-  nst_lbfgs_control(b.ctl, w, b.R, b.YY, s_dots, s_scal, *b.eval_loss, b.td_part, b.nblocks, mode);
+  nst_lbfgs_control(b.ctl, w, b.R, b.YY, b.dots, b.scal, *b.eval_loss, b.td_part, b.nblocks, mode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,6 +479,10 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
 cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s) {
   return launch_pdl(lbfgs_pass1_kernel, b.nblocks, LB_THREADS, lbfgs_ring_bytes(b), s, b);
 }
+cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s) {
+  const int warps_per_blk = 8;
+  return launch_pdl(lbfgs_pass1_reduce_kernel, (LB_PART_STRIDE + warps_per_blk - 1) / warps_per_blk, 32 * warps_per_blk, 0, s, b);
+}
 cudaError_t lbfgs_init() {
   cudaError_t e = cudaFuncSetAttribute(lbfgs_control_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_CTL_SMEM);
   const int ring_max = 128 + LB_RING * LB_MAX_VEC_PER_BLOCK * 32;
@@ -490,6 +499,7 @@ cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s) {
 
 cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s) {
   cudaError_t e = launch_lbfgs_pass1(b, s);
+  if (e == cudaSuccess) e = launch_lbfgs_reduce(b, s);
   if (e == cudaSuccess) e = launch_lbfgs_control(b, mode, s);
   if (e == cudaSuccess) e = launch_lbfgs_pass2(b, s);
   return e;

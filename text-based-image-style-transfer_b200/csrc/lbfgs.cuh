@@ -12,8 +12,8 @@ static constexpr int LB_RING = 4;                                  // stored pai
 static constexpr int LB_MAX_VEC_PER_BLOCK = LB_THREADS * LB_VEC_PER_THREAD;
 static constexpr int LB_PART_STRIDE = NST_LBFGS_SLOTS * NST_LBFGS_NDOT + NST_LBFGS_NSCAL;  // floats per block in pass-1 partials
 static constexpr int LB_CTL_THREADS = 512;
-// controller: work arrays + the reduced dot products of pass 1 + one mbarrier
-static constexpr int LB_CTL_SMEM = (NST_CTL_WORK_DOUBLES + LB_PART_STRIDE + 2) * 8;
+// controller: work arrays + one mbarrier
+static constexpr int LB_CTL_SMEM = (NST_CTL_WORK_DOUBLES + 2) * 8;
 
 struct LbfgsBuffers {
   int n_pad;        // vector length, multiple of 4; elements >= n are zero everywhere
@@ -29,6 +29,8 @@ struct LbfgsBuffers {
   float* hist;      // s = torch old_stps, y = torch old_dirs
   float* part;      // [LB_PART_STRIDE][nblocks] pass-1 per-block partial dots, output-major
   float* td_part;   // [nblocks] pass-2 per-block max|t d|
+  double* dots;     // [SLOTS*NDOT] reduced
+  double* scal;     // [NSCAL] reduced
   double* R;        // [SLOTS][SLOTS] s_i . y_j (upper triangle in age order)
   double* YY;       // [SLOTS][SLOTS] y_i . y_j
   NstLbfgsCtl* ctl;
@@ -43,11 +45,12 @@ size_t lbfgs_hist_floats(const LbfgsBuffers& b);
 cudaError_t lbfgs_init();
 // clears ctl.stop at step() entry
 cudaError_t launch_lbfgs_step_begin(const LbfgsBuffers& b, cudaStream_t s);
-// the three launches of one iteration, individually (timing) ...
+// the four launches of one iteration, individually (timing) ...
 cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s);
+cudaError_t launch_lbfgs_reduce(const LbfgsBuffers& b, cudaStream_t s);
 cudaError_t launch_lbfgs_control(const LbfgsBuffers& b, int mode, cudaStream_t s);
 cudaError_t launch_lbfgs_pass2(const LbfgsBuffers& b, cudaStream_t s);
-// ... and together: pass 1 + controller (which reduces pass 1's per-block partials first) + pass 2 = one L-BFGS iteration
+// ... and together: pass 1 + reduction + controller + pass 2 = one L-BFGS iteration after an evaluation
 cudaError_t launch_lbfgs_iteration(const LbfgsBuffers& b, int mode, cudaStream_t s);
 
 }  // namespace nst

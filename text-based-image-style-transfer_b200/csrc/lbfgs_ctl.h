@@ -272,8 +272,12 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (lane + 32 * j < k) zv[j] -= al * r4[j];
-        if (lane == lk) w.al[pk] = al;
+        // row k is final now: its owner's z_k IS al_k and is not touched again (no store inside the chain - the compiler
+        // could not move the next steps' matrix loads above a store through a pointer that may alias the matrix)
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < len) w.al[prow[j]] = zv[j];
     }
 #else
     if (tid < NST_CTL_NL) {
@@ -331,8 +335,10 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (lane + 32 * j > k) tv[j] -= ck * r4[j];
-        if (lane == lk) w.c[pk] = ck;
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < len) w.c[prow[j]] = tv[j];   // row k's t_k is c_k from step k on
     }
 #else
     if (tid < NST_CTL_NL) {
