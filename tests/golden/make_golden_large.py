@@ -120,16 +120,29 @@ def finalize(case, ta, tb):
         out[k] = v
     la, lb = a["loss_trace"], b["loss_trace"]
     n = min(len(la), len(lb))
-    out["self_loss_dev"] = np.array(float(np.max(np.abs(la[:n] - lb[:n]) / np.abs(la[:n]))))
+    self_dev = np.abs(la[:n] - lb[:n]) / np.abs(la[:n])
+    out["self_loss_dev"] = np.array(float(np.max(self_dev)))
+    out["self_dev_trace"] = self_dev
+    # evaluations before the reference parts from ITSELF (two thread counts more than 1e-3 apart): only there can a run-level
+    # tolerance be asked of anybody; behind it unit-step L-BFGS has overshot and the trajectory is chaotic
+    bad = np.nonzero(self_dev > 1e-3)[0]
+    out["stable_prefix"] = np.array(int(bad[0]) if len(bad) else n)
     out["self_psnr"] = np.array(psnr(a["x_final"], b["x_final"]))
     out["self_threads"] = np.array([ta, tb])
     out["self_n_evals"] = np.array([len(la), len(lb)])
     dec = float(np.mean(np.diff(la) < 0))
     out["frac_decreasing"] = np.array(dec)
+    # keep the fixtures small: intermediate iterates only up to 512^2; the uint8 image only up to 512^2 (it is the truncated
+    # float image); no images at all where the reference is not stable against itself (nothing can be compared with them)
+    big = a["content_u8"].shape[0] * a["content_u8"].shape[1] > 512 * 512
+    unstable = int(out["stable_prefix"]) < n
+    for k in list(out):
+        if (k.startswith("x_eval") and (big or unstable)) or (k == "final_u8" and (big or unstable)) or (k == "x_final" and unstable):
+            del out[k]
     path = os.path.join(HERE, "large_%s.npz" % case)
     np.savez_compressed(path, **out)
     print(case, "evals", len(la), "loss", la[0], "->", la[-1], "decreasing", dec, "self-noise: loss dev",
-          float(out["self_loss_dev"]), "psnr", float(out["self_psnr"]), "dB;", os.path.getsize(path), "bytes")
+          float(out["self_loss_dev"]), "psnr", float(out["self_psnr"]), "dB; stable prefix", int(out["stable_prefix"]), "evaluations;", os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

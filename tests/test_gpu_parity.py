@@ -651,7 +651,7 @@ def test_concurrent_frames_are_bit_identical_to_one_at_a_time(nst, oracle):
 
 
 # ------------------------------------------------------------------------------------------------ run-level parity at full size
-LARGE_CASES = ["nat512", "syn512", "boat512", "nat512_mix_ca", "nat1024", "nat720p"]
+LARGE_CASES = ["nat512", "syn512", "boat512", "nat512_mix_ca", "dog1024", "dog720p", "nat1024", "nat720p"]
 
 
 @pytest.mark.parametrize("name", LARGE_CASES)
@@ -677,19 +677,31 @@ def test_full_run_against_reference_golden_large(nst, rst, oracle, name):
     tr = s.trace()[:, 0].double().numpy()
     dev = np.abs(tr - ref) / np.abs(ref)
     x = s.result().cpu()
-    p = O.psnr(x, torch.from_numpy(g["x_final"].astype(np.float32)))
-    mid = {}
+    p = O.psnr(x, torch.from_numpy(g["x_final"].astype(np.float32))) if "x_final" in g.files else float("nan")
     print("\n[large golden %s] %d evals, loss %.5f -> %.5f (reference %.5f -> %.5f); max loss-curve deviation %.2e at eval %d "
           "(reference self-noise %.2e); final image %.1f dB (reference self-noise %.1f dB)"
           % (name, n, tr[0], tr[-1], ref[0], ref[-1], dev.max(), int(dev.argmax()), float(g["self_loss_dev"]), p, float(g["self_psnr"])))
-    assert dev.max() <= CURVE_TOL, (name, float(dev.max()), int(dev.argmax()))
-    assert p >= PSNR_MIN, (name, p)
     st = s.status()
     assert st.closure_calls == n and st.stop == 0
-    # drop-in form on the same inputs: PIL in, PIL out; bytes within the truncation noise of the float comparison above
-    u8 = O.to_u8(x)
-    d8 = np.abs(u8.astype(int) - g["final_u8"].astype(int))
-    assert d8.mean() < 1.0, (name, float(d8.mean()))
+    stable = int(g["stable_prefix"]) if "stable_prefix" in g.files else len(ref)
+    if stable == len(ref):
+        # the reference agrees with itself over the whole run: north_star's run-level tolerances apply to all of it
+        assert dev.max() <= CURVE_TOL, (name, float(dev.max()), int(dev.argmax()))
+        assert p >= PSNR_MIN, (name, p)
+        if "final_u8" in g.files:
+            d8 = np.abs(O.to_u8(x).astype(int) - g["final_u8"].astype(int))
+            assert d8.mean() < 1.0, (name, float(d8.mean()))
+    else:
+        # On this input the REFERENCE parts from itself after `stable` evaluations (two CPU thread counts more than 1e-3 apart:
+        # unit-step L-BFGS overshoots and the trajectory is chaotic from there).  The evaluations before that are
+        # held to the tolerance; the overshoot must be reproduced, not avoided: the curve leaves the band where the reference's
+        # does (within a factor of two of its loss at the first evaluation after the stable prefix).
+        print("  reference is stable against itself for the first %d evaluations only (self deviation %.1e at evaluation %d)"
+              % (stable, float(g["self_dev_trace"][stable]), stable))
+        assert stable >= 3
+        assert dev[:stable].max() <= CURVE_TOL, (name, dev[:stable])
+        assert 0.5 * ref[stable] <= tr[stable] <= 2.0 * ref[stable], (tr[stable], ref[stable])
+        assert np.isfinite(tr).all() and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
     s.close()
 
 

@@ -200,6 +200,134 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
       w.Sg[p] = dots[NST_LBFGS_NDOT * p + 1];
       w.Yg[p] = dots[NST_LBFGS_NDOT * p + 3];
     }
+#if defined(__CUDA_ARCH__)
+    // ===================================== device: no dependent chain =====================================================
+    // The two loops of the recursion are triangular solves with R (R_ij = s_i . y_j, j >= i in age order, R_ii = y_i . s_i):
+    //   loop 1:  R al = -Sg              loop 2:  R^T c = D al - yq0,  D = diag(R),  yq0_i = H (-Yg_i - sum_j al_j YY_ij)
+    // (substitute al_k = ro_k (s_k . q) and c_k = al_k - ro_k (y_k . r) into lbfgs.py:432-442).  Run as substitutions they
+    // are 2 x 100 dependent fp64 steps of ~140 cycles each (shuffle + DFMA latency): 7 us per loop whether blocked 32 x 32
+    // (r01) or run by a single warp (profiles/r02_lbfgs_controller_experiments.md).  On the device the matrix kept in w.R / Rg
+    // is therefore M = R^-1, maintained incrementally - appending a pair appends the column -M r / rho and the diagonal
+    // 1 / rho (one matrix-vector product), dropping the oldest pair drops the first row and column (the trailing block of
+    // the inverse of a triangular matrix is the inverse of the trailing block) - and both solves become matrix-vector
+    // products, al = -M Sg and c = M^T (D al - yq0): block parallel, ~1 us each.  fp64 throughout; algebraically identical.
+    if (ys > 1e-10) {
+      // lbfgs.py:407-421: accept the pair
+      for (int i = tid; i < len; i += nt) {
+        const int p = nst_ctl_slot(head, i);
+        const double Yy = dots[NST_LBFGS_NDOT * p + 2];
+        w.YY[p * TOT + pn] = Yy;
+        w.YY[pn * TOT + p] = Yy;
+        YYg[p * TOT + pn] = Yy;
+        YYg[pn * TOT + p] = Yy;
+        w.c[p] = dots[NST_LBFGS_NDOT * p + 0];   // r_i = s_i . y_new (scratch: w.c is rewritten below)
+      }
+      if (tid == 0) {
+        w.YY[pn * TOT + pn] = yy;
+        YYg[pn * TOT + pn] = yy;
+        w.Sg[pn] = scal[3];
+        w.Yg[pn] = scal[4];
+        c->ro[pn] = 1.0 / ys;
+      }
+      NST_BLOCK_SYNC();
+      const int first = len == hist_cap ? 1 : 0;   // old_dirs.pop(0): the oldest pair leaves
+      // row pn of M: the new pair is the newest, its row holds the diagonal only
+      for (int j = tid; j < TOT; j += nt) {
+        const double v = j == pn ? 1.0 / ys : 0.0;
+        w.R[pn * TOT + j] = v;
+        Rg[pn * TOT + j] = v;
+      }
+      // column pn of M for the retained rows: -(M r)_i / rho, four threads per row
+      {
+        const int row = first + (tid >> 2), part = tid & 3;
+        const bool live = row < len;
+        const int pi = nst_ctl_slot(head, live ? row : 0);
+        double acc = 0.0;
+        if (live) {
+          for (int j = row + part; j < len; j += 4) {
+            const int pj = nst_ctl_slot(head, j);
+            acc += w.R[pi * TOT + pj] * w.c[pj];
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (live && part == 0) {
+          const double v = -acc / ys;
+          w.R[pi * TOT + pn] = v;
+          Rg[pi * TOT + pn] = v;
+        }
+      }
+      if (first) head = nst_ctl_slot(head, 1);
+      else len += 1;
+      H_diag = ys / yy;
+    }
+    if (tid == 0) {
+      c->ys = ys;
+      c->yy = yy;
+    }
+    NST_BLOCK_SYNC();
+    for (int i = tid; i < len; i += nt) {
+      const int p = nst_ctl_slot(head, i);
+      w.ro[p] = c->ro[p];
+    }
+    NST_BLOCK_SYNC();
+    NST_CLK(2);
+    // al = -M Sg: row i sums over the columns j >= i, four threads per row
+    {
+      const int row = tid >> 2, part = tid & 3;
+      const bool live = row < len;
+      const int pi = nst_ctl_slot(head, live ? row : 0);
+      double acc = 0.0;
+      if (live) {
+        for (int j = row + part; j < len; j += 4) {
+          const int pj = nst_ctl_slot(head, j);
+          acc += w.R[pi * TOT + pj] * w.Sg[pj];
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (live && part == 0) w.al[pi] = -acc;
+    }
+    NST_BLOCK_SYNC();
+    NST_CLK(3);
+    // v_i = D_ii al_i - yq0_i with yq0_i = H (-Yg_i - sum_j al_j YY_ij), four threads per row
+    {
+      const int row = tid >> 2, part = tid & 3;
+      const bool live = row < len;
+      const int pi = nst_ctl_slot(head, live ? row : 0);
+      double acc = 0.0;
+      if (live) {
+        for (int j = part; j < len; j += 4) {
+          const int pj = nst_ctl_slot(head, j);
+          acc += w.al[pj] * w.YY[pi * TOT + pj];
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (live && part == 0) w.yq[pi] = w.al[pi] / w.ro[pi] - H_diag * (-w.Yg[pi] - acc);
+    }
+    NST_BLOCK_SYNC();
+    NST_CLK(4);
+    // c = M^T v: row i sums over j <= i
+    {
+      const int row = tid >> 2, part = tid & 3;
+      const bool live = row < len;
+      const int pi = nst_ctl_slot(head, live ? row : 0);
+      double acc = 0.0;
+      if (live) {
+        for (int j = part; j <= row; j += 4) {
+          const int pj = nst_ctl_slot(head, j);
+          acc += w.R[pj * TOT + pi] * w.yq[pj];
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (live && part == 0) w.c[pi] = acc;
+    }
+    NST_BLOCK_SYNC();
+    NST_CLK(5);
+#else
+    // ===================================== host (unit tests): the recursion as torch writes it ============================
     if (ys > 1e-10) {
       // lbfgs.py:407-421: accept the pair; its dot products with every retained pair enter R / YY
       for (int i = tid; i < len; i += nt) {
@@ -239,47 +367,6 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     NST_CLK(2);
     // lbfgs.py:432-435: for k newest..oldest: al_k = ro_k (s_k . q); q -= al_k y_k.  Column oriented: once al_k is
     // known every older row i subtracts al_k (s_i . y_k) from its running s_i . q - no reduction on the dependent chain.
-#if defined(__CUDA_ARCH__)
-    // Device: ONE warp runs the whole dependent chain, no block barrier inside it.  Lane l owns rows l, l + 32, l + 64, l + 96
-    // (age order) with their running values s_i . q in registers; a step is: the owner lane of row k forms al_k, one 64-bit
-    // shuffle broadcasts it, every lane applies it to its (at most four) older rows.  The matrix entries a step needs do not
-    // depend on the chain, so their shared-memory loads are issued ahead of it (the loop is unrolled).  r01 ran the chain in
-    // 32-row blocks with a block-wide update and two __syncthreads() per block: 9.8 us for 100 pairs; this form is bound by
-    // ~50 cycles per step.
-    // The chain itself is one shuffle and one multiply-add per step: the rows carry z_i = ro_i (s_i . q) instead of s_i . q, so
-    // al_k is the owner's z_k as it stands, and the update z_i -= al_k (ro_i R_ik) takes its factor ro_i R_ik from a product
-    // that does not depend on the chain.  (fp64 latency is what bounds this loop: ~50 cycles per dependent operation.)
-    if (tid < 32) {
-      const int lane = tid;
-      double zv[4], rov[4];
-      int prow[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = lane + 32 * j;
-        prow[j] = nst_ctl_slot(head, i < len ? i : 0);
-        rov[j] = i < len ? w.ro[prow[j]] : 0.0;
-        zv[j] = i < len ? rov[j] * w.c[prow[j]] : 0.0;
-      }
-#pragma unroll 4
-      for (int k = len - 1; k >= 0; --k) {
-        const int pk = nst_ctl_slot(head, k);
-        const int jk = k >> 5, lk = k & 31;
-        double r4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r4[j] = rov[j] * w.R[prow[j] * TOT + pk];
-        const double mine = jk == 0 ? zv[0] : (jk == 1 ? zv[1] : (jk == 2 ? zv[2] : zv[3]));
-        const double al = __shfl_sync(0xffffffffu, mine, lk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (lane + 32 * j < k) zv[j] -= al * r4[j];
-        // row k is final now: its owner's z_k IS al_k and is not touched again (no store inside the chain - the compiler
-        // could not move the next steps' matrix loads above a store through a pointer that may alias the matrix)
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (lane + 32 * j < len) w.al[prow[j]] = zv[j];
-    }
-#else
     if (tid < NST_CTL_NL) {
       for (int k = len - 1; k >= 0; --k) {
         const int pk = nst_ctl_slot(head, k);
@@ -292,7 +379,6 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         NST_WARP_SYNC();
       }
     }
-#endif
     NST_BLOCK_SYNC();
     NST_CLK(3);
     // y_i . r at the start of loop 2: H (y_i . q) = H (-(y_i . g) - sum_j al_j (y_i . y_j))          [block parallel]
@@ -309,38 +395,6 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
     NST_CLK(4);
     // lbfgs.py:439-442: r = H q; for k oldest..newest: be_k = ro_k (y_k . r); r += (al_k - be_k) s_k.  Once c_k is known
     // every younger row i adds c_k (s_k . y_i) to its running y_i . r.
-#if defined(__CUDA_ARCH__)
-    // device: the same single-warp form, forward
-    // rows carry t_i = al_i - ro_i (y_i . r): c_k is the owner's t_k, the update is t_i -= c_k (ro_i R_ki)
-    if (tid < 32) {
-      const int lane = tid;
-      double tv[4], rov[4];
-      int prow[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = lane + 32 * j;
-        prow[j] = nst_ctl_slot(head, i < len ? i : 0);
-        rov[j] = i < len ? w.ro[prow[j]] : 0.0;
-        tv[j] = i < len ? w.al[prow[j]] - rov[j] * w.yq[prow[j]] : 0.0;
-      }
-#pragma unroll 4
-      for (int k = 0; k < len; ++k) {
-        const int pk = nst_ctl_slot(head, k);
-        const int jk = k >> 5, lk = k & 31;
-        double r4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r4[j] = rov[j] * w.R[pk * TOT + prow[j]];
-        const double mine = jk == 0 ? tv[0] : (jk == 1 ? tv[1] : (jk == 2 ? tv[2] : tv[3]));
-        const double ck = __shfl_sync(0xffffffffu, mine, lk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (lane + 32 * j > k) tv[j] -= ck * r4[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (lane + 32 * j < len) w.c[prow[j]] = tv[j];   // row k's t_k is c_k from step k on
-    }
-#else
     if (tid < NST_CTL_NL) {
       for (int k = 0; k < len; ++k) {
         const int pk = nst_ctl_slot(head, k);
@@ -353,9 +407,10 @@ NST_HD inline void nst_lbfgs_control(NstLbfgsCtl* c, NstCtlWork w, double* Rg, d
         NST_WARP_SYNC();
       }
     }
-#endif
     NST_BLOCK_SYNC();
     NST_CLK(5);
+
+#endif
     for (int i = tid; i < len; i += nt) {
       const int p = nst_ctl_slot(head, i);
       c->coef[p] = static_cast<float>(w.c[p]);
