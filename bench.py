@@ -334,15 +334,16 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
     t_setup = time.perf_counter()
     styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=steps, device=dev, **synth.APP_WEIGHTS)
     styler.process_block(frames[:1])                       # warm-up: graph capture, allocator, pinned buffers
-    video.gather_frames(frames[:1].clone().to(dev), world, dev)   # ... and the communicator of the all-gather
+    lo, hi = video.shard_range(n_frames, world, rank)
+    video.gather_frames(frames[lo:hi].to(dev), n_frames, dev)    # ... and the communicator / buffers of the all-gather (same sizes)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
-    lo, hi = video.shard_range(n_frames, world, rank)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    local = styler.process_block(frames[lo:hi]) if hi > lo else torch.empty((0, H, W, 3), dtype=torch.uint8)
+    local = (styler.process_block(frames[lo:hi], out_device=dev if world > 1 else None) if hi > lo
+             else torch.empty((0, H, W, 3), dtype=torch.uint8))
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     out = video.gather_frames(local, n_frames, dev)

@@ -132,12 +132,12 @@ def finalize(case, ta, tb):
     out["self_n_evals"] = np.array([len(la), len(lb)])
     dec = float(np.mean(np.diff(la) < 0))
     out["frac_decreasing"] = np.array(dec)
-    # keep the fixtures small: intermediate iterates only up to 512^2; the uint8 image only up to 512^2 (it is the truncated
+    # keep the fixtures small: no intermediate iterates (the runs keep them under /tmp for debugging); the uint8 image only up to 512^2 (it is the truncated
     # float image); no images at all where the reference is not stable against itself (nothing can be compared with them)
     big = a["content_u8"].shape[0] * a["content_u8"].shape[1] > 512 * 512
     unstable = int(out["stable_prefix"]) < n
     for k in list(out):
-        if (k.startswith("x_eval") and (big or unstable)) or (k == "final_u8" and (big or unstable)) or (k == "x_final" and unstable):
+        if k.startswith("x_eval") or (k == "final_u8" and (big or unstable)) or (k == "x_final" and unstable):
             del out[k]
     path = os.path.join(HERE, "large_%s.npz" % case)
     np.savez_compressed(path, **out)

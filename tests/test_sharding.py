@@ -66,7 +66,7 @@ def _worker(rank, world, port, n_frames, q):
             def __call__(self, k, f):
                 raise AssertionError("run_sharded must use process_block when there is one")
 
-            def process_block(self, fr):
+            def process_block(self, fr, out_device=None):
                 self.blocks.append(int(fr.shape[0]))
                 return 255 - fr
 

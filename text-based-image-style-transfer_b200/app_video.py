@@ -160,8 +160,8 @@ class _Progress:
     def __init__(self, styler, num_frames, rank):
         self.styler, self.num_frames, self.rank, self.done = styler, num_frames, rank, 0
 
-    def process_block(self, frames_u8):
-        out = self.styler.process_block(frames_u8)
+    def process_block(self, frames_u8, out_device=None):
+        out = self.styler.process_block(frames_u8, out_device=out_device)
         for _ in range(int(frames_u8.shape[0])):
             self.done += 1
             print(f"Finished processing frame: {self.done} out of {self.num_frames}")

@@ -73,7 +73,9 @@ def run_sharded(frames: torch.Tensor, process_frame: Callable[[int, torch.Tensor
     rank = dist.get_rank() if dist else 0
     lo, hi = shard_range(frames.shape[0], world, rank)
     if hasattr(process_frame, "process_block") and hi > lo:
-        local = process_frame.process_block(frames[lo:hi])      # several frames at a time on this rank's GPU
+        # several frames at a time on this rank's GPU; with more than one rank the finished frames are also kept on the
+        # device (pinned -> device, 0.1 ms per 720p frame) so that the all-gather does not start with a pageable upload
+        local = process_frame.process_block(frames[lo:hi], out_device=device if world > 1 else None)
     else:
         done = [process_frame(k, frames[k]) for k in range(lo, hi)]
         local = torch.stack(done, 0) if done else torch.empty((0,) + tuple(frames.shape[1:]), dtype=torch.uint8)
@@ -122,24 +124,29 @@ class FrameStyler:
         self._ins = [self._in] + [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in self.sessions[1:]]
         self._outs = [self._out] + [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in self.sessions[1:]]
 
-    def __call__(self, index: int, frame_u8: torch.Tensor) -> torch.Tensor:
+    def _run_one(self, frame_u8: torch.Tensor) -> torch.Tensor:
+        """One frame through nst_run_frame_host; returns the pinned host buffer it was written to (valid until the next call)."""
         self._in.copy_(frame_u8)
         s = self.session
         with torch.cuda.device(self.device), torch.cuda.stream(s.stream):
             s.plan.run_frame_host(self._in, self._out, self.num_steps, *(self.ca or (None, None)))
-        return self._out.clone()
+        return self._out
 
-    def process_block(self, frames_u8: torch.Tensor) -> torch.Tensor:
+    def __call__(self, index: int, frame_u8: torch.Tensor) -> torch.Tensor:
+        return self._run_one(frame_u8).clone()
+
+    def process_block(self, frames_u8: torch.Tensor, out_device=None) -> torch.Tensor:
         """frames_u8: (n, H, W, 3) uint8 host tensor -> the n stylised frames, `concurrent` at a time (nst_run_frames_host).
-        Every frame's result is bit-identical to __call__ on that frame."""
+        Every frame's result is bit-identical to __call__ on that frame.  out_device: return them as a tensor on that CUDA
+        device (each finished frame is copied there from the pinned host buffer it was written to) instead of a host tensor."""
         import ctypes as C
         from . import _lib
         n = int(frames_u8.shape[0])
-        out = torch.empty((n,) + tuple(frames_u8.shape[1:]), dtype=torch.uint8)
+        out = torch.empty((n,) + tuple(frames_u8.shape[1:]), dtype=torch.uint8, device=out_device if out_device is not None else "cpu")
         K = len(self.sessions)
         if K == 1:
             for k in range(n):
-                out[k] = self(k, frames_u8[k])
+                out[k].copy_(self(k, frames_u8[k]) if out_device is None else self._run_one(frames_u8[k]))
             return out
         lib = _lib.load()
         w1, w2 = self.ca or (None, None)
@@ -156,7 +163,7 @@ class FrameStyler:
                                                    C.c_void_p(w1.data_ptr() if w1 is not None else None),
                                                    C.c_void_p(w2.data_ptr() if w2 is not None else None), streams, None))
             for j in range(cnt):
-                out[lo + j] = self._outs[j]
+                out[lo + j].copy_(self._outs[j])
         return out
 
     def close(self):
