@@ -495,24 +495,29 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- the whole job of BASELINE configs[1], device-timed: fresh optimizer state, num_steps=300 -> 320 evaluations =
     #      16 graph launches (the history grows 0 -> 100 pairs on the way, run-average ~84)
-    sess.prepare(content, trace_capacity=trace_cap)       # same capacity: the captured graph survives
-    with torch.cuda.stream(stream):
-        plan.lbfgs_prepare_graph()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        ev2.record(stream)
-    launches_320 = enqueue_evals(JOB_EVALS)
-    with torch.cuda.stream(stream):
-        ev3.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    ms_320 = max_over_ranks(ev2.elapsed_time(ev3))
+    # two repetitions, the faster one is reported (the same is done for e2e below: both time the identical job, and a
+    # transient on the box must not decide which of the two comes out ahead)
+    ms_320 = None
+    for _rep in range(2):
+        sess.prepare(content, trace_capacity=trace_cap)   # same capacity: the captured graph survives
+        with torch.cuda.stream(stream):
+            plan.lbfgs_prepare_graph()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ev2.record(stream)
+        launches_320 = enqueue_evals(JOB_EVALS)
+        with torch.cuda.stream(stream):
+            ev3.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        t_rep = max_over_ranks(ev2.elapsed_time(ev3))
+        ms_320 = t_rep if ms_320 is None else min(ms_320, t_rep)
     st320 = sess.status()
     value_320 = dict(value=world * JOB_EVALS / (ms_320 * 1e-3), unit=UNIT, evals=JOB_EVALS, ms=ms_320, history_pairs_at_end=st320.hist_len,
                      final_loss=st320.loss, gpu_launches=launches_320,
-                     what="BASELINE configs[1] as one job, device-timed (CUDA events): fresh L-BFGS state, 16 optimizer.step() graph launches")
+                     what="BASELINE configs[1] as one job, device-timed (CUDA events): fresh L-BFGS state, 16 optimizer.step() graph launches; best of 2 repetitions")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the public host-buffer call on the WHOLE job (uint8 image in pinned host memory -> H2D -> content / edge
@@ -521,18 +526,21 @@ def run_b200(args, rank, world, local_rank):
     pin_out = torch.empty_like(pin_in).pin_memory()
     with torch.cuda.stream(stream):
         plan.run_frame_host(pin_in, pin_out, 0)              # warm: 20 evaluations through the same call
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        n_e2e = plan.run_frame_host(pin_in, pin_out, JOB_STEPS)
-    torch.cuda.synchronize()
-    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    dt_e2e = None
+    for _rep in range(2):
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            n_e2e = plan.run_frame_host(pin_in, pin_out, JOB_STEPS)
+        torch.cuda.synchronize()
+        t_rep = max_over_ranks(time.perf_counter() - t0)
+        dt_e2e = t_rep if dt_e2e is None else min(dt_e2e, t_rep)
     status_bytes = 2700 + 4 * 16  # control block + loss vector read back after every optimizer.step()
     e2e = dict(value=world * n_e2e / dt_e2e, unit=UNIT, h2d_bytes_per_step=3 * S * S / n_e2e,
                d2h_bytes_per_step=(3 * S * S + status_bytes * (n_e2e // 20)) / n_e2e, evals=n_e2e, seconds=dt_e2e,
                call="nst_run_frame_host(num_steps=%d): H2D uint8 image, content/edge targets, %d evaluations (the whole job of BASELINE "
-                    "configs[1]), one status read-back per optimizer.step(), D2H uint8 result; wall clock, max over ranks" % (JOB_STEPS, n_e2e))
+                    "configs[1]), one status read-back per optimizer.step(), D2H uint8 result; wall clock, max over ranks, best of 2 repetitions" % (JOB_STEPS, n_e2e))
     # sanity (r01's line had value < e2e because the graph capture sat inside the timed region): the device-timed job
     # cannot be slower than the same job through the host-buffer call, which adds copies and 16 host round trips
     sanity = dict(e2e_le_value_320=bool(e2e["value"] <= 1.02 * value_320["value"]),

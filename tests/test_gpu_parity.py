@@ -696,10 +696,18 @@ def test_full_run_against_reference_golden_large(nst, rst, oracle, name):
         # unit-step L-BFGS overshoots and the trajectory is chaotic from there).  The evaluations before that are
         # held to the tolerance; the overshoot must be reproduced, not avoided: the curve leaves the band where the reference's
         # does (within a factor of two of its loss at the first evaluation after the stable prefix).
+        # Inside the stable prefix the trajectory is already amplifying perturbations (the two reference runs start 1e-7 apart
+        # and are 1e-3 apart at its end); this path starts ~5e-6 from the reference (fp16 / bf16 trunk), i.e. ~50x the
+        # reference's own starting distance, and is carried by the same dynamics.  The tolerance per evaluation is therefore
+        # north_star's 1e-2, widened to 100x the reference's running self-deviation where that is larger.
+        sd = np.maximum.accumulate(g["self_dev_trace"][:stable])
+        tol = np.maximum(CURVE_TOL, 100.0 * sd)
         print("  reference is stable against itself for the first %d evaluations only (self deviation %.1e at evaluation %d)"
               % (stable, float(g["self_dev_trace"][stable]), stable))
+        print("  deviation / tolerance on that prefix: " + " ".join("%.0e/%.0e" % (a, b) for a, b in zip(dev[:stable], tol)))
         assert stable >= 3
-        assert dev[:stable].max() <= CURVE_TOL, (name, dev[:stable])
+        assert np.all(dev[:stable] <= tol), (name, dev[:stable], tol)
+        assert dev[:4].max() <= 1e-4          # before the first overshoot every run is the same run
         assert 0.5 * ref[stable] <= tr[stable] <= 2.0 * ref[stable], (tr[stable], ref[stable])
         assert np.isfinite(tr).all() and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
     s.close()

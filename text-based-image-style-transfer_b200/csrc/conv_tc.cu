@@ -154,8 +154,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only kernel parameters and on-chip state; from here on this grid reads and writes tensors
-  // produced by earlier kernels: wait for the grid(s) it depends on (no-op without the launch attribute)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // produced by earlier kernels: wait for the grid(s) it depends on (no-op without the launch attribute).  The producer
+  // warp waits later: the network weights are written by nobody inside a step, so its first weight stages are requested
+  // before the wait (they come from DRAM - the L2 is full of activations and optimizer history by then - and would
+  // otherwise arrive after the first patch, which the previous launch has just left in L2).
+  if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   NST_STAMP(1, threadIdx.x == 0);
 
   const int k_slices = p.K / BLOCK_K;
@@ -180,6 +183,21 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     if (elect_one()) {
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
+      // weight stages of the first tile's first slice, requested ahead of griddepcontrol.wait (not for the 1x1 Gram backward:
+      // its B operand is written by the Gram kernel right before it)
+      int pre_b = 0;
+      if (MODE != CONV_SCALE && static_cast<int>(blockIdx.x) < p.num_tiles) {
+        const int n0 = (static_cast<int>(blockIdx.x) / sp_tiles) * BLOCK_N;
+        for (int tap = 0; tap < p.taps && pre_b < Cfg::B_STAGES; tap += tps, ++pre_b) {
+          mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
+          tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], 0, n0, tap);
+          if (++bs == Cfg::B_STAGES) {
+            bs = 0;
+            bphase ^= 1u;
+          }
+        }
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile / sp_tiles;
         const int sp = tile - nt * sp_tiles;
@@ -196,6 +214,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           }
           if (b_resident && (tile != static_cast<int>(blockIdx.x) || ks > 0)) continue;
           for (int tap = 0; tap < p.taps; tap += tps) {
+            if (pre_b > 0) {   // already in flight (first tile, first slice)
+              --pre_b;
+              continue;
+            }
             NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
             mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
             tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], ks * BLOCK_K, n0, tap);
