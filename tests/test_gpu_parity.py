@@ -853,3 +853,30 @@ def test_apply_video_process_mirror(nst, rst, oracle, tmp_path):
     # effects outside the hot path raise instead of being skipped
     with pytest.raises(nst.NstError):
         A.apply_video_process(path, ["Pixel Art", "Style Transfer"], input_style=style, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------------ several content layers
+def test_content_loss_over_layers_of_different_size(nst, rst, oracle, vgg_weights):
+    """content_loss is the MEAN over the content layers of the per-layer MSEs (style_transfer_losses.py:53-65).  With layers
+    of different resolution every layer's partial sums must carry its own 1 / numel - r01 normalised all of them by the
+    first layer's size.  Loss and gradient against the oracle with content on conv3_2 (1/4 resolution, 256 channels) and
+    conv4_2 (1/8, 512), one of them weighted up so that a wrong normalisation cannot hide."""
+    O = oracle
+    ws, bs = vgg_weights
+    content, style = O.synth_image(64, 80, 0), O.synth_image(64, 80, 1)
+    layers = ["conv3_2", "conv4_2"]
+    wts = dict(w_style=5e5, w_content=50.0, w_tv=2e1, w_edge=2e1)
+    c = O.to_tensor_u8(content).cuda()
+    s = rst.StyleTransferSession(O.VGG_MEAN, O.VGG_STD, c.shape[2:], [O.to_tensor_u8(style).cuda()], wts["w_style"], wts["w_content"],
+                                 wts["w_tv"], wts["w_edge"], 0.5, "cuda", content_layers=layers)
+    s.prepare(c)
+    co = O.ClosureOracle(ws, bs, c.cpu(), [O.to_tensor_u8(style)], content_layers=layers, **wts)
+    x = noisy(c, seed=9)
+    ref = co.evaluate(x)
+    with torch.cuda.stream(s.stream):
+        losses, grad = s.plan.eval(x.cuda())
+    l = losses.cpu().tolist()
+    assert l[1] == pytest.approx(ref["content"], rel=LOSS_TOL)
+    assert l[0] == pytest.approx(ref["total"], rel=LOSS_TOL)
+    assert rel(grad, ref["grad"]) < 2e-3
+    s.close()

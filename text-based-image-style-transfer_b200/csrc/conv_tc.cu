@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   // the TMA writes of the B operand competing with the tensor core's shared-memory reads?
   const bool b_resident = p.taps == 9 && 9 / Cfg::TPS <= Cfg::B_STAGES && !seed &&
                           ((k_slices == 1 && p.tiles_n == 1) || NST_DBG_FLAG(p, 4));
+  // one-slice tiles with resident weights are issued by two threads (see the MMA issuer)
+  const bool dual_issue = b_resident && k_slices == 1 && Cfg::HALO_STAGES == 2 && p.dual_issue != 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         NST_DBG_PTR(p)[13] = wacc1;
       }
     }
-  } else if (warp == 1 && elect_one()) {
-    // ===================== MMA issuer (one thread) =====================
+  } else if ((warp == 1 || (warp == 3 && dual_issue)) && elect_one()) {
+    // ===================== MMA issuer (one thread; two for layers whose weights are resident) =====================
     // The thread is chosen with elect.sync in a warp-uniform branch (not `lane == 0`): only then does the compiler know that
     // a single lane runs the uniform-datapath UTCHMMA / UTCBAR instructions and emits them back to back; with a divergent
     // predicate every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY serialisation loop (~45 cycles per MMA).
@@ -259,15 +261,24 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     // (measured: 45 cycles per MMA with constant descriptors, 76 with a few extra index operations,
     // profiles/r01_mma_issue_rate.log), so the 64-bit descriptors are not rebuilt per MMA: their upper halves are
     // loop constants and the lower halves (address >> 4) advance by compile-time immediates.
-    int as = 0, bs = 0, ts = 0;
+    // Two issuers (dual_issue): one thread cannot issue a tcgen05.mma more often than every ~47 cycles
+    // (profiles/r01_mma_issue_rate_elect.log: 47 cycles per MMA at N = 16, 51 at N = 64 in a bare loop; 70 - 79 inside this
+    // kernel with its barrier traffic), which is more than the 32 cycles an M128 x N64 MMA occupies the tensor core.  Where a
+    // tile is one 64-channel slice with resident weights (conv1_2 forward, conv1_1's data gradient) the tiles of a CTA
+    // are independent streams: warp 1 takes the CTA's even tiles (patch stage 0, accumulator stage 0), warp 3 the odd ones
+    // (stages 1), each with its own barriers - the producer and the epilogue already alternate the stages tile by tile.
+    const int issuer = warp == 3 ? 1 : 0;
+    const int tile_step = dual_issue ? 2 * static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x);
+    int as = dual_issue ? issuer : 0, bs = 0, ts = dual_issue ? issuer : 0;
     uint32_t aphase = 0, bphase = 0, tphase = 0;
+    const int first_tile = static_cast<int>(blockIdx.x) + issuer * static_cast<int>(gridDim.x);
     const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;  // bytes between 8-pixel groups of the A operand
     const uint32_t idesc = p.idesc;
     const uint32_t a_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, sbo) >> 32);
     const uint32_t b_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, 1024) >> 32);
     const uint32_t lbo_lo = static_cast<uint32_t>(umma_desc_sw128(0, 16, 0) & 0xffffffffu);  // LBO field, address 0
     const bool conv3x3 = p.taps == 9;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
       NST_WAIT(wacc2, mbar_wait(&tempty_bar[ts], tphase ^ 1u));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           for (int g = 0; g < 9 / Cfg::TPS; ++g) {
             // resident weights: stage g holds filter row(s) g for the whole launch; only the first tile waits for them
             if (b_resident) bs = g;
-            if (!b_resident || tile == static_cast<int>(blockIdx.x)) NST_WAIT(wacc1, mbar_wait(&bfull_bar[bs], bphase));
+            if (!b_resident || tile == first_tile) NST_WAIT(wacc1, mbar_wait(&bfull_bar[bs], bphase));
             tc_fence_after();
             const uint32_t b_lo0 = lbo_lo | (smem_u32(sB + bs * Cfg::B_STAGE_BYTES) >> 4);
             // TPS = 1: tap g;  TPS = 3: taps 3g .. 3g+2 (one filter row);  TPS = 9: all taps
@@ -294,7 +305,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
                                                    : static_cast<uint32_t>(tt * 8);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_lo_g + a_tap + static_cast<uint32_t>(k * 2));
+                // NST_DBG_FLAG bit 3 (instrumented build, wrong results): every tap reads the un-shifted view - what do the
+                // shifted (not 1024-byte aligned) A views cost the tensor core's shared-memory reads?
+                const uint32_t a_view = NST_DBG_FLAG(p, 8) ? a_lo0 : a_lo_g + a_tap;
+                const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_view + static_cast<uint32_t>(k * 2));
                 const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) |
                                     (b_lo0 + static_cast<uint32_t>(tt * (Cfg::B_TILE_BYTES / 16) + k * 2));
                 umma_f16(d_tmem, da, db, idesc, accumulate);
@@ -327,7 +341,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           }
         }
         umma_commit(&aempty_bar[as]);  // ... and the patch after its last tap
-        if (++as == Cfg::HALO_STAGES) {
+        if (dual_issue) {
+          aphase ^= 1u;   // this issuer's own patch stage, next use
+        } else if (++as == Cfg::HALO_STAGES) {
           as = 0;
           aphase ^= 1u;
         }
@@ -365,7 +381,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
       umma_commit(&tfull_bar[ts]);  // accumulator(s) complete
       NST_STAMP(3, tile == blockIdx.x);
-      if (++ts == 2) {
+      if (dual_issue) {
+        tphase ^= 1u;     // this issuer's own accumulator stage, next use
+      } else if (++ts == 2) {
         ts = 0;
         tphase ^= 1u;
       }
@@ -653,6 +671,8 @@ int conv_block_n(int N, int H, int W, int k_total, int num_sms) {
 }
 
 void conv_finalize_params(ConvParams& p, int mode) {
+  static const bool single_issue = getenv("NST_SINGLE_ISSUE") != nullptr;
+  p.dual_issue = single_issue ? 0 : 1;
   const int bn = p.block_n;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;

@@ -59,6 +59,7 @@ struct ConvParams {
   int block_n;     // N tile: 64, 128 or 256 (conv_block_n)
   int tiles_w, tiles_h, tiles_n, num_tiles;
   uint32_t idesc;
+  int dual_issue;  // != 0: one-slice layers with resident weights are issued by two threads (conv_tc.cu); NST_SINGLE_ISSUE clears it
   // ---- CONV_FWD
   const float* bias;   // [N]
   __half* out_tap;     // [H,W,N] pre-ReLU or nullptr
@@ -85,7 +86,7 @@ struct ConvParams {
   // (atomicMin / atomicMax by every CTA): tools/conv_timeline.py
   unsigned long long* tl;
   // timing experiments that produce WRONG results: bit 0 = skip the epilogue's global stores, bit 1 = skip its global
-  // loads, bit 2 = never re-stream the weights
+  // loads, bit 2 = never re-stream the weights, bit 3 = every filter tap reads the un-shifted patch view
   int dbg_flags;
 #endif
 };
