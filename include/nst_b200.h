@@ -204,7 +204,7 @@ int nst_lbfgs_step_timed_grouped(nst_plan* plan, nst_launch_time* out, int max_o
 int nst_plan_conv_phases(nst_plan* plan, int conv, int mode, long long* out14, void* stream);
 /* launch spans {earliest CTA start, latest CTA end} (%globaltimer ns) of the convolution launches inside the captured
    step: slot = conv (forward), 16 + conv (data gradient), 32 + conv (Gram backward); enable re-captures the step with
-   the slots armed, out96 (2 x 48 values, may be NULL) reads them back and re-arms: tuning aid, tools/conv_timeline.py */
+   the slots armed, out96 (8 x 48 values, may be NULL) reads them back and re-arms: tuning aid, tools/conv_timeline.py */
 int nst_plan_timeline(nst_plan* plan, int enable, unsigned long long* out96, void* stream);
 /* SM clock at the phase boundaries of the most recent L-BFGS controller launch (slots: csrc/lbfgs_ctl.h), 8 values:
    tuning aid, tools/ctl_phases.py */

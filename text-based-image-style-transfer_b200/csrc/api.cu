@@ -220,7 +220,7 @@ struct nst_plan {
   // seed_folded[i]: the Gram backward of style layer conv i runs inside the data gradient of conv i+1 (no launch of its own)
   bool seed_folded[NST_MAX_CONV] = {};
 #ifdef NST_INSTRUMENT
-  unsigned long long* timeline = nullptr;  // [48][2] launch spans of the conv kernels (nst_plan_timeline)
+  unsigned long long* timeline = nullptr;  // [48][8] launch spans of the conv kernels (nst_plan_timeline)
   bool timeline_on = false;
 #endif
 };
@@ -313,7 +313,8 @@ static int build_conv_params(nst_plan* p) {
     f.taps = 9;
     if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
     f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
-    if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n) != 0)
+    f.pair = conv_use_pair(CONV_FWD, f.block_n, 9, kCin[i], kCout[i]) ? 1 : 0;
+    if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n, f.pair != 0) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
     f.bias = net->b32[i];
     f.out_tap = p->tap[i];
@@ -337,7 +338,8 @@ static int build_conv_params(nst_plan* p) {
     d.taps = 9;
     if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
     d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
-    if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n) != 0)
+    d.pair = conv_use_pair(CONV_DGRAD, d.block_n, 9, kCout[i], kCin[i]) ? 1 : 0;
+    if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n, d.pair != 0) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
     const bool prev_pooled = kPoolAfter[i - 1] != 0;  // conv i reads the pooled output of conv i-1
     d.out_grad = p->gpre[i - 1];
@@ -418,9 +420,9 @@ static int build_conv_params(nst_plan* p) {
       if (d.block_n > 128 || d.route != nullptr) continue;
       const int C = kCout[j];
       if (make_tmap_act(&d.tmA2, p->tap[j], d.H, d.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d, folded)", j);
-      if (make_tmap_wgt(&d.tmB2, p->dh[l], 1, C, C, d.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
+      if (make_tmap_wgt(&d.tmB2, p->dh[l], 1, C, C, d.block_n, d.pair != 0) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
       d.seed_k = C;
-      d.idesc2 = umma_idesc_f16(128, d.block_n, 0, 0, 0);
+      d.idesc2 = umma_idesc_f16(d.pair ? 256 : 128, d.block_n, 0, 0, 0);
       d.alpha = p->alpha + l;
       d.addend = nullptr;
       p->seed_folded[j] = true;
@@ -456,7 +458,7 @@ static int build_gram_params(nst_plan* p) {
   return NST_OK;
 }
 
-static int conv_grid(const ConvParams& c) { return c.num_tiles < g_num_sms ? c.num_tiles : g_num_sms; }
+static int conv_grid(const ConvParams& c) { return conv_grid_ctas(c, g_num_sms); }
 
 // Plans the shallow style layers' Gram launch for the SMs that stay idle beside the deeper convolutions (nst_plan).
 static int build_gram_narrow(nst_plan* p) {
@@ -1341,15 +1343,22 @@ extern "C" int nst_lbfgs_ctl_clocks(nst_plan* p, long long* out8, void* stream) 
 // Debug / tuning aid: where do the convolution launches sit inside the captured step?  enable = 1 gives every conv launch
 // of the plan a slot {earliest CTA start, latest CTA end} in %globaltimer ns (slot = conv for forward, 16 + conv for data
 // gradients, 32 + conv for Gram backward) and drops the captured graph so that the next step re-captures with the slots;
-// out96 != nullptr reads the slots back (2 x 48 values) and re-arms them.
+// out96 != nullptr reads the slots back (8 x 48 values: start, end, earliest return from
+// griddepcontrol.wait, latest completion of a CTA's last accumulator, earliest / latest first MMA, latest last MMA issue, spare) and re-arms them.
 extern "C" int nst_plan_timeline(nst_plan* p, int enable, unsigned long long* out96, void* stream) {
   if (!p) return fail(NST_ERR_ARG, "nst_plan_timeline: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (enable && !p->timeline) CKI(plan_alloc_t(p, &p->timeline, 96));
-  unsigned long long init[96];
+  if (enable && !p->timeline) CKI(plan_alloc_t(p, &p->timeline, 384));
+  unsigned long long init[384];
   for (int i = 0; i < 48; ++i) {
-    init[2 * i] = ~0ull;
-    init[2 * i + 1] = 0ull;
+    init[8 * i] = ~0ull;      // earliest CTA start
+    init[8 * i + 1] = 0ull;   // latest CTA end
+    init[8 * i + 2] = ~0ull;  // earliest return from griddepcontrol.wait
+    init[8 * i + 3] = 0ull;   // latest "accumulator of the CTA's last tile complete"
+    init[8 * i + 4] = ~0ull;  // earliest first MMA (first patch and first weight stage have arrived)
+    init[8 * i + 5] = 0ull;   // latest first MMA
+    init[8 * i + 6] = 0ull;   // latest "last MMA of the CTA's last tile issued"
+    init[8 * i + 7] = 0ull;
   }
   if (out96 && p->timeline) {
     CK(cudaStreamSynchronize(s));
@@ -1562,9 +1571,9 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
 #ifdef NST_INSTRUMENT
 static void timeline_arm(nst_plan* p, bool on) {
   for (int i = 0; i < p->n_layers; ++i) {
-    p->fwd[i].tl = on ? p->timeline + 2 * i : nullptr;
-    p->dgrad[i].tl = on ? p->timeline + 2 * (16 + i) : nullptr;
-    p->scale[i].tl = on ? p->timeline + 2 * (32 + i) : nullptr;
+    p->fwd[i].tl = on ? p->timeline + 8 * i : nullptr;
+    p->dgrad[i].tl = on ? p->timeline + 8 * (16 + i) : nullptr;
+    p->scale[i].tl = on ? p->timeline + 8 * (32 + i) : nullptr;
   }
 }
 #endif

@@ -76,7 +76,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int MODE, bool TMA_OUT>
+// PAIR: two CTAs on the two SMs of a TPC (cluster of 2) work on two neighbouring pixel tiles of the same N tile with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own patch and HALF of the weight rows, the tensor cores of both SMs
+// read every weight half once.  Per K = 16 step a CTA's shared memory then delivers (128 + N/2) x 32 B instead of
+// (128 + N) x 32 B - 48 cycles at N = 128, below the 64 cycles of math; alone an SM needs all 64 and has nothing left for
+// the TMA writes of the weight stream (measured 81 cycles per MMA) - and one issuing thread feeds two tensor cores, which
+// halves the per-MMA issue cost that bounds the N = 64 layers.  The leader (cluster rank 0) issues every MMA; both CTAs keep
+// their own producer and epilogue warps.
+template <int BLOCK_N, int MODE, bool TMA_OUT, bool PAIR>
 __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -98,6 +105,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // persistent workers: CTAs, or CTA pairs
+  const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int B_HALF_DIV = PAIR ? 2 : 1;   // weight rows of a stage held by this CTA: BLOCK_N / B_HALF_DIV
   const bool dbg = NST_DBG_PTR(p) != nullptr && blockIdx.x == 0;
   const long long life0 = NST_DBG_PTR(p) != nullptr ? clock64() : 0;
 #define NST_STAMP(slot, cond)                                        \
@@ -141,16 +153,24 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], Cfg::EPI_WARPS);  // one arrival per epilogue warp
+      // one arrival per epilogue warp; the leader of a pair also collects its peer's (the accumulator stage of BOTH CTAs
+      // is rewritten by the leader's next MMA)
+      mbar_init(&tempty_bar[s], Cfg::EPI_WARPS * (PAIR ? 2 : 1));
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_slot, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  // pair: the peer's barriers must exist before a remote arrival, a multicast commit or a TMA completion reaches them
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only kernel parameters and on-chip state; from here on this grid reads and writes tensors
@@ -160,12 +180,28 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   // otherwise arrive after the first patch, which the previous launch has just left in L2).
   if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   NST_STAMP(1, threadIdx.x == 0);
+  if (NST_TL_PTR(p) != nullptr && threadIdx.x == 128) atomicMin(&NST_TL_PTR(p)[2], globaltimer_ns());
 
   const int k_slices = p.K / BLOCK_K;
   const int pad = p.taps == 9 ? 1 : 0;
   const int halo_w = TILE_W + 2 * pad;                     // pixels per patch row
   const uint32_t a_tx = p.taps == 9 ? HALO_TX_BYTES : FLAT_TX_BYTES;
   const int sp_tiles = p.tiles_w * p.tiles_h;
+  // work items: (N tile, pixel tile), or (N tile, two consecutive pixel tiles) for a pair - this CTA takes the tile of its
+  // rank; with an odd tile count the last pair's second tile lies below the image (all loads zero-fill, nothing is stored)
+  const int sp_items = PAIR ? (sp_tiles + 1) >> 1 : sp_tiles;
+  const int num_items = sp_items * p.tiles_n;
+  auto item_coords = [&](int item, int& nt, int& th, int& tw) {
+    nt = item / sp_items;
+    const int sp = PAIR ? 2 * (item - nt * sp_items) + cta_rank : item - nt * sp_items;
+    if (PAIR && sp >= sp_tiles) {
+      th = p.tiles_h;
+      tw = 0;
+    } else {
+      th = sp / p.tiles_w;
+      tw = sp - th * p.tiles_w;
+    }
+  };
   const int tps = p.taps == 9 ? Cfg::TPS : 1;              // taps per weight stage (the weight tensor map's box depth)
   // A layer with 64 input channels has ONE 64-channel slice: its whole weight set (nine taps) fits the weight ring.  It
   // is then loaded once per CTA and stays resident - re-streaming it for every tile (72 KB next to a 23 KB patch at
@@ -178,7 +214,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   const bool b_resident = p.taps == 9 && 9 / Cfg::TPS <= Cfg::B_STAGES && !seed &&
                           ((k_slices == 1 && p.tiles_n == 1) || NST_DBG_FLAG(p, 4));
   // one-slice tiles with resident weights are issued by two threads (see the MMA issuer)
-  const bool dual_issue = b_resident && k_slices == 1 && Cfg::HALO_STAGES == 2 && p.dual_issue != 0;
+  const bool dual_issue = !PAIR && b_resident && k_slices == 1 && Cfg::HALO_STAGES == 2 && p.dual_issue != 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -188,11 +224,25 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       // weight stages of the first tile's first slice, requested ahead of griddepcontrol.wait (not for the 1x1 Gram backward:
       // its B operand is written by the Gram kernel right before it)
       int pre_b = 0;
-      if (MODE != CONV_SCALE && static_cast<int>(blockIdx.x) < p.num_tiles) {
-        const int n0 = (static_cast<int>(blockIdx.x) / sp_tiles) * BLOCK_N;
+      // pair: the leader's barrier counts the bytes of both CTAs' loads (a weight stage is BLOCK_N rows either way, a patch
+      // stage two patches); the peer only issues its loads, which report to the leader's barrier
+      const bool expects = !PAIR || cta_rank == 0;
+      const uint32_t a_expect = PAIR ? 2u * a_tx : a_tx;
+      const int n_rank = PAIR ? cta_rank * (BLOCK_N / 2) : 0;
+      auto load_a = [&](const CUtensorMap* tm, int stage, uint32_t bytes, int c0, int c1, int c2) {
+        if (expects) mbar_arrive_expect_tx(&afull_bar[stage], bytes);
+        if constexpr (PAIR) tma_load_3d_2sm(sA + stage * HALO_STAGE_BYTES, tm, mapa_u32(smem_u32(&afull_bar[stage]), 0), c0, c1, c2);
+        else tma_load_3d(sA + stage * HALO_STAGE_BYTES, tm, &afull_bar[stage], c0, c1, c2);
+      };
+      auto load_b = [&](const CUtensorMap* tm, int stage, uint32_t bytes, int c0, int c1, int c2) {
+        if (expects) mbar_arrive_expect_tx(&bfull_bar[stage], bytes);
+        if constexpr (PAIR) tma_load_3d_2sm(sB + stage * Cfg::B_STAGE_BYTES, tm, mapa_u32(smem_u32(&bfull_bar[stage]), 0), c0, c1 + n_rank, c2);
+        else tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, tm, &bfull_bar[stage], c0, c1, c2);
+      };
+      if (MODE != CONV_SCALE && worker < num_items) {
+        const int n0 = (worker / sp_items) * BLOCK_N;
         for (int tap = 0; tap < p.taps && pre_b < Cfg::B_STAGES; tap += tps, ++pre_b) {
-          mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
-          tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], 0, n0, tap);
+          load_b(&p.tmB, bs, static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES, 0, n0, tap);
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;
@@ -200,29 +250,25 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         }
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile / sp_tiles;
-        const int sp = tile - nt * sp_tiles;
-        const int th = sp / p.tiles_w;
-        const int tw = sp - th * p.tiles_w;
+      for (int tile = worker; tile < num_items; tile += workers) {
+        int nt, th, tw;
+        item_coords(tile, nt, th, tw);
         const int h0 = th * TILE_H, w0 = tw * TILE_W, n0 = nt * BLOCK_N;
         for (int ks = 0; ks < k_slices; ++ks) {
           NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
-          mbar_arrive_expect_tx(&afull_bar[as], a_tx);
-          tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA, &afull_bar[as], ks * BLOCK_K, w0 - pad, h0 - pad);
+          load_a(&p.tmA, as, a_expect, ks * BLOCK_K, w0 - pad, h0 - pad);
           if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
           }
-          if (b_resident && (tile != static_cast<int>(blockIdx.x) || ks > 0)) continue;
+          if (b_resident && (tile != worker || ks > 0)) continue;
           for (int tap = 0; tap < p.taps; tap += tps) {
             if (pre_b > 0) {   // already in flight (first tile, first slice)
               --pre_b;
               continue;
             }
             NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
-            mbar_arrive_expect_tx(&bfull_bar[bs], static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES);
-            tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB, &bfull_bar[bs], ks * BLOCK_K, n0, tap);
+            load_b(&p.tmB, bs, static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES, ks * BLOCK_K, n0, tap);
             if (++bs == Cfg::B_STAGES) {
               bs = 0;
               bphase ^= 1u;
@@ -232,18 +278,38 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         // folded Gram backward: the tile of the tap (no halo) and the matching slice of dh, one 64-channel slice at a time
         for (int ks2 = 0; ks2 < seed_slices; ++ks2) {
           NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
-          mbar_arrive_expect_tx(&afull_bar[as], FLAT_TX_BYTES);
-          tma_load_3d(sA + as * HALO_STAGE_BYTES, &p.tmA2, &afull_bar[as], ks2 * BLOCK_K, w0, h0);
+          load_a(&p.tmA2, as, (PAIR ? 2u : 1u) * FLAT_TX_BYTES, ks2 * BLOCK_K, w0, h0);
           if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
           }
           NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
-          mbar_arrive_expect_tx(&bfull_bar[bs], Cfg::B_TILE_BYTES);
-          tma_load_3d(sB + bs * Cfg::B_STAGE_BYTES, &p.tmB2, &bfull_bar[bs], ks2 * BLOCK_K, n0, 0);
+          load_b(&p.tmB2, bs, Cfg::B_TILE_BYTES, ks2 * BLOCK_K, n0, 0);
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;
+          }
+        }
+      }
+      if constexpr (PAIR) {
+        // The peer never issues an MMA: it releases the dependent launch here, when its last load is on its way (the leader's
+        // MMA thread, which comes later, decides).  Then both producers stay until every stage they filled has been released:
+        // the leader's commits arrive at this CTA's barriers, which must still exist.
+        if (cta_rank != 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        for (int s = 0; s < Cfg::HALO_STAGES; ++s) {
+          mbar_wait(&aempty_bar[as], aphase ^ 1u);
+          if (++as == Cfg::HALO_STAGES) {
+            as = 0;
+            aphase ^= 1u;
+          }
+        }
+        if (!b_resident) {
+          for (int s = 0; s < Cfg::B_STAGES; ++s) {
+            mbar_wait(&bempty_bar[bs], bphase ^ 1u);
+            if (++bs == Cfg::B_STAGES) {
+              bs = 0;
+              bphase ^= 1u;
+            }
           }
         }
       }
@@ -252,7 +318,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         NST_DBG_PTR(p)[13] = wacc1;
       }
     }
-  } else if ((warp == 1 || (warp == 3 && dual_issue)) && elect_one()) {
+  } else if ((warp == 1 || (warp == 3 && dual_issue)) && (!PAIR || cta_rank == 0) && elect_one()) {
     // ===================== MMA issuer (one thread; two for layers whose weights are resident) =====================
     // The thread is chosen with elect.sync in a warp-uniform branch (not `lane == 0`): only then does the compiler know that
     // a single lane runs the uniform-datapath UTCHMMA / UTCBAR instructions and emits them back to back; with a divergent
@@ -268,24 +334,37 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     // are independent streams: warp 1 takes the CTA's even tiles (patch stage 0, accumulator stage 0), warp 3 the odd ones
     // (stages 1), each with its own barriers - the producer and the epilogue already alternate the stages tile by tile.
     const int issuer = warp == 3 ? 1 : 0;
-    const int tile_step = dual_issue ? 2 * static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x);
+    const int tile_step = dual_issue ? 2 * workers : workers;
     int as = dual_issue ? issuer : 0, bs = 0, ts = dual_issue ? issuer : 0;
     uint32_t aphase = 0, bphase = 0, tphase = 0;
-    const int first_tile = static_cast<int>(blockIdx.x) + issuer * static_cast<int>(gridDim.x);
+    const int first_tile = worker + issuer * workers;
     const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;  // bytes between 8-pixel groups of the A operand
     const uint32_t idesc = p.idesc;
     const uint32_t a_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, sbo) >> 32);
     const uint32_t b_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, 1024) >> 32);
     const uint32_t lbo_lo = static_cast<uint32_t>(umma_desc_sw128(0, 16, 0) & 0xffffffffu);  // LBO field, address 0
     const bool conv3x3 = p.taps == 9;
-    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+      if constexpr (PAIR) umma_f16_2sm(d, da, db, id, acc);
+      else umma_f16(d, da, db, id, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (PAIR) umma_commit_2sm(bar);
+      else umma_commit(bar);
+    };
+    for (int tile = first_tile; tile < num_items; tile += tile_step) {
       NST_WAIT(wacc2, mbar_wait(&tempty_bar[ts], tphase ^ 1u));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * BLOCK_N);
       uint32_t accumulate = 0;
       for (int ks = 0; ks < k_slices; ++ks) {
         NST_WAIT(wacc0, mbar_wait(&afull_bar[as], aphase));
-        NST_STAMP(2, ks == 0 && tile == blockIdx.x);
+        NST_STAMP(2, ks == 0 && tile == worker);
+        if (NST_TL_PTR(p) != nullptr && ks == 0 && tile == first_tile) {
+          const unsigned long long now = globaltimer_ns();
+          atomicMin(&NST_TL_PTR(p)[4], now);
+          atomicMax(&NST_TL_PTR(p)[5], now);
+        }
         const uint32_t a_lo0 = lbo_lo | (smem_u32(sA + as * HALO_STAGE_BYTES) >> 4);
         if (conv3x3) {
           // nine taps = nine row shifts of the patch: (dr * 10 + ds) rows of 128 B = (dr * 10 + ds) * 8 descriptor units
@@ -310,13 +389,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
                 const uint32_t a_view = NST_DBG_FLAG(p, 8) ? a_lo0 : a_lo_g + a_tap;
                 const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_view + static_cast<uint32_t>(k * 2));
                 const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) |
-                                    (b_lo0 + static_cast<uint32_t>(tt * (Cfg::B_TILE_BYTES / 16) + k * 2));
-                umma_f16(d_tmem, da, db, idesc, accumulate);
+                                    (b_lo0 + static_cast<uint32_t>(tt * (Cfg::B_TILE_BYTES / B_HALF_DIV / 16) + k * 2));
+                mma(d_tmem, da, db, idesc, accumulate);
                 accumulate = 1u;
               }
             }
             if (b_resident) continue;
-            umma_commit(&bempty_bar[bs]);  // frees the weight stage when its MMAs retire
+            commit(&bempty_bar[bs]);  // frees the weight stage when its MMAs retire
             if (++bs == Cfg::B_STAGES) {
               bs = 0;
               bphase ^= 1u;
@@ -331,16 +410,16 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + static_cast<uint32_t>(k * 2));
             const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + static_cast<uint32_t>(k * 2));
-            umma_f16(d_tmem, da, db, idesc, accumulate);
+            mma(d_tmem, da, db, idesc, accumulate);
             accumulate = 1u;
           }
-          umma_commit(&bempty_bar[bs]);
+          commit(&bempty_bar[bs]);
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;
           }
         }
-        umma_commit(&aempty_bar[as]);  // ... and the patch after its last tap
+        commit(&aempty_bar[as]);  // ... and the patch after its last tap
         if (dual_issue) {
           aphase ^= 1u;   // this issuer's own patch stage, next use
         } else if (++as == Cfg::HALO_STAGES) {
@@ -364,23 +443,24 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = (static_cast<uint64_t>(a_hi2) << 32) | (a_lo0 + static_cast<uint32_t>(k * 2));
             const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + static_cast<uint32_t>(k * 2));
-            umma_f16(d2_tmem, da, db, idesc2, acc2);
+            mma(d2_tmem, da, db, idesc2, acc2);
             acc2 = 1u;
           }
-          umma_commit(&bempty_bar[bs]);
+          commit(&bempty_bar[bs]);
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;
           }
-          umma_commit(&aempty_bar[as]);
+          commit(&aempty_bar[as]);
           if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
           }
         }
       }
-      umma_commit(&tfull_bar[ts]);  // accumulator(s) complete
-      NST_STAMP(3, tile == blockIdx.x);
+      commit(&tfull_bar[ts]);  // accumulator(s) complete
+      NST_STAMP(3, tile == worker);
+      if (NST_TL_PTR(p) != nullptr && tile + tile_step >= num_items) atomicMax(&NST_TL_PTR(p)[6], globaltimer_ns());
       if (dual_issue) {
         tphase ^= 1u;     // this issuer's own accumulator stage, next use
       } else if (++ts == 2) {
@@ -426,10 +506,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     DgradAux aux_nxt;
     float gp[3] = {0.f, 0.f, 0.f}, gp_x[3] = {0.f, 0.f, 0.f};
     auto coords = [&](int tile_, int& h_, int& w_, int& n0_, bool& valid_) {
-      const int nt_ = tile_ / sp_tiles;
-      const int sp_ = tile_ - nt_ * sp_tiles;
-      const int th_ = sp_ / p.tiles_w;
-      const int tw_ = sp_ - th_ * p.tiles_w;
+      int nt_, th_, tw_;
+      item_coords(tile_, nt_, th_, tw_);
       h_ = th_ * TILE_H + hl;
       w_ = tw_ * TILE_W + wl;
       n0_ = nt_ * BLOCK_N;
@@ -453,9 +531,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
     };
     if constexpr (XT) {
-      if (static_cast<int>(blockIdx.x) < p.num_tiles) request(blockIdx.x, aux, gp);
+      if (worker < num_items) request(worker, aux, gp);
     }
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;   // the leader's barriers (8 bytes apart)
+    for (int tile = worker; tile < num_items; tile += workers) {
       int h, w, n0;
       bool valid;
       coords(tile, h, w, n0, valid);
@@ -466,13 +545,14 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
       }
       if constexpr (XT) {
-        if (tile + static_cast<int>(gridDim.x) < p.num_tiles) request(tile + gridDim.x, aux_x, gp_x);
+        if (tile + workers < num_items) request(tile + workers, aux_x, gp_x);
       } else if constexpr (MODE == CONV_DGRAD) {
         request(tile, aux, gp);
       }
       NST_WAIT(wacc0, mbar_wait(&tfull_bar[ts], tphase));
       tc_fence_after();
-      NST_STAMP(4, threadIdx.x == 128 && tile == blockIdx.x);
+      NST_STAMP(4, threadIdx.x == 128 && tile == worker);
+      if (NST_TL_PTR(p) != nullptr && threadIdx.x == 128 && tile + workers >= num_items) atomicMax(&NST_TL_PTR(p)[3], globaltimer_ns());
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * BLOCK_N + col0);
       if constexpr (MODE == CONV_DGRAD_PIX) {
@@ -557,8 +637,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
       tc_fence_before();
       __syncwarp();
-      NST_STAMP(5, threadIdx.x == 128 && tile == blockIdx.x);
-      if (lane == 0) mbar_arrive(&tempty_bar[ts]);
+      NST_STAMP(5, threadIdx.x == 128 && tile == worker);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(ts) * 8u);
+        else mbar_arrive(&tempty_bar[ts]);
+      }
       if (++ts == 2) {
         ts = 0;
         tphase ^= 1u;
@@ -569,10 +652,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   if (dbg && threadIdx.x == 128) NST_DBG_PTR(p)[11] = wacc0;
   if (TMA_OUT && warp >= 4 && lane == 0) bulk_wait_all();  // the staging buffers must outlive the stores reading them
   tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may leave (shared memory, barriers, tensor memory) while the other still refers to it
+  if constexpr (PAIR) cluster_sync_relaxed(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, MODE == CONV_DGRAD ? Cfg::TMEM_COLS_SEED : Cfg::TMEM_COLS);
   }
   NST_STAMP(6, threadIdx.x == 64);
   if (NST_DBG_PTR(p) != nullptr && threadIdx.x == 64) NST_DBG_PTR(p)[16 + blockIdx.x] = clock64() - life0;  // lifetime of every CTA
@@ -630,12 +715,24 @@ int conv_taps_per_stage(int block_n, int taps) {
   return block_n >= 256 ? ConvCfg<256>::TPS : (block_n >= 128 ? ConvCfg<128>::TPS : (block_n >= 64 ? ConvCfg<64>::TPS : ConvCfg<16>::TPS));
 }
 
-int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n) {
+bool conv_use_pair(int mode, int block_n, int taps, int K, int N) {
+  // NST_PAIR: 0 = never; otherwise a bit mask: bit 0 forward, bit 1 data gradient, bit 2 also the forward layers whose whole
+  // weight set stays resident (one 64-channel slice, one N tile: conv1_2).  Those are bound by their epilogue, not by the
+  // operand stream, and lose as a pair (two CTAs in lock step per tile: 34.7 vs 31.9 us inside the step at 512^2).
+  static const int mask = getenv("NST_PAIR") ? atoi(getenv("NST_PAIR")) : 7;
+  if (taps != 9 || (block_n != 64 && block_n != 128)) return false;
+  if (mode == CONV_FWD) return (mask & 1) != 0 && ((mask & 4) != 0 || !(K == BLOCK_K && N == block_n));
+  if (mode == CONV_DGRAD) return (mask & 2) != 0;
+  return false;
+}
+
+int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n, bool pair) {
   auto fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(taps)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(N) * K * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_n),
+  // a CTA of a pair loads half of the N tile's rows per stage
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(pair ? box_n / 2 : box_n),
                        static_cast<cuuint32_t>(conv_taps_per_stage(box_n, taps))};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -678,13 +775,20 @@ void conv_finalize_params(ConvParams& p, int mode) {
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_n = p.N / bn;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  p.idesc = umma_idesc_f16(BLOCK_M, bn, (mode == CONV_DGRAD || mode == CONV_DGRAD_PIX) ? 1 : 0, 0, 0);
+  p.idesc = umma_idesc_f16(p.pair ? 2 * BLOCK_M : BLOCK_M, bn, (mode == CONV_DGRAD || mode == CONV_DGRAD_PIX) ? 1 : 0, 0, 0);
 }
 
-template <int BLOCK_N, int MODE, bool TMA_OUT>
+int conv_grid_ctas(const ConvParams& p, int num_sms) {
+  if (!p.pair) return p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const int items = ((p.tiles_w * p.tiles_h + 1) / 2) * p.tiles_n;
+  const int pairs = items < num_sms / 2 ? items : num_sms / 2;
+  return 2 * pairs;
+}
+
+template <int BLOCK_N, int MODE, bool TMA_OUT, bool PAIR>
 static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const int grid = conv_grid_ctas(p, num_sms);
   static const bool pdl = getenv("NST_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -694,29 +798,56 @@ static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t s
   // live on L1 hits (34 KB less L1 cost conv1_2's data gradient 17 us inside the step)
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES - (TMA_OUT ? 0 : Cfg::EPI_BYTES);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, TMA_OUT>, p);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, TMA_OUT, PAIR>, p);
+}
+template <int BLOCK_N, int MODE, bool TMA_OUT>
+static cudaError_t launch_one_p(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  if constexpr ((MODE == CONV_FWD || MODE == CONV_DGRAD) && (BLOCK_N == 64 || BLOCK_N == 128)) {
+    if (p.pair) return launch_one_t<BLOCK_N, MODE, TMA_OUT, true>(p, num_sms, stream);
+  }
+  if (p.pair) return cudaErrorInvalidValue;
+  return launch_one_t<BLOCK_N, MODE, TMA_OUT, false>(p, num_sms, stream);
 }
 template <int BLOCK_N, int MODE>
 static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   if constexpr (MODE == CONV_DGRAD_PIX) {
-    return launch_one_t<BLOCK_N, MODE, false>(p, num_sms, stream);
+    return launch_one_p<BLOCK_N, MODE, false>(p, num_sms, stream);
   } else {
-    return p.tma_out ? launch_one_t<BLOCK_N, MODE, true>(p, num_sms, stream) : launch_one_t<BLOCK_N, MODE, false>(p, num_sms, stream);
+    return p.tma_out ? launch_one_p<BLOCK_N, MODE, true>(p, num_sms, stream) : launch_one_p<BLOCK_N, MODE, false>(p, num_sms, stream);
   }
 }
 
 template <int BLOCK_N, int MODE>
 static cudaError_t init_one() {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ConvCfg<BLOCK_N>::SMEM_BYTES);
   if constexpr (MODE != CONV_DGRAD_PIX) {
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<BLOCK_N>::SMEM_BYTES);
+  }
+  if constexpr ((MODE == CONV_FWD || MODE == CONV_DGRAD) && (BLOCK_N == 64 || BLOCK_N == 128)) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<BLOCK_N>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<BLOCK_N>::SMEM_BYTES);
   }
   return e;

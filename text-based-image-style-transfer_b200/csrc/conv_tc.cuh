@@ -59,6 +59,8 @@ struct ConvParams {
   int block_n;     // N tile: 64, 128 or 256 (conv_block_n)
   int tiles_w, tiles_h, tiles_n, num_tiles;
   uint32_t idesc;
+  int pair;        // != 0: the launch runs as CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): conv_use_pair; set BEFORE
+                   // make_tmap_wgt (the weight box is half an N tile) and conv_finalize_params (instruction descriptor)
   int dual_issue;  // != 0: one-slice layers with resident weights are issued by two threads (conv_tc.cu); NST_SINGLE_ISSUE clears it
   // ---- CONV_FWD
   const float* bias;   // [N]
@@ -93,7 +95,11 @@ struct ConvParams {
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
 int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
-int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n);
+int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n, bool pair = false);
+// whether a launch of this mode / N tile / filter size runs as CTA pairs (NST_PAIR=0 turns them off)
+bool conv_use_pair(int mode, int block_n, int taps, int K, int N);
+// CTAs of the launch (persistent: at most one per SM; pairs: an even number)
+int conv_grid_ctas(const ConvParams& p, int num_sms);
 // output map for the epilogue's TMA stores: [H][W][C] 16-bit tensor, box (box_c, box_w, box_h); box_c * 2 = 128, 64 or 32 bytes
 int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h);
 // filter taps the kernel loads per weight stage for this N tile (the depth of the weight tensor map's box)
