@@ -225,6 +225,26 @@ int nst_run_frame_host(nst_plan* plan, const uint8_t* content_u8, uint8_t* out_u
 int nst_run_frames_host(nst_plan* const* plans, int count, const uint8_t* const* content_u8, uint8_t* const* out_u8, int num_steps,
                         int channel_attention, const float* ca_w1, const float* ca_w2, void* const* streams, int* closure_calls);
 
+/* ---- several images per launch (SURVEY 8 f row 2: "batch dimension b > 1 in conv / Gram") -------------------------------------
+ * The reference evaluates one image per call; its gram_matrix already normalises by the batch size b
+ * (multi_style_transfer/style_transfer_losses.py:84-93) and apply_video_process (app.py:784-815) runs the same loop on
+ * independent frames.  nst_batch_create makes a HEAD plan for `batch` (2..8) images of H x W (multiples of 16) plus `batch`
+ * MEMBER plans: the head owns every tensor the tcgen05 convolution / Gram / Gram-backward launches touch as [batch][...] arrays
+ * and processes all images in ONE launch each; the members are ordinary single-image plans over their slices and carry what is
+ * per image (targets, pixel-space losses, conv1_1, the L-BFGS state).  Set targets / initialise / read status, trace and result
+ * through the members (nst_batch_member); set norm / weights on the head (forwarded); step with nst_lbfgs_step(head): one CUDA
+ * graph per optimizer.step() of all members.  nst_plan_destroy(head) destroys the members. */
+int nst_batch_create(nst_plan** head_out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
+                     uint32_t content_mask, int batch);
+int nst_batch_size(const nst_plan* plan);                 /* images per launch: `batch` for a head, 1 otherwise */
+nst_plan* nst_batch_member(nst_plan* head, int index);    /* NULL + nst_last_error() when out of range */
+/* frozen != 0: the member sits out the following nst_lbfgs_step(head) calls (its own loop has ended, run_style_transfer.py:100,
+ * while other members still run); cleared by nst_lbfgs_init.  Asynchronous on `stream`. */
+int nst_lbfgs_freeze(nst_plan* member, int frozen, void* stream);
+/* nst_run_frames_host for a head: frame k (k < count <= batch) on member k, host uint8 in / out, copies inside. */
+int nst_run_batch_host(nst_plan* head, int count, const uint8_t* const* content_u8, uint8_t* const* out_u8, int num_steps,
+                       int channel_attention, const float* ca_w1, const float* ca_w2, void* stream, int* closure_calls);
+
 /* ---- mask compositing: text/segmentation_style_transfer.py:5-94 (segmentation_style_transfer + _edge_smoothing), the step that
  * follows run_multi_style_transfer in app.py:203,318,407,512.  content, style, out: [H][W][C] uint8 device buffers (C <= 4),
  * mask: [H][W] bytes (non-zero = stylised pixel).  edge_smoothing = 0 selects (np.where, :52); otherwise the mask is blurred

@@ -219,6 +219,18 @@ struct nst_plan {
   float* pooled_dev = nullptr;
   // seed_folded[i]: the Gram backward of style layer conv i runs inside the data gradient of conv i+1 (no launch of its own)
   bool seed_folded[NST_MAX_CONV] = {};
+  // ---- several images per launch (nst_batch_create).  The HEAD (batch > 1) owns the tensors the convolution and
+  // Gram launches touch - taps, activations, routing bytes, gradients, seeds, Gram targets / backward operands / scalars - as
+  // [batch][...] arrays and the parameter sets that process all images in one launch each.  Its MEMBERS (head != nullptr) are
+  // ordinary single-image plans whose pointers to those tensors are slices of the head's: image `index`.  Everything per
+  // image - pixel-space losses, content loss, loss assembly, conv1_1 (fp32 planar image on either side), the optimizer and
+  // its history - runs per member; a member is also usable on its own (targets from the content frame, status, trace).
+  int batch = 1;
+  nst_plan* head = nullptr;
+  int index = 0;
+  std::vector<nst_plan*> members;
+  int style_fin_stride[GRAM_MAX_LAYERS] = {};         // head: per-image distance inside fin_part of the layer's Gram set
+  int style_fin_stride_narrow[GRAM_MAX_LAYERS] = {};
 #ifdef NST_INSTRUMENT
   unsigned long long* timeline = nullptr;  // [48][8] launch spans of the conv kernels (nst_plan_timeline)
   bool timeline_on = false;
@@ -251,6 +263,8 @@ static void drop_graph(nst_plan* p) {
 
 extern "C" void nst_plan_destroy(nst_plan* p) {
   if (!p) return;
+  for (nst_plan* m : p->members) nst_plan_destroy(m);
+  p->members.clear();
   drop_graph(p);
   if (p->side) cudaStreamDestroy(p->side);
   if (p->side2) cudaStreamDestroy(p->side2);
@@ -299,6 +313,7 @@ static int build_conv_params(nst_plan* p) {
       f.tma_out = 1;
     }
   }
+  const int B = p->batch;   // head: every launch below covers B images ([B][H][W][C] tensors, stacked view B * H rows for outputs)
   for (int i = 1; i < p->n_layers; ++i) {
     const int lv = kLevel[i];
     const int H = p->lh[lv], W = p->lw[lv];
@@ -311,8 +326,9 @@ static int build_conv_params(nst_plan* p) {
     f.K = kCin[i];
     f.N = kCout[i];
     f.taps = 9;
-    if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
-    f.block_n = conv_block_n(kCout[i], H, W, 9 * kCin[i], g_num_sms);
+    f.batch = B;
+    if (make_tmap_act(&f.tmA, p->act[i - 1], H, W, kCin[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2, B) != 0) return fail(NST_ERR_CUDA, "tensor map (act %d)", i);
+    f.block_n = conv_block_n(kCout[i], H * B, W, 9 * kCin[i], g_num_sms);
     f.pair = conv_use_pair(CONV_FWD, f.block_n, 9, kCin[i], kCout[i]) ? 1 : 0;
     if (make_tmap_wgt(&f.tmB, net->wf[i], 9, kCout[i], kCin[i], f.block_n, f.pair != 0) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights %d)", i);
@@ -323,8 +339,8 @@ static int build_conv_params(nst_plan* p) {
     f.pool = pooled ? 1 : 0;
     conv_finalize_params(f, CONV_FWD);
     if (tma_out) {
-      if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out %d)", i);
-      if (!pooled && f.out_act && make_tmap_out(&f.tmO1, f.out_act, H, W, kCout[i], 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (act out %d)", i);
+      if (f.out_tap && make_tmap_out(&f.tmO0, f.out_tap, H, W, kCout[i], 32, CONV_TILE_W, 4, B) != 0) return fail(NST_ERR_CUDA, "tensor map (tap out %d)", i);
+      if (!pooled && f.out_act && make_tmap_out(&f.tmO1, f.out_act, H, W, kCout[i], 32, CONV_TILE_W, 4, B) != 0) return fail(NST_ERR_CUDA, "tensor map (act out %d)", i);
       f.tma_out = 1;
     }
     if (!p->with_grad) continue;
@@ -336,8 +352,9 @@ static int build_conv_params(nst_plan* p) {
     d.K = kCout[i];
     d.N = kCin[i];
     d.taps = 9;
-    if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
-    d.block_n = conv_block_n(kCin[i], H, W, 9 * kCout[i], g_num_sms);
+    d.batch = B;
+    if (make_tmap_act(&d.tmA, p->gpre[i], H, W, kCout[i], 64, CONV_TILE_W + 2, CONV_TILE_H + 2, B) != 0) return fail(NST_ERR_CUDA, "tensor map (grad %d)", i);
+    d.block_n = conv_block_n(kCin[i], H * B, W, 9 * kCout[i], g_num_sms);
     d.pair = conv_use_pair(CONV_DGRAD, d.block_n, 9, kCout[i], kCin[i]) ? 1 : 0;
     if (make_tmap_wgt(&d.tmB, net->wb[i], 9, kCin[i], kCout[i], d.block_n, d.pair != 0) != 0)
       return fail(NST_ERR_CUDA, "tensor map (weights^T %d)", i);
@@ -356,8 +373,8 @@ static int build_conv_params(nst_plan* p) {
     }
     conv_finalize_params(d, CONV_DGRAD);
     if (tma_out) {
-      const int rc = prev_pooled ? make_tmap_out(&d.tmO0, d.out_grad, d.Hup, d.Wup, kCin[i], 16, 2 * CONV_TILE_W, 8)
-                                 : make_tmap_out(&d.tmO0, d.out_grad, H, W, kCin[i], 32, CONV_TILE_W, 4);
+      const int rc = prev_pooled ? make_tmap_out(&d.tmO0, d.out_grad, d.Hup, d.Wup, kCin[i], 16, 2 * CONV_TILE_W, 8, B)
+                                 : make_tmap_out(&d.tmO0, d.out_grad, H, W, kCin[i], 32, CONV_TILE_W, 4, B);
       if (rc != 0) return fail(NST_ERR_CUDA, "tensor map (grad out %d)", i);
       // Measured (profiles/r01_conv_phases_tma_store.log, r01_timeline_512_tma_store.log): data gradients keep their direct
       // 16-byte stores.  The plain masked gradient gains nothing from the TMA store (conv1_2: 40 -> 50 us).  The pool-routing
@@ -396,14 +413,17 @@ static int build_conv_params(nst_plan* p) {
     c.K = C;
     c.N = C;
     c.taps = 1;
-    if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
-    c.block_n = conv_block_n(C, c.H, c.W, C, g_num_sms);
-    if (make_tmap_wgt(&c.tmB, p->dh[l], 1, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
+    c.batch = B;
+    c.b_per_image = 1;                 // dh: [B][C][C], the image in the map's third dimension
+    c.alpha_stride = GRAM_MAX_LAYERS;  // alpha: [B][GRAM_MAX_LAYERS]
+    if (make_tmap_act(&c.tmA, p->tap[i], c.H, c.W, C, 64, CONV_TILE_W, CONV_TILE_H, B) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d)", i);
+    c.block_n = conv_block_n(C, c.H * B, c.W, C, g_num_sms);
+    if (make_tmap_wgt(&c.tmB, p->dh[l], B, C, C, c.block_n) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d)", i);
     c.alpha = p->alpha + l;
     c.out_grad = i == p->n_layers - 1 ? p->gpre[i] : p->gadd[i];
     conv_finalize_params(c, CONV_SCALE);
     if (tma_out) {
-      if (make_tmap_out(&c.tmO0, c.out_grad, c.H, c.W, C, 32, CONV_TILE_W, 4) != 0) return fail(NST_ERR_CUDA, "tensor map (seed out %d)", i);
+      if (make_tmap_out(&c.tmO0, c.out_grad, c.H, c.W, C, 32, CONV_TILE_W, 4, B) != 0) return fail(NST_ERR_CUDA, "tensor map (seed out %d)", i);
       c.tma_out = 1;
     }
   }
@@ -419,8 +439,10 @@ static int build_conv_params(nst_plan* p) {
       ConvParams& d = p->dgrad[i];
       if (d.block_n > 128 || d.route != nullptr) continue;
       const int C = kCout[j];
-      if (make_tmap_act(&d.tmA2, p->tap[j], d.H, d.W, C, 64, CONV_TILE_W, CONV_TILE_H) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d, folded)", j);
-      if (make_tmap_wgt(&d.tmB2, p->dh[l], 1, C, C, d.block_n, d.pair != 0) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
+      if (make_tmap_act(&d.tmA2, p->tap[j], d.H, d.W, C, 64, CONV_TILE_W, CONV_TILE_H, B) != 0) return fail(NST_ERR_CUDA, "tensor map (tap %d, folded)", j);
+      if (make_tmap_wgt(&d.tmB2, p->dh[l], B, C, C, d.block_n, d.pair != 0) != 0) return fail(NST_ERR_CUDA, "tensor map (dh %d, folded)", j);
+      d.b_per_image = 1;
+      d.alpha_stride = GRAM_MAX_LAYERS;
       d.seed_k = C;
       d.idesc2 = umma_idesc_f16(d.pair ? 256 : 128, d.block_n, 0, 0, 0);
       d.alpha = p->alpha + l;
@@ -446,6 +468,7 @@ static int build_gram_params(nst_plan* p) {
     L.HW = p->lh[lv] * p->lw[lv];
     L.inv_norm = 1.f / (static_cast<float>(L.C) * static_cast<float>(L.HW));
     L.target = p->style_target[l];
+    L.target_stride = static_cast<size_t>(L.C) * L.C;   // head: [batch][C][C], one target per image
     L.gram_out = nullptr;   // only G - T's fp16 image (dh) and its sum of squares are consumed
     L.dh = p->dh[l];
     L.dh_scale = p->dh_scale + l;
@@ -453,7 +476,7 @@ static int build_gram_params(nst_plan* p) {
     // d/dF of w_s/n_style * mean((G-T)^2), G = F F^T / (C HW): 4 w_s (G-T) F / (n_style C^3 HW)
     L.grad_coef = 4.f * p->w_style / (static_cast<float>(p->n_style) * static_cast<float>(L.C) *
                                       static_cast<float>(L.C) * static_cast<float>(L.C) * static_cast<float>(L.HW));
-    if (make_tmap_feat(&g.tm[k], p->tap[i], L.HW, L.C) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
+    if (make_tmap_feat(&g.tm[k], p->tap[i], L.HW, L.C, p->batch) != 0) return fail(NST_ERR_CUDA, "tensor map (gram %d)", i);
   }
   return NST_OK;
 }
@@ -466,6 +489,7 @@ static int build_gram_narrow(nst_plan* p) {
   for (int l = 0; l < GRAM_MAX_LAYERS; ++l) {
     p->style_fin_narrow[l] = p->style_fin[l];
     p->style_fin_n_narrow[l] = p->style_fin_n[l];
+    p->style_fin_stride_narrow[l] = p->style_fin_stride[l];
   }
   const GramParams& wide = p->gram_shallow;
   if (wide.num_layers == 0 || p->side == nullptr || getenv("NST_GRAM_WIDE") != nullptr) return NST_OK;
@@ -485,27 +509,39 @@ static int build_gram_narrow(nst_plan* p) {
   if (idle < 8) return NST_OK;
   GramParams& g = p->gram_shallow_narrow;
   g = wide;
-  const size_t ws = gram_plan(g, idle);
+  const size_t ws = gram_plan(g, idle / p->batch > 0 ? idle / p->batch : 1);
   g.max_ctas = idle;
   float* wsp = nullptr;
   float* fin = nullptr;
-  CKI(plan_alloc_t(p, &wsp, ws));
-  CKI(plan_alloc_t(p, &fin, static_cast<size_t>(g.num_fin_blocks), true));
+  CKI(plan_alloc_t(p, &wsp, ws * p->batch));
+  CKI(plan_alloc_t(p, &fin, static_cast<size_t>(g.num_fin_blocks) * p->batch, true));
   g.ws = wsp;
   g.fin_part = fin;
+  g.ws_img = ws;
   for (int j = 0; j < g.num_layers; ++j) {
     const GramLayer& L = g.L[j];
     for (int q = 0; q < p->n_style; ++q)
       if (p->dh[q] == L.dh) {
         p->style_fin_narrow[q] = fin + L.fin_blk0;
         p->style_fin_n_narrow[q] = L.fused ? L.pairs : L.fin_blocks;
+        p->style_fin_stride_narrow[q] = g.num_fin_blocks;
       }
   }
   return NST_OK;
 }
 
+static int plan_create_impl(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
+                            uint32_t content_mask, int with_grad, int batch, nst_plan* head, int index);
+
 extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
                                uint32_t content_mask, int with_grad) {
+  return plan_create_impl(out, net, H, W, tap_mask, style_mask, content_mask, with_grad, 1, nullptr, 0);
+}
+
+// batch > 1: a head (shared tensors x batch, batched parameter sets, no optimizer state of its own);
+// head != nullptr: member `index` of that head (shared tensors are slices of the head's)
+static int plan_create_impl(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
+                            uint32_t content_mask, int with_grad, int batch, nst_plan* head, int index) {
   if (!out || !net || H < 1 || W < 1) return fail(NST_ERR_ARG, "nst_plan_create: bad arguments");
   CKI(nst_device_check());
   tap_mask |= style_mask | content_mask;
@@ -519,6 +555,17 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
   p->style_mask = style_mask;
   p->content_mask = content_mask;
   p->with_grad = with_grad ? 1 : 0;
+  p->batch = batch;
+  p->head = head;
+  p->index = index;
+  // tensor shared between a head and its members: the head allocates it for all images, a member takes its slice
+  auto shared = [&](auto** ptr, auto* head_field, size_t count, bool zero) -> int {
+    if (head != nullptr) {
+      *ptr = head_field + static_cast<size_t>(index) * count;
+      return NST_OK;
+    }
+    return plan_alloc_t(p, ptr, count * static_cast<size_t>(batch), zero);
+  };
   int n_layers = 0;
   for (int i = 0; i < NST_MAX_CONV; ++i)
     if (tap_mask & (1u << i)) n_layers = i + 1;
@@ -570,32 +617,33 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     const int C = kCout[i];
     const bool last = i == n_layers - 1;
     const bool pooled = kPoolAfter[i] && !last;
-    if (tap_mask & (1u << i)) PA(plan_alloc_t(p, &p->tap[i], pix * C));
+    if (tap_mask & (1u << i)) PA(shared(&p->tap[i], head ? head->tap[i] : nullptr, pix * C, false));
     if (!last) {
       const size_t opix = pooled ? static_cast<size_t>(p->lh[lv + 1]) * p->lw[lv + 1] : pix;
-      PA(plan_alloc_t(p, &p->act[i], opix * C));
-      if (pooled) PA(plan_alloc_t(p, &p->route[i], opix * C));
+      PA(shared(&p->act[i], head ? head->act[i] : nullptr, opix * C, false));
+      if (pooled) PA(shared(&p->route[i], head ? head->route[i] : nullptr, opix * C, false));
     }
     if (with_grad) {
-      PA(plan_alloc_t(p, &p->gpre[i], pix * C, true));
-      if (((style_mask | content_mask) & (1u << i)) && !last) PA(plan_alloc_t(p, &p->gadd[i], pix * C, true));
+      PA(shared(&p->gpre[i], head ? head->gpre[i] : nullptr, pix * C, true));
+      if (((style_mask | content_mask) & (1u << i)) && !last) PA(shared(&p->gadd[i], head ? head->gadd[i] : nullptr, pix * C, true));
     }
   }
   // ---- style / content / pixel state
-  PA(plan_alloc_t(p, &p->alpha, GRAM_MAX_LAYERS, true));
-  PA(plan_alloc_t(p, &p->dh_scale, GRAM_MAX_LAYERS, true));
+  PA(shared(&p->alpha, head ? head->alpha : nullptr, GRAM_MAX_LAYERS, true));
+  PA(shared(&p->dh_scale, head ? head->dh_scale : nullptr, GRAM_MAX_LAYERS, true));
   {
     const float ones[GRAM_MAX_LAYERS] = {1.f, 1.f, 1.f, 1.f, 1.f};   // until nst_plan_set_style_target derives it from the target
-    if (cudaMemcpy(p->dh_scale, ones, sizeof(ones), cudaMemcpyHostToDevice) != cudaSuccess) {
-      nst_plan_destroy(p);
-      return fail(NST_ERR_CUDA, "cudaMemcpy (operand scales)");
-    }
+    for (int b = 0; b < (head ? 1 : batch); ++b)
+      if (cudaMemcpy(p->dh_scale + b * GRAM_MAX_LAYERS, ones, sizeof(ones), cudaMemcpyHostToDevice) != cudaSuccess) {
+        nst_plan_destroy(p);
+        return fail(NST_ERR_CUDA, "cudaMemcpy (operand scales)");
+      }
   }
   PA(plan_alloc_t(p, &p->losses, NST_LOSS_COUNT, true));
   for (int l = 0; l < p->n_style; ++l) {
     const size_t cc = static_cast<size_t>(kCout[p->style_conv[l]]) * kCout[p->style_conv[l]];
-    PA(plan_alloc_t(p, &p->style_target[l], cc, true));
-    PA(plan_alloc_t(p, &p->dh[l], cc, true));
+    PA(shared(&p->style_target[l], head ? head->style_target[l] : nullptr, cc, true));
+    PA(shared(&p->dh[l], head ? head->dh[l] : nullptr, cc, true));
   }
   int cpart = 0;
   for (int l = 0; l < p->n_content; ++l) {
@@ -618,14 +666,18 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
     for (int k = 0; k < 2; ++k) {
       if (sets[k]->num_layers == 0) continue;
       // the side-stream set shares the SMs with the forward convolutions of the deeper layers: plan it for all
-      // SMs anyway (its CTAs run wherever a conv tile is not resident)
-      const size_t ws = gram_plan(*sets[k], g_num_sms);
+      // SMs anyway (its CTAs run wherever a conv tile is not resident); a head's item list runs once per image
+      const int share = g_num_sms / batch > 0 ? g_num_sms / batch : 1;
+      const size_t ws = gram_plan(*sets[k], share);
       float* wsp = nullptr;
       float* fin = nullptr;
-      PA(plan_alloc_t(p, &wsp, ws));
-      PA(plan_alloc_t(p, &fin, static_cast<size_t>(sets[k]->num_fin_blocks), true));
+      PA(plan_alloc_t(p, &wsp, ws * batch));
+      PA(plan_alloc_t(p, &fin, static_cast<size_t>(sets[k]->num_fin_blocks) * batch, true));
       sets[k]->ws = wsp;
       sets[k]->fin_part = fin;
+      sets[k]->batch = batch;
+      sets[k]->ws_img = ws;
+      sets[k]->scal_stride = GRAM_MAX_LAYERS;
       // where the loss assembly finds each style layer's per-block sums
       for (int j = 0; j < sets[k]->num_layers; ++j) {
         const GramLayer& L = sets[k]->L[j];
@@ -634,6 +686,7 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
           if (p->dh[q] == L.dh) l = q;
         p->style_fin[l] = fin + L.fin_blk0;
         p->style_fin_n[l] = L.fused ? L.pairs : L.fin_blocks;
+        p->style_fin_stride[l] = sets[k]->num_fin_blocks;
       }
     }
   }
@@ -654,8 +707,8 @@ extern "C" int nst_plan_create(nst_plan** out, const nst_net* net, int H, int W,
       p->side2 = nullptr;
     }
   }
-  // ---- optimizer
-  if (with_grad) {
+  // ---- optimizer (a head has none: its members optimise)
+  if (with_grad && batch == 1) {
     LbfgsBuffers& b = p->lb;
     b.n_pad = static_cast<int>((n + 3) / 4 * 4);
     lbfgs_plan(b, g_num_sms);
@@ -687,11 +740,13 @@ extern "C" int nst_plan_set_norm(nst_plan* p, const float mean[3], const float s
     p->pc.stdv[c] = std[c];
   }
   drop_graph(p);
+  for (nst_plan* m : p->members) CKI(nst_plan_set_norm(m, mean, std));
   return NST_OK;
 }
 
 extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content, float w_tv, float w_edge) {
   if (!p) return fail(NST_ERR_ARG, "nst_plan_set_weights: null plan");
+  for (nst_plan* m : p->members) CKI(nst_plan_set_weights(m, w_style, w_content, w_tv, w_edge));
   p->w_style = w_style;
   p->w_content = w_content;
   p->w_tv = w_tv;
@@ -955,11 +1010,25 @@ struct LaunchTimer {
 // only feeds it sideways (pixel-space losses, Gram + finalize + Gram-backward seeds of the shallower style layers,
 // content loss, loss assembly) runs on the side stream and fills the SMs that layers with fewer than 148 tiles
 // leave idle.  Under stream capture this becomes parallel branches of the CUDA graph.
+//
+// A head (p->batch > 1, nst_batch_create) enqueues the same DAG for all its members: the convolution, Gram and Gram-backward
+// launches once for every image (the head's parameter sets), the per-image kernels once per member on the member's buffers
+// - x, grad, counter and stop_flag are then the members' optimizer buffers and the arguments are ignored (grad != nullptr
+// still selects the backward pass).
 static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, const int* stop_flag, int* launches,
                         cudaStream_t s, LaunchTimer* tm = nullptr) {
   int nl = 0;
   const bool use_vgg = (p->w_style > 0.f && p->n_style > 0) || (p->w_content > 0.f && p->n_content > 0);
   if (grad != nullptr && !p->with_grad) return fail(NST_ERR_STATE, "plan was created without gradient buffers");
+  const bool is_head = p->batch > 1;
+  if (is_head && (tm != nullptr || static_cast<int>(p->members.size()) != p->batch))
+    return fail(NST_ERR_STATE, "a batch head evaluates through its members and is not timed per launch");
+  // the plans that own the per-image state: the plan itself, or the members of a head
+  nst_plan* const self[1] = {p};
+  nst_plan* const* img = is_head ? p->members.data() : self;
+  const int n_img = is_head ? p->batch : 1;
+  auto img_x = [&](int m) -> const float* { return is_head ? img[m]->lb.x : x; };
+  auto img_grad = [&](int m) -> float* { return is_head ? img[m]->lb.g : grad; };
   TB(NST_K_START);
   TM(NST_K_START, -1);
   const bool conc = tm == nullptr && p->side != nullptr && use_vgg;
@@ -1016,25 +1085,35 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   auto content_launch = [&](int l, int accumulate, cudaStream_t st) -> cudaError_t {
     const int i = p->content_conv[l];
     const size_t numel = static_cast<size_t>(p->lh[kLevel[i]]) * p->lw[kLevel[i]] * kCout[i];
-    // seed of the backward pass: d/dF of w_c/n_content * mean((F - Fc)^2).  A conv that is both a style and a
-    // content layer gets its Gram seed first, then this one in accumulate mode.
-    __nv_bfloat16* seed = nullptr;
-    if (grad != nullptr && (accumulate || style_index(p, i) < 0)) seed = i == last ? p->gpre[i] : p->gadd[i];
     const float gcoef = 2.f * p->w_content / (static_cast<float>(numel) * static_cast<float>(p->n_content));
-    return launch_content_loss(p->tap[i], p->content_target[l], seed, p->content_part + p->content_part_off[l], numel, gcoef,
-                               accumulate, st);
+    for (int m = 0; m < n_img; ++m) {
+      nst_plan* q = img[m];
+      // seed of the backward pass: d/dF of w_c/n_content * mean((F - Fc)^2).  A conv that is both a style and a
+      // content layer gets its Gram seed first, then this one in accumulate mode.
+      __nv_bfloat16* seed = nullptr;
+      if (grad != nullptr && (accumulate || style_index(p, i) < 0)) seed = i == last ? q->gpre[i] : q->gadd[i];
+      cudaError_t e = launch_content_loss(q->tap[i], q->content_target[l], seed, q->content_part + q->content_part_off[l], numel,
+                                          gcoef, accumulate, st);
+      if (e != cudaSuccess) return e;
+    }
+    nl += n_img - 1;   // the callers count one launch
+    return cudaSuccess;
   };
 
   // ---- side: pixel-space terms
   CK(edge(EV_FORK, s, s2));
   TB(NST_K_PIXEL);
-  CK(launch_pixel_losses(x, p->tedge, p->grad_pix, p->tv_part, p->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
-  ++nl;
+  for (int m = 0; m < n_img; ++m) {
+    nst_plan* q = img[m];
+    CK(launch_pixel_losses(img_x(m), q->tedge, q->grad_pix, q->tv_part, q->edge_part, p->H, p->W, p->pc, p->w_tv, p->w_edge, s2));
+    ++nl;
+  }
   TM(NST_K_PIXEL, -1);
   if (use_vgg) {
-    // ---- main: VGG forward
+    // ---- main: VGG forward (conv1_1 reads the fp32 planar image of each member)
     TB(NST_K_CONV1_FWD);
-    CK(conv1_forward(p, x, s));
+    for (int m = 0; m < n_img; ++m) CK(conv1_forward(img[m], img_x(m), s));
+    nl += n_img - 1;
     TM(NST_K_CONV1_FWD, 0);
     if (max_content == 0) CK(edge(EV_CONTENT_IN, s, s2));
     for (int i = 1; i < p->n_layers; ++i) {
@@ -1127,18 +1206,23 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     shallow_joined = true;
   }
   CK(edge(EV_GRAM, s, s2));
+  TB(NST_K_ASSEMBLE);
+  for (int m = 0; m < n_img; ++m) {
+  nst_plan* q = img[m];
   LossAssembleArgs a;
   memset(&a, 0, sizeof(a));
-  a.tv_part = p->tv_part;
+  a.tv_part = q->tv_part;
   a.n_tv = pixel_blocks(p->H, p->W);
-  a.edge_part = p->edge_part;
+  a.edge_part = q->edge_part;
   a.n_edge = pixel_blocks(p->H, p->W);
-  a.content_part = p->content_part;
+  a.content_part = q->content_part;
   a.n_content = use_vgg ? p->content_part_off[p->n_content] : 0;
   a.num_style = use_vgg ? p->n_style : 0;
   for (int l = 0; l < p->n_style; ++l) {
     const double c = kCout[p->style_conv[l]];
-    a.style_fin[l] = narrow ? p->style_fin_narrow[l] : p->style_fin[l];
+    // the Gram launches are the head's: image m's per-block sums follow image m - 1's inside each set
+    a.style_fin[l] = narrow ? p->style_fin_narrow[l] + static_cast<size_t>(m) * p->style_fin_stride_narrow[l]
+                            : p->style_fin[l] + static_cast<size_t>(m) * p->style_fin_stride[l];
     a.style_fin_n[l] = narrow ? p->style_fin_n_narrow[l] : p->style_fin_n[l];
     a.style_inv_cc[l] = static_cast<float>(1.0 / (c * c));
   }
@@ -1150,14 +1234,14 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
   a.edge_norm = (p->H > 2 && p->W > 2) ? 1.0 / (static_cast<double>(p->H - 2) * (p->W - 2)) : 0.0;
   // mean over the content layers of the per-layer MSEs; each layer's partial sums are already divided by its own numel
   if (p->n_content > 0) a.content_norm = 1.0 / p->n_content;
-  a.out = p->losses;
-  a.counter = counter;
-  a.stop_flag = stop_flag;
-  a.trace = p->trace;
-  a.trace_cap = p->trace_cap;
-  TB(NST_K_ASSEMBLE);
+  a.out = q->losses;
+  a.counter = is_head ? &q->lb.ctl->closure_calls : counter;
+  a.stop_flag = is_head ? &q->lb.ctl->stop : stop_flag;
+  a.trace = q->trace;
+  a.trace_cap = q->trace_cap;
   CK(launch_loss_assemble(a, s2));
   ++nl;
+  }
   TM(NST_K_ASSEMBLE, -1);
   if (conc) CK(cudaEventRecord(p->ev[EV_JOIN], s2));
   // ---- main: backward chain
@@ -1189,22 +1273,28 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       {
         static const bool cuda_core_conv1 = getenv("NST_CONV1_CUDA_CORES") != nullptr;
         if (cuda_core_conv1) {
+          if (is_head) return fail(NST_ERR_UNSUPPORTED, "NST_CONV1_CUDA_CORES with a batch head");
           TB(NST_K_CONV1_DGRAD);
           CK(launch_conv1_dgrad(p->gpre[0], p->net->w32[0], p->grad_pix, grad, p->H, p->W, p->pc, s));
         } else {
-          ConvParams d = p->dgrad[0];
-          d.out_pix = grad;
-          for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
           TB(NST_K_CONV1_DGRAD);
-          CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
+          for (int m = 0; m < n_img; ++m) {
+            ConvParams d = img[m]->dgrad[0];
+            d.out_pix = img_grad(m);
+            for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
+            CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
+          }
+          nl += n_img - 1;
         }
       }
       ++nl;
       TM(NST_K_CONV1_DGRAD, 0);
     } else {
-      CK(cudaMemcpyAsync(grad, p->grad_pix, static_cast<size_t>(3) * p->H * p->W * sizeof(float),
-                         cudaMemcpyDeviceToDevice, s));
-      ++nl;
+      for (int m = 0; m < n_img; ++m) {
+        CK(cudaMemcpyAsync(img_grad(m), img[m]->grad_pix, static_cast<size_t>(3) * p->H * p->W * sizeof(float),
+                           cudaMemcpyDeviceToDevice, s));
+        ++nl;
+      }
     }
   } else if (conc) {
     CK(cudaStreamWaitEvent(s, p->ev[EV_JOIN], 0));
@@ -1537,9 +1627,16 @@ __global__ void lbfgs_ctl_reset_kernel(NstLbfgsCtl* c, int trace_cap) {
   c->trace_cap = trace_cap;
 }
 
+#define NOT_A_HEAD(p, who)                                                                                                   \
+  do {                                                                                                                       \
+    if ((p)->batch > 1) return fail(NST_ERR_STATE, who ": a batch head has no optimizer state of its own - use its members"); \
+  } while (0)
+
 extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, void* stream) {
   if (!p || !x0) return fail(NST_ERR_ARG, "nst_lbfgs_init: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  NOT_A_HEAD(p, "nst_lbfgs_init");
+  if (p->head != nullptr && trace_capacity > p->trace_cap) drop_graph(p->head);  // the trace pointer is baked into the head's graph too
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   LbfgsBuffers& b = p->lb;
   const size_t n = static_cast<size_t>(3) * p->H * p->W;
@@ -1571,6 +1668,9 @@ extern "C" int nst_lbfgs_init(nst_plan* p, const float* x0, int trace_capacity, 
 #ifdef NST_INSTRUMENT
 static void timeline_arm(nst_plan* p, bool on) {
   for (int i = 0; i < p->n_layers; ++i) {
+    // NST_TL_FLAGS: the wrong-result timing experiments of ConvParams::dbg_flags for the launches of the traced evaluation
+    static const int tl_flags = getenv("NST_TL_FLAGS") ? atoi(getenv("NST_TL_FLAGS")) : 0;
+    p->fwd[i].dbg_flags = p->dgrad[i].dbg_flags = on ? tl_flags : 0;
     p->fwd[i].tl = on ? p->timeline + 8 * i : nullptr;
     p->dgrad[i].tl = on ? p->timeline + 8 * (16 + i) : nullptr;
     p->scale[i].tl = on ? p->timeline + 8 * (32 + i) : nullptr;
@@ -1578,7 +1678,49 @@ static void timeline_arm(nst_plan* p, bool on) {
 }
 #endif
 
+// One optimizer.step() of every member of a head: the evaluations are shared launches (eval_enqueue), each member's
+// optimizer iteration (four launches, ~25 us of them serial latency) runs on the member's own side stream beside the others'.
+static int step_enqueue_head(nst_plan* p, int* launches, cudaStream_t s, int max_evals) {
+  int nl = 0, evals = 0;
+  const int B = p->batch;
+  if (static_cast<int>(p->members.size()) != B) return fail(NST_ERR_STATE, "batch head without members");
+  nst_plan* m0 = p->members[0];
+  for (int m = 0; m < B; ++m) {
+    CK(launch_lbfgs_step_begin(p->members[m]->lb, s));
+    ++nl;
+  }
+  CKI(eval_enqueue(p, m0->lb.x, m0->lb.g, nullptr, nullptr, &nl, s, nullptr));
+  ++evals;
+  const int max_iter = 20;
+  for (int k = 1; k <= max_iter && evals < max_evals + (max_evals >= 20 ? 1 : 0); ++k) {
+    const int mode = k == 1 ? NST_CTL_BEGIN : NST_CTL_MID;
+    // fork: ev[0] is free between evaluations (EV_FORK is recorded and consumed at the start of each)
+    CK(cudaEventRecord(p->ev[0], s));
+    for (int m = 0; m < B; ++m) {
+      nst_plan* q = p->members[m];
+      cudaStream_t sm = q->side != nullptr ? q->side : s;
+      if (sm != s) CK(cudaStreamWaitEvent(sm, p->ev[0], 0));
+      CK(launch_lbfgs_iteration(q->lb, mode, sm));
+      nl += 4;
+      if (sm != s) {
+        CK(cudaEventRecord(q->ev[0], sm));
+        CK(cudaStreamWaitEvent(s, q->ev[0], 0));
+      }
+    }
+    if (k != max_iter) {
+      CKI(eval_enqueue(p, m0->lb.x, m0->lb.g, nullptr, nullptr, &nl, s, nullptr));
+      ++evals;
+    }
+  }
+  if (launches) *launches = nl;
+  return NST_OK;
+}
+
 static int step_enqueue(nst_plan* p, int* launches, cudaStream_t s, int max_evals, LaunchTimer* tm) {
+  if (p->batch > 1) {
+    if (tm != nullptr) return fail(NST_ERR_UNSUPPORTED, "per-launch timing of a batch head");
+    return step_enqueue_head(p, launches, s, max_evals);
+  }
   LbfgsBuffers& b = p->lb;
   int nl = 0, evals = 0;
   CK(launch_lbfgs_step_begin(b, s));
@@ -1675,6 +1817,7 @@ extern "C" int nst_lbfgs_launches_per_step(const nst_plan* p) { return p ? p->la
 extern "C" int nst_lbfgs_status(nst_plan* p, nst_status* out, void* stream) {
   if (!p || !out) return fail(NST_ERR_ARG, "nst_lbfgs_status: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  NOT_A_HEAD(p, "nst_lbfgs_status");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static thread_local NstLbfgsCtl h;
   CK(cudaMemcpyAsync(&h, p->lb.ctl, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -1699,6 +1842,7 @@ extern "C" int nst_lbfgs_status(nst_plan* p, nst_status* out, void* stream) {
 extern "C" int nst_lbfgs_get_x(nst_plan* p, float* out, void* stream) {
   if (!p || !out) return fail(NST_ERR_ARG, "nst_lbfgs_get_x: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  NOT_A_HEAD(p, "nst_lbfgs_get_x");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   clamp_copy_kernel<<<592, 256, 0, s>>>(p->lb.x, out, static_cast<size_t>(3) * p->H * p->W);  // run_style_transfer.py:153-155
   CK(cudaGetLastError());
@@ -1708,6 +1852,7 @@ extern "C" int nst_lbfgs_get_x(nst_plan* p, float* out, void* stream) {
 extern "C" int nst_lbfgs_trace(nst_plan* p, float* host_out, int max_rows, void* stream) {
   if (!p || !host_out || max_rows < 0) return fail(NST_ERR_ARG, "nst_lbfgs_trace: bad arguments");
   if (!p->with_grad) return fail(NST_ERR_STATE, "plan was created without optimizer state");
+  NOT_A_HEAD(p, "nst_lbfgs_trace");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int calls = 0;
   CK(cudaMemcpyAsync(&calls, &p->lb.ctl->closure_calls, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1803,6 +1948,95 @@ extern "C" int nst_run_frame_host(nst_plan* p, const uint8_t* content_u8, uint8_
   CKI(frame_end(p, out_u8, s));
   CK(cudaStreamSynchronize(s));
   return st.closure_calls;
+}
+
+// ---- several images per launch ------------------------------------------------------------------------------
+extern "C" int nst_batch_create(nst_plan** out, const nst_net* net, int H, int W, uint32_t tap_mask, uint32_t style_mask,
+                                uint32_t content_mask, int batch) {
+  if (!out) return fail(NST_ERR_ARG, "nst_batch_create: bad arguments");
+  if (batch < 2 || batch > 8) return fail(NST_ERR_ARG, "nst_batch_create: batch must be 2..8 (got %d)", batch);
+  // tiles (16 x 8 pixels) and 2 x 2 pooling windows must not straddle two images at any of the five resolutions
+  if (H % 16 != 0 || W % 16 != 0) return fail(NST_ERR_UNSUPPORTED, "nst_batch_create: H and W must be multiples of 16 (got %dx%d)", H, W);
+  nst_plan* head = nullptr;
+  CKI(plan_create_impl(&head, net, H, W, tap_mask, style_mask, content_mask, 1, batch, nullptr, 0));
+  for (int m = 0; m < batch; ++m) {
+    nst_plan* q = nullptr;
+    const int rc = plan_create_impl(&q, net, H, W, tap_mask, style_mask, content_mask, 1, 1, head, m);
+    if (rc != NST_OK) {
+      nst_plan_destroy(head);
+      return rc;
+    }
+    head->members.push_back(q);
+    head->bytes += q->bytes;
+  }
+  *out = head;
+  return NST_OK;
+}
+
+extern "C" int nst_batch_size(const nst_plan* p) { return p ? p->batch : 0; }
+
+extern "C" nst_plan* nst_batch_member(nst_plan* head, int index) {
+  if (!head || index < 0 || index >= static_cast<int>(head->members.size())) {
+    fail(NST_ERR_ARG, "nst_batch_member: no member %d", index);
+    return nullptr;
+  }
+  return head->members[index];
+}
+
+extern "C" int nst_lbfgs_freeze(nst_plan* p, int frozen, void* stream) {
+  if (!p || !p->with_grad) return fail(NST_ERR_ARG, "nst_lbfgs_freeze: bad arguments");
+  NOT_A_HEAD(p, "nst_lbfgs_freeze");
+  CK(cudaMemsetAsync(&p->lb.ctl->frozen, frozen ? 1 : 0, sizeof(int), static_cast<cudaStream_t>(stream)));
+  return NST_OK;
+}
+
+// `count` (<= batch) frames through one head: frame k on member k, the remaining members frozen.  Every optimizer.step()
+// of all frames is ONE graph launch; a frame whose own loop has ended (run_style_transfer.py:100) is frozen while the others
+// finish.  Each frame's trajectory is the one nst_run_frame_host gives on a single-image plan up to the order of the
+// floating-point sums inside the shared launches (the tile -> CTA assignment differs).
+extern "C" int nst_run_batch_host(nst_plan* head, int count, const uint8_t* const* content_u8, uint8_t* const* out_u8, int num_steps,
+                                  int channel_attention, const float* ca_w1, const float* ca_w2, void* stream, int* closure_calls) {
+  if (!head || head->batch < 2 || !content_u8 || !out_u8 || count < 1 || count > head->batch)
+    return fail(NST_ERR_ARG, "nst_run_batch_host: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = head->batch;
+  nst_status st[8];
+  int guard[8];
+  memset(st, 0, sizeof(st));
+  memset(guard, 0, sizeof(guard));
+  for (int k = 0; k < B; ++k) {
+    nst_plan* q = head->members[k];
+    if (k < count) {
+      if (!content_u8[k] || !out_u8[k]) return fail(NST_ERR_ARG, "nst_run_batch_host: bad arguments");
+      CKI(frame_begin(q, content_u8[k], num_steps, channel_attention, ca_w1, ca_w2, s));
+    } else {
+      if (!q->img_dev) CKI(plan_alloc_t(q, &q->img_dev, static_cast<size_t>(3) * q->H * q->W, true));
+      CKI(nst_lbfgs_init(q, q->img_dev, 0, s));
+      CKI(nst_lbfgs_freeze(q, 1, s));
+    }
+  }
+  for (;;) {
+    bool active[8], any = false;
+    for (int k = 0; k < count; ++k) {
+      active[k] = st[k].closure_calls <= num_steps && guard[k] <= num_steps + 2;
+      any |= active[k];
+    }
+    if (!any) break;
+    for (int k = 0; k < count; ++k)
+      if (!active[k]) CKI(nst_lbfgs_freeze(head->members[k], 1, s));
+    CKI(nst_lbfgs_step(head, s));
+    for (int k = 0; k < count; ++k) {
+      if (!active[k]) continue;
+      CKI(nst_lbfgs_status(head->members[k], &st[k], s));
+      if (st[k].stop == NST_STOP_NONFINITE) return fail(NST_ERR_STATE, "frame %d: non-finite loss at evaluation %d", k, st[k].closure_calls);
+      ++guard[k];
+    }
+  }
+  for (int k = 0; k < count; ++k) CKI(frame_end(head->members[k], out_u8[k], s));
+  CK(cudaStreamSynchronize(s));
+  for (int k = 0; k < count; ++k)
+    if (closure_calls) closure_calls[k] = st[k].closure_calls;
+  return NST_OK;
 }
 
 // K independent frames on K plans / streams, stepped in lock step: every optimizer.step() of every frame is enqueued

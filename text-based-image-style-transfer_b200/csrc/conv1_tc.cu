@@ -332,8 +332,8 @@ conv1_tc_kernel(const __grid_constant__ ConvParams p, const float* __restrict__ 
       __syncwarp();
       if (lane == 0 && !skip) {
         const int w0 = tw * C1_TILE_W, h0 = th * C1_TILE_H + q * 4;
-        if (p.out_tap != nullptr) tma_store_3d(&p.tmO0, buf_tap, 0, w0, h0);
-        if (p.out_act != nullptr) tma_store_3d(&p.tmO1, buf_act, 0, w0, h0);
+        if (p.out_tap != nullptr) tma_store_4d(&p.tmO0, buf_tap, 0, w0, h0, 0);
+        if (p.out_act != nullptr) tma_store_4d(&p.tmO1, buf_act, 0, w0, h0, 0);
         bulk_commit();
       }
     }

@@ -81,12 +81,13 @@ struct EpiStore {
   int next;       // buffer the next store uses
   uint8_t* cur;   // buffer being filled by a store that spans two calls (data gradient: two 16-channel chunks per row)
   int lane;
-  int w0, h0;     // tile-row origin of this warp's 8 x 4 pixel block in the output tensor
+  int w0, h0;     // tile-row origin of this warp's 8 x 4 pixel block inside its image
+  int b;          // image of a batched launch (the output maps are 4-D (C, W, H, image): boxes are clipped per image)
 };
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
@@ -128,7 +129,7 @@ __device__ __forceinline__ void epi_submit(const EpiStore& st, const uint8_t* b,
   fence_async_smem();
   __syncwarp();
   if (st.lane == 0 && !skip) {
-    tma_store_3d(tm, b, c0, w0, h0);
+    tma_store_4d(tm, b, c0, w0, h0, st.b);
     bulk_commit();
   }
 }
@@ -210,7 +211,8 @@ __device__ __forceinline__ void epilogue_fwd(const ConvParams& p, float (&v)[32]
   }
   const int Hp = p.H >> 1, Wp = p.W >> 1;
   const int hp = h >> 1, wp = w >> 1;
-  if (hp < Hp && wp < Wp) {
+  // several images per launch: H and W are even (multiples of 16) and h counts rows of the stacked [batch * H] view
+  if (p.batch > 1 ? valid : (hp < Hp && wp < Wp)) {
     const size_t ppix = static_cast<size_t>(hp) * Wp + wp;
     // each of the four lanes of a window stores 8 of the 32 channels
 #pragma unroll

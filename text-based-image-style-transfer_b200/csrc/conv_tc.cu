@@ -189,11 +189,20 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
   const int sp_tiles = p.tiles_w * p.tiles_h;
   // work items: (N tile, pixel tile), or (N tile, two consecutive pixel tiles) for a pair - this CTA takes the tile of its
   // rank; with an odd tile count the last pair's second tile lies below the image (all loads zero-fill, nothing is stored)
-  const int sp_items = PAIR ? (sp_tiles + 1) >> 1 : sp_tiles;
+  // Several images per launch (p.batch > 1): the tensors are [batch][H][W][C]; an item also names its image.  Pairs never
+  // straddle two images.
+  const int img_items = PAIR ? (sp_tiles + 1) >> 1 : sp_tiles;
+  const int sp_items = img_items * p.batch;
   const int num_items = sp_items * p.tiles_n;
-  auto item_coords = [&](int item, int& nt, int& th, int& tw) {
+  auto item_coords = [&](int item, int& nt, int& b, int& th, int& tw) {
     nt = item / sp_items;
-    const int sp = PAIR ? 2 * (item - nt * sp_items) + cta_rank : item - nt * sp_items;
+    int r = item - nt * sp_items;
+    b = 0;
+    if (p.batch > 1) {
+      b = r / img_items;
+      r -= b * img_items;
+    }
+    const int sp = PAIR ? 2 * r + cta_rank : r;
     if (PAIR && sp >= sp_tiles) {
       th = p.tiles_h;
       tw = 0;
@@ -229,10 +238,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       const bool expects = !PAIR || cta_rank == 0;
       const uint32_t a_expect = PAIR ? 2u * a_tx : a_tx;
       const int n_rank = PAIR ? cta_rank * (BLOCK_N / 2) : 0;
-      auto load_a = [&](const CUtensorMap* tm, int stage, uint32_t bytes, int c0, int c1, int c2) {
+      auto load_a = [&](const CUtensorMap* tm, int stage, uint32_t bytes, int c0, int c1, int c2, int c3) {
         if (expects) mbar_arrive_expect_tx(&afull_bar[stage], bytes);
-        if constexpr (PAIR) tma_load_3d_2sm(sA + stage * HALO_STAGE_BYTES, tm, mapa_u32(smem_u32(&afull_bar[stage]), 0), c0, c1, c2);
-        else tma_load_3d(sA + stage * HALO_STAGE_BYTES, tm, &afull_bar[stage], c0, c1, c2);
+        if constexpr (PAIR) tma_load_4d_2sm(sA + stage * HALO_STAGE_BYTES, tm, mapa_u32(smem_u32(&afull_bar[stage]), 0), c0, c1, c2, c3);
+        else tma_load_4d(sA + stage * HALO_STAGE_BYTES, tm, &afull_bar[stage], c0, c1, c2, c3);
       };
       auto load_b = [&](const CUtensorMap* tm, int stage, uint32_t bytes, int c0, int c1, int c2) {
         if (expects) mbar_arrive_expect_tx(&bfull_bar[stage], bytes);
@@ -251,12 +260,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int tile = worker; tile < num_items; tile += workers) {
-        int nt, th, tw;
-        item_coords(tile, nt, th, tw);
+        int nt, b, th, tw;
+        item_coords(tile, nt, b, th, tw);
         const int h0 = th * TILE_H, w0 = tw * TILE_W, n0 = nt * BLOCK_N;
+        const int b_dh = p.b_per_image ? b : 0;   // Gram-backward operand: one matrix per image in the third map dimension
         for (int ks = 0; ks < k_slices; ++ks) {
           NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
-          load_a(&p.tmA, as, a_expect, ks * BLOCK_K, w0 - pad, h0 - pad);
+          load_a(&p.tmA, as, a_expect, ks * BLOCK_K, w0 - pad, h0 - pad, b);
           if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
               continue;
             }
             NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
-            load_b(&p.tmB, bs, static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES, ks * BLOCK_K, n0, tap);
+            load_b(&p.tmB, bs, static_cast<uint32_t>(tps) * Cfg::B_TILE_BYTES, ks * BLOCK_K, n0, tap + (MODE == CONV_SCALE ? b_dh : 0));
             if (++bs == Cfg::B_STAGES) {
               bs = 0;
               bphase ^= 1u;
@@ -278,13 +288,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
         // folded Gram backward: the tile of the tap (no halo) and the matching slice of dh, one 64-channel slice at a time
         for (int ks2 = 0; ks2 < seed_slices; ++ks2) {
           NST_WAIT(wacc0, mbar_wait(&aempty_bar[as], aphase ^ 1u));
-          load_a(&p.tmA2, as, (PAIR ? 2u : 1u) * FLAT_TX_BYTES, ks2 * BLOCK_K, w0, h0);
+          load_a(&p.tmA2, as, (PAIR ? 2u : 1u) * FLAT_TX_BYTES, ks2 * BLOCK_K, w0, h0, b);
           if (++as == Cfg::HALO_STAGES) {
             as = 0;
             aphase ^= 1u;
           }
           NST_WAIT(wacc1, mbar_wait(&bempty_bar[bs], bphase ^ 1u));
-          load_b(&p.tmB2, bs, Cfg::B_TILE_BYTES, ks2 * BLOCK_K, n0, 0);
+          load_b(&p.tmB2, bs, Cfg::B_TILE_BYTES, ks2 * BLOCK_K, n0, b_dh);
           if (++bs == Cfg::B_STAGES) {
             bs = 0;
             bphase ^= 1u;
@@ -344,6 +354,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     const uint32_t b_hi = static_cast<uint32_t>(umma_desc_sw128(0, 16, 1024) >> 32);
     const uint32_t lbo_lo = static_cast<uint32_t>(umma_desc_sw128(0, 16, 0) & 0xffffffffu);  // LBO field, address 0
     const bool conv3x3 = p.taps == 9;
+    long long tl_c0 = 0;
+    unsigned long long tl_g0 = 0;
     auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
       if constexpr (PAIR) umma_f16_2sm(d, da, db, id, acc);
       else umma_f16(d, da, db, id, acc);
@@ -364,6 +376,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
           const unsigned long long now = globaltimer_ns();
           atomicMin(&NST_TL_PTR(p)[4], now);
           atomicMax(&NST_TL_PTR(p)[5], now);
+          tl_c0 = clock64();
+          tl_g0 = now;
         }
         const uint32_t a_lo0 = lbo_lo | (smem_u32(sA + as * HALO_STAGE_BYTES) >> 4);
         if (conv3x3) {
@@ -460,7 +474,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
       }
       commit(&tfull_bar[ts]);  // accumulator(s) complete
       NST_STAMP(3, tile == worker);
-      if (NST_TL_PTR(p) != nullptr && tile + tile_step >= num_items) atomicMax(&NST_TL_PTR(p)[6], globaltimer_ns());
+      if (NST_TL_PTR(p) != nullptr && tile + tile_step >= num_items) {
+        const unsigned long long now = globaltimer_ns();
+        atomicMax(&NST_TL_PTR(p)[6], now);
+        // SM clock over this CTA's main loops: (SM cycles << 32) | nanoseconds, worker 0 only
+        if (worker == 0) NST_TL_PTR(p)[7] = (static_cast<unsigned long long>(clock64() - tl_c0) << 32) | ((now - tl_g0) & 0xffffffffull);
+      }
       if (dual_issue) {
         tphase ^= 1u;     // this issuer's own accumulator stage, next use
       } else if (++ts == 2) {
@@ -505,18 +524,21 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     DgradAux aux_x[XT ? DG_PRE : 1];
     DgradAux aux_nxt;
     float gp[3] = {0.f, 0.f, 0.f}, gp_x[3] = {0.f, 0.f, 0.f};
-    auto coords = [&](int tile_, int& h_, int& w_, int& n0_, bool& valid_) {
+    // h_ addresses the [batch * H][W][C] view of the tensors (image b's rows follow image b - 1's); valid_ is the pixel's
+    // place inside its own image
+    auto coords = [&](int tile_, int& h_, int& w_, int& n0_, bool& valid_, int& b_) {
       int nt_, th_, tw_;
-      item_coords(tile_, nt_, th_, tw_);
+      item_coords(tile_, nt_, b_, th_, tw_);
       h_ = th_ * TILE_H + hl;
       w_ = tw_ * TILE_W + wl;
       n0_ = nt_ * BLOCK_N;
       valid_ = h_ < p.H && w_ < p.W;
+      h_ += b_ * p.H;
     };
     auto request = [&](int tile_, DgradAux* a_, float* g_) {
-      int h_, w_, n0_;
+      int h_, w_, n0_, b_;
       bool valid_;
-      coords(tile_, h_, w_, n0_, valid_);
+      coords(tile_, h_, w_, n0_, valid_, b_);
       if constexpr (MODE == CONV_DGRAD) {
 #pragma unroll
         for (int c = 0; c < DG_PRE; ++c) dgrad_aux_load(p, a_[c], h_, w_, n0_ + col0 + c * DG_CH, valid_);
@@ -535,11 +557,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kern
     }
     const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;   // the leader's barriers (8 bytes apart)
     for (int tile = worker; tile < num_items; tile += workers) {
-      int h, w, n0;
+      int h, w, n0, bimg;
       bool valid;
-      coords(tile, h, w, n0, valid);
-      est.w0 = w - wl;            // this warp's 8 x 4 pixel block of the tile
-      est.h0 = h - hl + q * 4;
+      coords(tile, h, w, n0, valid, bimg);
+      if (p.batch > 1 && (MODE == CONV_SCALE || seed)) alpha = __ldg(p.alpha + bimg * p.alpha_stride);
+      est.w0 = w - wl;            // this warp's 8 x 4 pixel block of the tile, inside its image
+      est.h0 = h - bimg * p.H - hl + q * 4;
+      est.b = bimg;
       if constexpr (MODE == CONV_FWD) {
         for (int j = et; j < BLOCK_N; j += Cfg::EPI_WARPS * 32) sbias[ts * BLOCK_N + j] = __ldg(p.bias + n0 + j);
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");  // the epilogue warps only
@@ -681,31 +705,35 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h) {
+int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h, int batch) {
   auto fn = get_encode_fn();
   if (!fn) return -1;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
-  cuuint32_t estr[3] = {1, 1, 1};
+  // always 4-D (C, W, H, image): with one image the last coordinate is 0
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   // FLOAT16 and BFLOAT16 only differ for NaN fill; both are 2-byte element moves
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h) {
+int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h, int batch) {
   auto fn = get_encode_fn();
   if (!fn) return -1;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
-  cuuint32_t estr[3] = {1, 1, 1};
+  // always 4-D (C, W, H, image): a box that overhangs the bottom of its image is clipped there, not written into the next one
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapSwizzle sw = box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                   : (box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   if (box_c * 2 != 128 && box_c * 2 != 64 && box_c * 2 != 32) return -2;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
@@ -771,16 +799,17 @@ void conv_finalize_params(ConvParams& p, int mode) {
   static const bool single_issue = getenv("NST_SINGLE_ISSUE") != nullptr;
   p.dual_issue = single_issue ? 0 : 1;
   const int bn = p.block_n;
+  if (p.batch < 1) p.batch = 1;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_n = p.N / bn;
-  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.batch;
   p.idesc = umma_idesc_f16(p.pair ? 2 * BLOCK_M : BLOCK_M, bn, (mode == CONV_DGRAD || mode == CONV_DGRAD_PIX) ? 1 : 0, 0, 0);
 }
 
 int conv_grid_ctas(const ConvParams& p, int num_sms) {
   if (!p.pair) return p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  const int items = ((p.tiles_w * p.tiles_h + 1) / 2) * p.tiles_n;
+  const int items = ((p.tiles_w * p.tiles_h + 1) / 2) * p.tiles_n * (p.batch < 1 ? 1 : p.batch);
   const int pairs = items < num_sms / 2 ? items : num_sms / 2;
   return 2 * pairs;
 }

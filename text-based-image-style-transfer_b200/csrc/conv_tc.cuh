@@ -59,6 +59,14 @@ struct ConvParams {
   int block_n;     // N tile: 64, 128 or 256 (conv_block_n)
   int tiles_w, tiles_h, tiles_n, num_tiles;
   uint32_t idesc;
+  // Several images per launch: every activation / gradient / routing tensor is [batch][H][W][C] (image stride = one image),
+  // tmA / tmA2 are 4-D maps (C, W, H, batch) so that the zero fill at the image border still is the padding; outputs, masks
+  // and seeds read / written by single threads are addressed through the stacked [batch * H][W][C] view (H and W multiples of 16:
+  // 2 x 2 windows never straddle two images at any resolution); the output maps tmO0 / tmO1 are 4-D like tmA, so a TMA store
+  // box that overhangs the bottom of its image (deep layers: fewer than 16 rows) is clipped there.  batch == 1: exactly the single-image launch.
+  int batch;
+  int alpha_stride;  // floats between the alpha scalars of consecutive images
+  int b_per_image;   // != 0: tmB (CONV_SCALE) / tmB2 (folded Gram backward) hold one [N][K] matrix per image in their third dimension
   int pair;        // != 0: the launch runs as CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): conv_use_pair; set BEFORE
                    // make_tmap_wgt (the weight box is half an N tile) and conv_finalize_params (instruction descriptor)
   int dual_issue;  // != 0: one-slice layers with resident weights are issued by two threads (conv_tc.cu); NST_SINGLE_ISSUE clears it
@@ -94,14 +102,14 @@ struct ConvParams {
 };
 
 // tensor-map builders (driver entry point resolved at run time; no link-time dependency on libcuda)
-int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h);
+int make_tmap_act(CUtensorMap* out, const void* base, int H, int W, int C, int box_c, int box_w, int box_h, int batch = 1);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int taps, int N, int K, int box_n, bool pair = false);
 // whether a launch of this mode / N tile / filter size runs as CTA pairs (NST_PAIR=0 turns them off)
 bool conv_use_pair(int mode, int block_n, int taps, int K, int N);
 // CTAs of the launch (persistent: at most one per SM; pairs: an even number)
 int conv_grid_ctas(const ConvParams& p, int num_sms);
 // output map for the epilogue's TMA stores: [H][W][C] 16-bit tensor, box (box_c, box_w, box_h); box_c * 2 = 128, 64 or 32 bytes
-int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h);
+int make_tmap_out(CUtensorMap* out, void* base, int H, int W, int C, int box_c, int box_w, int box_h, int batch = 1);
 // filter taps the kernel loads per weight stage for this N tile (the depth of the weight tensor map's box)
 int conv_taps_per_stage(int block_n, int taps);
 

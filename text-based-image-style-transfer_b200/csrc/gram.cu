@@ -57,10 +57,17 @@ __device__ __forceinline__ void gram_pair_to_blocks(int pair, int nblk, int& bi,
 // What one work item (block pair x K split of one layer) is
 struct GramItem {
   int l, local, pair, bi, bj, c_begin, c_end, a_boxes, b_boxes, nb, kmul;
+  int img;       // image of a batched launch (GramParams::batch > 1): items [img * num_items, (img + 1) * num_items)
 };
 __device__ __forceinline__ GramItem gram_item(const GramParams& p, int item) {
   GramItem it;
+  it.img = 0;
+  if (p.batch > 1) {
+    it.img = item / p.num_items;
+    item -= it.img * p.num_items;
+  }
   it.l = gram_find_layer_by_item(p, item);
+
   const GramLayer& L = p.L[it.l];
   it.local = item - L.item0;
   it.pair = it.local / L.splits;
@@ -128,12 +135,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   // dependent is released at the end.
   if (p.max_ctas == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const int total_items = p.num_items * (p.batch > 1 ? p.batch : 1);
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const GramItem it = gram_item(p, item);
         const CUtensorMap* tm = &p.tm[it.l];
         for (int c = it.c_begin; c < it.c_end; c += it.kmul) {
@@ -144,9 +152,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
             uint8_t* sa = smem + stage * G_STAGE_BYTES + j * it.nb * G_BOX_BYTES;
             uint8_t* sb = sa + it.a_boxes * G_BOX_BYTES;
             for (int b = 0; b < it.a_boxes; ++b)
-              tma_load_2d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], it.bi * 128 + b * 64, (c + j) * G_KCHUNK);
+              tma_load_3d(sa + b * G_BOX_BYTES, tm, &full_bar[stage], it.bi * 128 + b * 64, (c + j) * G_KCHUNK, it.img);
             for (int b = 0; b < it.b_boxes; ++b)
-              tma_load_2d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], it.bj * 128 + b * 64, (c + j) * G_KCHUNK);
+              tma_load_3d(sb + b * G_BOX_BYTES, tm, &full_bar[stage], it.bj * 128 + b * 64, (c + j) * G_KCHUNK, it.img);
           }
           if (++stage == G_STAGES) {
             stage = 0;
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
   } else if (warp == 1) {
     int stage = 0, ts = 0;
     uint32_t phase = 0, tphase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const GramItem it = gram_item(p, item);
       const GramLayer& L = p.L[it.l];
       const uint32_t idesc = umma_idesc_f16(128, L.bn, 0, 1, 1);
@@ -200,18 +208,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
     const int row = q * 32 + lane;
     int ts = 0;
     uint32_t tphase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const GramItem it = gram_item(p, item);
       const GramLayer& L = p.L[it.l];
       const int bi = it.bi, bj = it.bj;
+      // per-image outputs of a batched launch: [batch][C][C] operands / targets, [batch][GRAM_MAX_LAYERS] scalars
+      const size_t cc_off = static_cast<size_t>(it.img) * L.C * L.C;
+      const int sc_off = it.img * p.scal_stride;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ts * 128);
       const bool row_ok = bi * 128 + row < L.C;
       if (L.fused && L.target != nullptr) {
         // ---- the layer is finished here: d = G - T, fp16 backward operand d * dh_scale (both triangles), sum of d^2.
         // Everything that does not depend on the accumulator is fetched before waiting for it.
         const int gi = bi * 128 + row;
-        const float scale = L.dh_scale != nullptr ? __ldg(L.dh_scale) : 1.f;
-        const float* trow = L.target + static_cast<size_t>(row_ok ? gi : 0) * L.C + bj * 128;
+        const float scale = L.dh_scale != nullptr ? __ldg(L.dh_scale + sc_off) : 1.f;
+        const float* trow = L.target + static_cast<size_t>(it.img) * L.target_stride + static_cast<size_t>(row_ok ? gi : 0) * L.C + bj * 128;
         float sq = 0.f;
         const float w = bi == bj ? 1.f : 2.f;   // an off-diagonal block stands for its mirror image too
         // target row, one 32-column chunk ahead of its use: the first chunk is requested before the accumulator is waited for
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
               hv[j] = __float2half_rn(d * scale);
             }
             if (L.dh != nullptr) {
-              __half* drow = L.dh + static_cast<size_t>(gi) * L.C + bj * 128 + c * 32;
+              __half* drow = L.dh + cc_off + static_cast<size_t>(gi) * L.C + bj * 128 + c * 32;
 #pragma unroll
               for (int j = 0; j < 4; ++j) *(reinterpret_cast<uint4*>(drow) + j) = *(reinterpret_cast<const uint4*>(hv) + j);
               if (bi != bj) {
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   const int gj = bj * 128 + c * 32 + j;
-                  if (gj < L.C) L.dh[static_cast<size_t>(gj) * L.C + gi] = hv[j];
+                  if (gj < L.C) L.dh[cc_off + static_cast<size_t>(gj) * L.C + gi] = hv[j];
                 }
               }
             }
@@ -267,14 +278,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_partial_kernel(const __grid
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
         if (warp == 4 && lane == 0) {
-          p.fin_part[L.fin_blk0 + it.pair] = ((s_sq[0] + s_sq[1]) + s_sq[2]) + s_sq[3];
-          if (it.pair == 0 && L.alpha != nullptr) *L.alpha = L.grad_coef / scale;
+          p.fin_part[it.img * p.num_fin_blocks + L.fin_blk0 + it.pair] = ((s_sq[0] + s_sq[1]) + s_sq[2]) + s_sq[3];
+          if (it.pair == 0 && L.alpha != nullptr) L.alpha[sc_off] = L.grad_coef / scale;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // s_sq is rewritten by the next item
       } else {
         mbar_wait(&tfull_bar[ts], tphase);
         tc_fence_after();
-        float* dst = p.ws + L.ws_off + (static_cast<size_t>(it.local) * 128 + row) * L.bn;
+        float* dst = p.ws + static_cast<size_t>(it.img) * p.ws_img + L.ws_off + (static_cast<size_t>(it.local) * 128 + row) * L.bn;
 #pragma unroll 1
         for (int c = 0; c < L.bn / 32; ++c) {
           uint32_t r[32];
@@ -316,7 +327,7 @@ struct FinElem {
   bool ok, offdiag;
   float g;
 };
-__device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const GramLayer& L, int blk_in_layer, float* s_part) {
+__device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const GramLayer& L, int blk_in_layer, float* s_part, int img) {
   FinElem e;
   const int tile = 128 * L.bn;
   const int QL = L.fin_q;                       // 1 or 4
@@ -342,7 +353,7 @@ __device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const Gram
   }
   float a0 = 0.f, a1 = 0.f;
   if (e.ok) {
-    const float* src = p.ws + L.ws_off + (static_cast<size_t>(pair) * L.splits * 128 + li) * L.bn + lj;
+    const float* src = p.ws + static_cast<size_t>(img) * p.ws_img + L.ws_off + (static_cast<size_t>(pair) * L.splits * 128 + li) * L.bn + lj;
     int s = q;
     for (; s + QL < L.splits; s += 2 * QL) {
       a0 += src[static_cast<size_t>(s) * tile];
@@ -370,32 +381,39 @@ __device__ __forceinline__ FinElem gram_fin_elem(const GramParams& p, const Gram
 __global__ void __launch_bounds__(GRAM_FIN_THREADS) gram_finalize_kernel(const __grid_constant__ GramParams p) {
   __shared__ float scratch[GRAM_FIN_THREADS / 32];
   __shared__ float s_part[GRAM_FIN_THREADS];
-  const int l = gram_find_layer_by_finblk(p, blockIdx.x);
+  int img = 0, blk = blockIdx.x;
+  if (p.batch > 1) {
+    img = blk / p.num_fin_blocks;
+    blk -= img * p.num_fin_blocks;
+  }
+  const int l = gram_find_layer_by_finblk(p, blk);
   const GramLayer& L = p.L[l];
-  const float scale = (L.dh_scale != nullptr && !L.fused) ? __ldg(L.dh_scale) : 1.f;  // set with the target: not written by the previous launch
+  const size_t cc_off = static_cast<size_t>(img) * L.C * L.C;
+  const int sc_off = img * p.scal_stride;
+  const float scale = (L.dh_scale != nullptr && !L.fused) ? __ldg(L.dh_scale + sc_off) : 1.f;  // set with the target: not written by the previous launch
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (L.fused && L.target != nullptr) return;
-  FinElem e = gram_fin_elem(p, L, blockIdx.x - L.fin_blk0, s_part);
+  FinElem e = gram_fin_elem(p, L, blk - L.fin_blk0, s_part, img);
   float sq = 0.f;
   if (e.ok) {
     float d = e.g;
-    if (L.target != nullptr) d -= L.target[static_cast<size_t>(e.gi) * L.C + e.gj];
+    if (L.target != nullptr) d -= L.target[static_cast<size_t>(img) * L.target_stride + static_cast<size_t>(e.gi) * L.C + e.gj];
     if (L.gram_out != nullptr) {
       L.gram_out[static_cast<size_t>(e.gi) * L.C + e.gj] = d;
       if (e.offdiag) L.gram_out[static_cast<size_t>(e.gj) * L.C + e.gi] = d;
     }
     if (L.dh != nullptr) {
       const __half h = __float2half_rn(d * scale);
-      L.dh[static_cast<size_t>(e.gi) * L.C + e.gj] = h;
-      if (e.offdiag) L.dh[static_cast<size_t>(e.gj) * L.C + e.gi] = h;
+      L.dh[cc_off + static_cast<size_t>(e.gi) * L.C + e.gj] = h;
+      if (e.offdiag) L.dh[cc_off + static_cast<size_t>(e.gj) * L.C + e.gi] = h;
     }
     sq = e.offdiag ? 2.f * d * d : d * d;
   }
   sq = block_sum(sq, scratch);
   if (threadIdx.x == 0) {
     p.fin_part[blockIdx.x] = sq;
-    if (blockIdx.x == L.fin_blk0 && L.alpha != nullptr) *L.alpha = L.grad_coef / scale;
+    if (blk == L.fin_blk0 && L.alpha != nullptr) L.alpha[sc_off] = L.grad_coef / scale;
   }
 }
 
@@ -419,18 +437,19 @@ __global__ void __launch_bounds__(256) gram_target_scale_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C) {
+int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C, int batch) {
   void* ptr = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
       qres != cudaDriverEntryPointSuccess || ptr == nullptr)
     return -1;
   auto fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(HW)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
-  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(G_KCHUNK)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  // (C, HW, image): rows behind the last pixel of an image zero-fill, they are not the next image's first pixels
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(HW), static_cast<cuuint64_t>(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(HW) * C * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(G_KCHUNK), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
@@ -517,10 +536,12 @@ static bool gram_needs_finalize(const GramParams& p) {
 int gram_launches(const GramParams& p) { return gram_needs_finalize(p) ? 2 : 1; }
 
 cudaError_t launch_gram(const GramParams& p, cudaStream_t stream) {
-  const int grid = (p.max_ctas > 0 && p.max_ctas < p.num_items) ? p.max_ctas : p.num_items;
+  const int nb = p.batch > 1 ? p.batch : 1;
+  const int items = p.num_items * nb;
+  const int grid = (p.max_ctas > 0 && p.max_ctas < items) ? p.max_ctas : items;
   cudaError_t e = launch_pdl(gram_partial_kernel, grid, G_THREADS, G_SMEM_BYTES, stream, p);
   if (e != cudaSuccess || !gram_needs_finalize(p)) return e;
-  return launch_pdl(gram_finalize_kernel, p.num_fin_blocks, GRAM_FIN_THREADS, 0, stream, p);
+  return launch_pdl(gram_finalize_kernel, p.num_fin_blocks * nb, GRAM_FIN_THREADS, 0, stream, p);
 }
 
 cudaError_t launch_gram_target_scale(const float* target, int cc, float* scale_out, cudaStream_t stream) {

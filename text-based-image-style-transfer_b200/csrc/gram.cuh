@@ -28,6 +28,7 @@ struct GramLayer {
                   // from tensor memory - no workspace round trip, no finalize launch; its fin blocks are its block pairs
   size_t ws_off;  // float offset of this layer's partial tiles in the workspace
   // finalize inputs / outputs
+  size_t target_stride; // batched launch: floats between the targets of consecutive images (0: one target for all)
   const float* target;  // [C,C] target Gram or nullptr (then `gram_out` receives G itself)
   float* gram_out;      // [C,C] G (if target == nullptr) or G - T
   __half* dh;           // [C,C] (G - T) * dh_scale as fp16 (backward operand), or nullptr
@@ -44,13 +45,19 @@ struct GramParams {
   GramLayer L[GRAM_MAX_LAYERS];
   int num_layers;
   int num_items;
+  // Several images per launch (batch > 1): the feature maps are [batch][HW][C] (3-D tensor maps (C, HW, image): the last 64-pixel
+  // chunk of an image zero-fills behind ITS last pixel), the item list is repeated per image; per-image outputs: dh [batch][C][C], dh_scale / alpha [batch][scal_stride],
+  // fin_part [batch][num_fin_blocks], ws [batch][ws_img].
+  int batch;
+  int scal_stride;
+  size_t ws_img;
   int max_ctas;     // 0: one CTA per item; else the Gram kernel runs persistent on at most this many CTAs (see gram.cu)
   int num_fin_blocks;
   float* ws;        // split-K partial tiles [item][128][bn]
   float* fin_part;  // [num_fin_blocks] partial sums of (G - T)^2; summed per layer in a fixed order by the loss assembly
 };
 
-int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C);
+int make_tmap_feat(CUtensorMap* out, const void* base, int HW, int C, int batch = 1);
 // fills nblk/pairs/bn/splits/chunks/item0/fin_* /ws_off and the totals; returns workspace floats needed
 size_t gram_plan(GramParams& p, int target_ctas);
 cudaError_t launch_gram(const GramParams& p, cudaStream_t stream);

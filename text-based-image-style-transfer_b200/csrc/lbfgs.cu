@@ -76,7 +76,7 @@ __device__ __forceinline__ void warp_reduce8(float (&a)[8], int lane) {
 }
 
 __global__ void lbfgs_step_begin_kernel(NstLbfgsCtl* ctl) {
-  ctl->stop = NST_RUN;
+  ctl->stop = ctl->frozen != 0 ? NST_STOP_FROZEN : NST_RUN;
   ctl->run_pass2 = 0;
 }
 

@@ -37,6 +37,7 @@
 #define NST_STOP_STEP 4        // lbfgs.py:522  max|t d| <= tolerance_change
 #define NST_STOP_LOSS 5        // lbfgs.py:525  |loss - prev_loss| < tolerance_change
 #define NST_STOP_NONFINITE 6   // loss is NaN/Inf (not in the reference; guards the device loop)
+#define NST_STOP_FROZEN 7      // the member sits this step() out (not in the reference: batches of frames, nst_batch_create)
 
 // controller modes
 #define NST_CTL_BEGIN 0  // first controller call of a step(): follows the entry evaluation
@@ -46,7 +47,8 @@ struct NstLbfgsCtl {
   // ---- configuration (torch defaults: lr 1, tolerance_grad 1e-7, tolerance_change 1e-9, history 100)
   double lr, tol_grad, tol_change;
   int history_size;
-  int pad0;
+  int frozen;      // != 0: step() entry sets stop = NST_STOP_FROZEN instead of clearing it - a member of a batch whose own loop has
+                   // ended while the other members keep stepping (nst_lbfgs_freeze); zero after nst_lbfgs_init
   // ---- persistent optimizer state (torch `state` dict)
   int n_iter;      // state['n_iter']
   int func_evals;  // state['func_evals']

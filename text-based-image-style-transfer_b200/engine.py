@@ -258,8 +258,96 @@ class Plan:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.nst_plan_destroy(self.handle)
+            if getattr(self, "_owned", True):
+                self.lib.nst_plan_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def _wrap(cls, net: "Net", handle, H, W, taps, style_layers, content_layers, owned):
+        """A Plan object around an existing nst_plan handle (a batch head or one of its members)."""
+        self = cls.__new__(cls)
+        self.lib = net.lib
+        self.net = net
+        self.device = net.device
+        self.H, self.W = int(H), int(W)
+        self.taps = [n for n in CONV_NAMES if n in set(taps) | set(style_layers) | set(content_layers)]
+        self.style_layers = list(style_layers)
+        self.content_layers = list(content_layers)
+        self.handle = handle if isinstance(handle, C.c_void_p) else C.c_void_p(handle)
+        self._owned = owned
+        return self
+
+
+class BatchPlan:
+    """Several images per launch (nst_batch_create, SURVEY 8 f row 2): `head` steps all images with ONE set of convolution /
+    Gram launches per evaluation; `members[k]` is image k's single-image plan over its slice of the head's tensors (targets,
+    optimizer state, status, trace, result).  The reference evaluates one image per call (run_style_transfer.py:27-159); its
+    gram_matrix already divides by the batch size (style_transfer_losses.py:84-93) and apply_video_process loops over
+    independent frames (app.py:784-815) - this is that loop, `batch` frames at a time."""
+
+    def __init__(self, net: Net, H: int, W: int, style_layers: Sequence[str], content_layers: Sequence[str], batch: int,
+                 mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)):
+        self.lib = net.lib
+        self.net = net
+        self.device = net.device
+        self.batch = int(batch)
+        taps = list(content_layers) + list(style_layers)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.nst_batch_create(C.byref(h), net.handle, int(H), int(W), mask_of([n for n in CONV_NAMES if n in set(taps)]),
+                                            mask_of(style_layers), mask_of(content_layers), self.batch))
+        self.head = Plan._wrap(net, h, H, W, taps, style_layers, content_layers, owned=True)
+        self.members = []
+        for k in range(self.batch):
+            m = self.lib.nst_batch_member(h, k)
+            if not m:
+                raise NstError(self.lib.nst_last_error().decode())
+            self.members.append(Plan._wrap(net, m, H, W, taps, style_layers, content_layers, owned=False))
+        self.head.set_norm(mean, std)
+
+    def set_weights(self, w_style, w_content, w_tv, w_edge):
+        self.head.set_weights(w_style, w_content, w_tv, w_edge)   # forwarded to the members by the library
+
+    def set_style_targets(self, targets: dict):
+        for m in self.members:
+            for name in m.style_layers:
+                m.set_style_target(name, targets[name])
+
+    def step(self):
+        """One optimizer.step() of every member that is not frozen: one CUDA-graph launch."""
+        self.head.lbfgs_step()
+
+    def freeze(self, k: int, frozen: bool = True):
+        with torch.cuda.device(self.device):
+            check(self.lib.nst_lbfgs_freeze(self.members[k].handle, 1 if frozen else 0, _stream_ptr(self.device)))
+
+    def run_batch_host(self, ins, outs, num_steps: int, ca_w1=None, ca_w2=None):
+        """ins / outs: lists (<= batch) of contiguous pinned uint8 [H,W,3] host tensors; returns the evaluations each frame ran."""
+        cnt = len(ins)
+        pi = (C.c_void_p * cnt)(*[t.data_ptr() for t in ins])
+        po = (C.c_void_p * cnt)(*[t.data_ptr() for t in outs])
+        calls = (C.c_int * cnt)()
+        with torch.cuda.device(self.device):
+            check(self.lib.nst_run_batch_host(self.head.handle, cnt, pi, po, int(num_steps), 1 if ca_w1 is not None else 0,
+                                              _ptr(ca_w1), _ptr(ca_w2), _stream_ptr(self.device), calls))
+        return list(calls)
+
+    def bytes(self) -> int:
+        return self.head.bytes()
+
+    def close(self):
+        for m in self.members:
+            m.handle = None
+        self.members = []
+        if getattr(self, "head", None) is not None:
+            self.head.close()
+            self.head = None
 
     def __del__(self):
         try:

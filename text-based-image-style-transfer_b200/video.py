@@ -87,7 +87,8 @@ class FrameStyler:
     apply_video_process (app.py:794-798 -> run_multi_style_transfer) with everything frame-independent hoisted."""
 
     def __init__(self, vgg_mean, vgg_std, frame_hw, style_imgs: List[torch.Tensor], w_style, w_content, w_tv, w_edge,
-                 num_steps: int, style_img_weight=0.5, channel_attention=False, device="cuda", concurrent: int = 1):
+                 num_steps: int, style_img_weight=0.5, channel_attention=False, device="cuda", concurrent: int = 1,
+                 batch: int = 1):
         from .multi_style_transfer.run_style_transfer import StyleTransferSession, STYLE_LAYERS, channel_attention_gate_weights
         from .engine import _require_cuda
         self.device = _require_cuda(device)
@@ -123,6 +124,22 @@ class FrameStyler:
                                                       style_img_weight, self.device, style_targets=self.session.style_targets))
         self._ins = [self._in] + [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in self.sessions[1:]]
         self._outs = [self._out] + [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in self.sessions[1:]]
+        # `batch` frames per LAUNCH (process_block): one head plan whose tcgen05 convolution / Gram launches carry a batch
+        # dimension (engine.BatchPlan, nst_batch_create) - SURVEY 8f row 2 as written.  Small frames then fill the GPU the way
+        # one large frame does (four 256 x 256 frames = the tiles of one 512 x 512 frame).  Frame sizes must be multiples of 16.
+        self.batch_plan = None
+        if int(batch) > 1:
+            from . import engine
+            from .multi_style_transfer.run_style_transfer import CONTENT_LAYERS
+            s0 = self.session
+            with torch.cuda.device(self.device), torch.cuda.stream(s0.stream):
+                self.batch_plan = engine.BatchPlan(s0.net, H, W, STYLE_LAYERS, CONTENT_LAYERS, int(batch), mean=s0.mean, std=s0.std)
+                self.batch_plan.set_weights(w_style, w_content, w_tv, w_edge)
+                self.batch_plan.set_style_targets(s0.style_targets)
+                s0.stream.synchronize()
+            while len(self._ins) < int(batch):
+                self._ins.append(torch.empty((H, W, 3), dtype=torch.uint8).pin_memory())
+                self._outs.append(torch.empty((H, W, 3), dtype=torch.uint8).pin_memory())
 
     def _run_one(self, frame_u8: torch.Tensor) -> torch.Tensor:
         """One frame through nst_run_frame_host; returns the pinned host buffer it was written to (valid until the next call)."""
@@ -143,6 +160,19 @@ class FrameStyler:
         from . import _lib
         n = int(frames_u8.shape[0])
         out = torch.empty((n,) + tuple(frames_u8.shape[1:]), dtype=torch.uint8, device=out_device if out_device is not None else "cpu")
+        if self.batch_plan is not None:
+            B = self.batch_plan.batch
+            w1, w2 = self.ca or (None, None)
+            s0 = self.session
+            for lo in range(0, n, B):
+                cnt = min(B, n - lo)
+                for j in range(cnt):
+                    self._ins[j].copy_(frames_u8[lo + j])
+                with torch.cuda.device(self.device), torch.cuda.stream(s0.stream):
+                    self.batch_plan.run_batch_host(self._ins[:cnt], self._outs[:cnt], self.num_steps, w1, w2)
+                for j in range(cnt):
+                    out[lo + j].copy_(self._outs[j])
+            return out
         K = len(self.sessions)
         if K == 1:
             for k in range(n):
@@ -167,6 +197,9 @@ class FrameStyler:
         return out
 
     def close(self):
+        if self.batch_plan is not None:
+            self.batch_plan.close()
+            self.batch_plan = None
         for s in self.sessions:
             s.close()
 

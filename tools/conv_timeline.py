@@ -34,22 +34,24 @@ nst_b200._lib.check(lib.nst_plan_timeline(sess.plan.handle, 0, buf, st))
 v = list(buf)
 spans = []
 for slot in range(48):
-    t0, t1, tw, ta, tf0, tf1, tl = v[8 * slot:8 * slot + 7]
+    t0, t1, tw, ta, tf0, tf1, tl, ck = v[8 * slot:8 * slot + 8]
     if t1 == 0:
         continue
     tag = ("fwd", "dgrad", "gram_bwd")[slot // 16]
-    spans.append((t0, t1, "%s %d" % (tag, slot % 16), tw, ta, tf0, tf1, tl))
+    spans.append((t0, t1, "%s %d" % (tag, slot % 16), tw, ta, tf0, tf1, tl, ck))
 spans.sort()
 base = spans[0][0]
 print("%-12s %10s %10s %10s %10s | %s" % ("launch", "start us", "end us", "span us", "gap us",
       "previous launch's last CTA end -> dependency wait returns -> first patch of the first CTA (.. of the last CTA) -> last MMA issued -> last accumulator complete -> last CTA end"))
 prev_end = None
 tot = {"fwd": 0.0, "dgrad": 0.0, "gram_bwd": 0.0}
-for t0, t1, name, tw, ta, tf0, tf1, tl in spans:
+for t0, t1, name, tw, ta, tf0, tf1, tl, ck in spans:
     gap = (t0 - prev_end) / 1e3 if prev_end is not None else 0.0
     extra = ""
     if prev_end is not None and tw != 2 ** 64 - 1 and ta != 0:
         extra = " | %6.1f %6.1f (%4.1f) %6.1f %6.1f %6.1f" % ((tw - prev_end) / 1e3, (tf0 - tw) / 1e3, (tf1 - tw) / 1e3, (tl - tf0) / 1e3, (ta - tl) / 1e3, (t1 - ta) / 1e3)
+        if ck & 0xffffffff:
+            extra += "  SM clock %4.0f MHz" % ((ck >> 32) * 1e3 / (ck & 0xffffffff))
     print("%-12s %10.1f %10.1f %10.1f %10.1f%s" % (name, (t0 - base) / 1e3, (t1 - base) / 1e3, (t1 - t0) / 1e3, gap, extra))
     tot[name.split()[0]] += (t1 - t0) / 1e3
     prev_end = max(prev_end, t1) if prev_end is not None else t1
