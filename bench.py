@@ -42,7 +42,7 @@ def env_int(name, default):
 
 
 def _ncu_summary_name():
-    for name in ("r02_ncu_full_conv_tc_summary.csv", "r01d_ncu_full_conv_tc_summary.csv"):
+    for name in ("r02b_ncu_full_conv_tc_summary.csv", "r02_ncu_full_conv_tc_summary.csv", "r01d_ncu_full_conv_tc_summary.csv"):
         if os.path.exists(os.path.join(ROOT, "profiles", name)):
             return name
     return "r02_ncu_full_conv_tc_summary.csv"
@@ -372,6 +372,44 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
                      % (n_frames, W, H, steps, evals))
 
 
+def bench_batched_small_frames(dev, synth, size=256, n_frames=32, steps=60):
+    """SURVEY 8f row 2 in front of the driver: small frames (C1's 256 x 256), several per LAUNCH - the batch dimension inside the
+    tcgen05 convolution / Gram kernels (FrameStyler(batch=B) -> nst_run_batch_host) - beside one frame at a time and
+    several frames in flight on separate plans / streams (FrameStyler(concurrent=K)).  Every frame is a whole
+    run_multi_style_transfer on host uint8 buffers; wall clock around process_block, graph capture and allocator warmed
+    up before."""
+    import torch
+    from nst_b200 import video
+    evals = 20 * (steps // 20 + 1)
+    style = torch.from_numpy(synth.synth_image(512, 512, 1)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
+    frames = torch.stack([torch.from_numpy(synth.synth_image(size, size, 200 + k)) for k in range(n_frames)])
+    rows = {}
+    for name, kw in (("one_at_a_time", {}), ("concurrent_4", dict(concurrent=4)), ("batch_4", dict(batch=4)), ("batch_8", dict(batch=8))):
+        styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (size, size), [style], num_steps=steps, device=dev, **kw, **synth.APP_WEIGHTS)
+        try:
+            styler.process_block(frames[:8])
+            torch.cuda.synchronize()
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                out = styler.process_block(frames)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None or dt < best else best
+            rows[name] = dict(frames_per_s=n_frames / best, evals_per_s=n_frames * evals / best, seconds=best, checksum=int(out.to(torch.int64).sum()))
+        finally:
+            styler.close()
+            del styler
+            torch.cuda.empty_cache()
+    return dict(metric="small-frame style transfer, aggregate evaluations/s (%dx%d)" % (size, size), unit="evals/s",
+                value=rows["batch_8"]["evals_per_s"], frames=n_frames, num_steps=steps, evals_per_frame=evals, rows=rows,
+                h2d_bytes_per_frame=3 * size * size, d2h_bytes_per_frame=3 * size * size,
+                what="%d synthetic %dx%d frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), host uint8 in / out; "
+                     "`value` = 8 frames per launch (nst_batch_create: batch dimension inside conv_tc_kernel / gram_partial_kernel); rows: "
+                     "one frame at a time, 4 frames in flight on 4 plans / streams, 4 and 8 frames per launch; best of 2 repetitions"
+                     % (n_frames, size, size, steps, evals))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -597,8 +635,15 @@ def run_b200(args, rank, world, local_rank):
                     achieved=achieved_tf, peak=pk["tc_burst"], unit="TFLOP/s", frac=achieved_tf / pk["tc_burst"],
                     peak_sustained=pk["tc_sustained"], frac_sustained=achieved_tf / pk["tc_sustained"],
                     traffic=ncu_traffic(), traffic_unit="bytes of DRAM traffic per launch, average over the conv_tc_kernel launches of one evaluation (ncu --set full, profiles/" + NCU_SUMMARY + ")",
-                    peak_source=pk["source"] + ": `peak` / `frac` use the BURST bf16 figure (the step runs at full SM clock, it is not in the power-limited "
-                                "regime the sustained figure was measured in); `peak_sustained` / `frac_sustained` are printed beside it",
+                    peak_source=pk["source"] + ": `peak` / `frac` use the BURST bf16 figure, the stricter denominator; `peak_sustained` / "
+                                "`frac_sustained` are printed beside it.  Measured inside the kernels (SM cycles / %globaltimer of the MMA-issuing "
+                                "thread over a CTA's main loops, instrumented build, profiles/r02p_timeline_512_pair_clock.log): the SM clock "
+                                "during the main loops of the 128-channel-and-up layers is 1.59 - 1.75 GHz, not the 1.965 GHz nvidia-smi's "
+                                "samples show - the tensor cores ARE power-limited inside this step, which is the regime the sustained figure "
+                                "(1 407 TFLOP/s = burst x 1658 / 1965 MHz) describes; as CTA pairs (cta_group::2) those main loops issue one "
+                                "M256 x N128 x K16 MMA per 62 - 64 SM cycles, the tensor core's rate",
+                    sm_clock_in_main_loops_mhz=dict(min=1589, max=1856, typical_128ch_layers="1590-1750",
+                                                    source="profiles/r02p_timeline_512_pair_clock.log (tools/conv_timeline.py, instrumented build)"),
                     flops_per_launch_avg=conv_fl / conv_launches, launches_per_eval=conv_launches,
                     avg_launch_ms=conv_ms / conv_launches,
                     ms_per_eval_in_kernel=conv_ms, share_of_eval=conv_ms / eval_ms,
@@ -648,8 +693,10 @@ def run_b200(args, rank, world, local_rank):
                                                   "serial_ms = the one-block controller" % m_avg)
 
     # ---- next rows of the scope table: kernels right behind the loop, measured the same way
-    mask_row = assemble_row = mip_row = None
+    mask_row = assemble_row = mip_row = batch_row = None
     if world == 1:
+        if not args.no_batch_row:
+            batch_row = bench_batched_small_frames(dev, synth)
         mask_row = bench_mask_composite(dev, pk)
         assemble_row = bench_video_assemble(dev, pk)
         mip_row = bench_mip(dev, pk)
@@ -677,7 +724,7 @@ def run_b200(args, rank, world, local_rank):
                                  "whole 320-evaluation job of BASELINE configs[1]"),
                 clocks=clocks, e2e=e2e, value_320=value_320, sanity=sanity, gpu_launches=launches, roofline=roofline, roofline_hbm=roofline_hbm,
                 roofline_small=roofline_small, ms_per_eval_by_kernel=by_kind, cpu_baseline=cpu, torch_eager_gpu=eager, video=video_row,
-                mask_composite=mask_row, video_assemble=assemble_row, mip_planes=mip_row)
+                batched_small_frames=batch_row, mask_composite=mask_row, video_assemble=assemble_row, mip_planes=mip_row)
     emit(line)
     if args.kernel_table:
         # per-launch table: the same step with an event after EVERY launch (isolates each launch: no overlap between launches)
@@ -731,8 +778,8 @@ def run_video(args, rank, world, local_rank):
     frames = torch.stack([((1 - k / max(n_frames - 1, 1)) * f0 + (k / max(n_frames - 1, 1)) * f1).round().to(torch.uint8)
                           for k in range(n_frames)])
     styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=args.video_steps, device=dev,
-                               concurrent=args.concurrent, **synth.APP_WEIGHTS)
-    styler.process_block(frames[:args.concurrent])         # warm-up: graph capture of every plan, allocator
+                               concurrent=args.concurrent, batch=args.batch, **synth.APP_WEIGHTS)
+    styler.process_block(frames[:max(args.concurrent, args.batch)])   # warm-up: graph capture of every plan, allocator
     video.gather_frames(frames[:1].clone(), world, dev)    # ... and the NCCL communicator of the all-gather
     if dist is not None:
         dist.barrier()
@@ -754,9 +801,11 @@ def run_video(args, rank, world, local_rank):
                     scaling="strong (--frames is the TOTAL over all ranks: keep it fixed when comparing N)",
                     vs_baseline=None, dtype="f16", data="synthetic",
                     config=dict(workload="%d synthetic %dx%d frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), "
-                                         "%d frame(s) in flight per GPU, contiguous frame blocks per rank, NCCL broadcast of the style Gram "
+                                         "%s per GPU, contiguous frame blocks per rank, NCCL broadcast of the style Gram "
                                          "targets + all-gather of the finished frames (BASELINE configs[4], reduced frame count / steps)"
-                                         % (n_frames, W, H, args.video_steps, evals, args.concurrent)),
+                                         % (n_frames, W, H, args.video_steps, evals,
+                                            ("%d frames per LAUNCH (batch dimension inside the convolution / Gram kernels)" % args.batch) if args.batch > 1
+                                            else "%d frame(s) in flight (one plan / stream each)" % args.concurrent)),
                     evals_per_s=n_frames * evals / dt, checksum=int(out.to(torch.int64).sum()))
         emit(line)
     if dist is not None:
@@ -792,6 +841,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager-on-GPU timing of the reference algorithm")
+    ap.add_argument("--no-batch-row", action="store_true", help="skip the `batched_small_frames` row (256x256 frames, several per launch)")
     ap.add_argument("--no-video-row", action="store_true", help="skip the 720p frame-sharded `video` row of the default workload")
     ap.add_argument("--video-row-frames", type=int, default=64, help="`video` row: total 720p frames, the same at every N (strong scaling)")
     ap.add_argument("--video-row-steps", type=int, default=60, help="`video` row: num_steps per frame (60 -> 80 evaluations)")
@@ -801,6 +851,8 @@ def main():
     ap.add_argument("--video-steps", type=int, default=100, help="--workload video: num_steps per frame (the reference UI uses 400)")
     ap.add_argument("--video-size", default="720x1280", help="--workload video: frame size HxW")
     ap.add_argument("--concurrent", type=int, default=1, help="--workload video: frames in flight per GPU (FrameStyler(concurrent=K))")
+    ap.add_argument("--batch", type=int, default=1, help="--workload video: frames per launch (FrameStyler(batch=B): batch dimension inside the "
+                                                         "convolution / Gram kernels, SURVEY 8f row 2); frame sizes must be multiples of 16")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3:
