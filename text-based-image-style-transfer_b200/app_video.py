@@ -106,11 +106,13 @@ def apply_video_process(video_filepath, checkbox_values, slowmo_slider_input=Non
                         p_select_im=False, p_in=None, p_in_slid=10,
                         style_image_weight=None, style_image1=None, style_image2=None, color_palette_style=None,
                         d_check_box=None, depth_mip_n=2,
-                        *, device="cuda", num_steps=NUM_STEPS, jpeg=True, concurrent=1, output_video_filepath=None,
+                        *, device="cuda", num_steps=NUM_STEPS, jpeg=True, concurrent=1, batch=1, output_video_filepath=None,
                         frame_sink: Optional[Callable[[np.ndarray], None]] = None):
     """Apply the selected style-transfer effects on a video and save it (reference: app.py:742-864; same positional
     parameters).  Keyword-only extras: `device` (a CUDA device), `num_steps` (the reference hard-codes 400, app.py:380),
-    `jpeg` (reproduce the JPEG round trip of app.py:790-791), `concurrent` (frames in flight per GPU), `output_video_filepath`
+    `jpeg` (reproduce the JPEG round trip of app.py:790-791), `concurrent` (frames in flight per GPU, bit-identical per frame), `batch` (frames per LAUNCH for small
+    frames whose sides are multiples of 16 - a batch dimension inside the convolution / Gram kernels, video.FrameStyler; per frame
+    equal to the one-frame path up to the order of the Gram sums), `output_video_filepath`
     (default: a fresh temporary directory like app.py:844), `frame_sink` (called on rank 0 with the final BGR frame list
     [F,H,W,3] before it is encoded).  Under torch.distributed every rank must call this; rank 0 returns the path."""
     from PIL import Image
@@ -136,7 +138,7 @@ def apply_video_process(video_filepath, checkbox_values, slowmo_slider_input=Non
             raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (3) at non-singleton dimension 1"
                                % [t.shape[1] for t in style_t if t.shape[1] != 3][0])
         styler = video.FrameStyler(VGG_MEAN, VGG_STD, (H, W), style_t, W_STYLE, W_CONTENT, W_TV, W_EDGE, num_steps=num_steps,
-                                   style_img_weight=weight, channel_attention=ca, device=dev, concurrent=concurrent)
+                                   style_img_weight=weight, channel_attention=ca, device=dev, concurrent=concurrent, batch=batch)
         try:
             cur = video.run_sharded(cur, _Progress(styler, num_frames, rank), dev).cpu()
         finally:
