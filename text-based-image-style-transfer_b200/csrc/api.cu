@@ -58,6 +58,8 @@ extern "C" int nst_abi_version(void) { return NST_ABI_VERSION; }
 extern "C" const char* nst_last_error(void) { return g_err; }
 
 static int g_num_sms = 0;
+// SMs the convolution launches may occupy (NST_CONV_SMS; default all): leaves the rest to work of another frame that runs beside them
+static int g_conv_sms = 0;
 extern "C" int nst_device_check(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -78,6 +80,11 @@ extern "C" int nst_device_check(void) {
     if (e == cudaSuccess) e = lbfgs_init();
     if (e != cudaSuccess) return fail(NST_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(e));
     g_num_sms = prop.multiProcessorCount;
+    g_conv_sms = g_num_sms;
+    if (getenv("NST_CONV_SMS") != nullptr) {
+      const int v = atoi(getenv("NST_CONV_SMS"));
+      if (v >= 2 && v <= g_num_sms) g_conv_sms = v & ~1;
+    }
   }
   if (dev >= 0 && dev < 64) checked[dev] = true;
   return NST_OK;
@@ -768,14 +775,14 @@ extern "C" int nst_plan_set_weights(nst_plan* p, float w_style, float w_content,
 // conv1_1 forward: tcgen05 with fp16 high/low operand splitting (conv1_tc.cu), or the fp32 CUDA-core kernel (pixel.cu)
 // when the TMA output maps are switched off (NST_DIRECT_STORES / NST_CONV1_CUDA_CORES)
 static cudaError_t conv1_forward(nst_plan* p, const float* x, cudaStream_t s) {
-  if (p->fwd[0].tma_out) return launch_conv1_tc(p->fwd[0], x, p->net->w32[0], p->pc, g_num_sms, s);
+  if (p->fwd[0].tma_out) return launch_conv1_tc(p->fwd[0], x, p->net->w32[0], p->pc, g_conv_sms, s);
   return launch_conv1_fwd(x, p->net->w32[0], p->net->b32[0], p->tap[0], p->act[0], p->H, p->W, p->pc, s);
 }
 
 static int forward_enqueue(nst_plan* p, const float* x, cudaStream_t s) {
   const nst_net* net = p->net;
   CK(conv1_forward(p, x, s));
-  for (int i = 1; i < p->n_layers; ++i) CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
+  for (int i = 1; i < p->n_layers; ++i) CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_conv_sms, s));
   return NST_OK;
 }
 
@@ -1118,7 +1125,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     if (max_content == 0) CK(edge(EV_CONTENT_IN, s, s2));
     for (int i = 1; i < p->n_layers; ++i) {
       TB(NST_K_CONV_FWD);
-      CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_num_sms, s));
+      CK(launch_conv_tc(p->fwd[i], CONV_FWD, g_conv_sms, s));
       TM(NST_K_CONV_FWD, i);
       if (i == at_shallow) {
         // ---- side: Gram, style MSE and backward operand of the shallower style layers
@@ -1187,7 +1194,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
       const int i = p->style_conv[l];
       if (p->seed_folded[i]) continue;  // computed inside the data gradient of conv i+1
       TB(NST_K_GRAM_BWD);
-      CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_num_sms, s2));
+      CK(launch_conv_tc(p->scale[i], CONV_SCALE, g_conv_sms, s2));
       ++nl;
       TM(NST_K_GRAM_BWD, i);
       const int cl = content_index(p, i);
@@ -1249,7 +1256,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
     if (use_vgg) {
       if (deep_style) {
         TB(NST_K_GRAM_BWD);
-        CK(launch_conv_tc(p->scale[last], CONV_SCALE, g_num_sms, s));
+        CK(launch_conv_tc(p->scale[last], CONV_SCALE, g_conv_sms, s));
         ++nl;
         TM(NST_K_GRAM_BWD, last);
         const int cl = content_index(p, last);
@@ -1265,7 +1272,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
         if (conc && i - 1 == max_content) CK(cudaStreamWaitEvent(s, p->ev[EV_CONTENT], 0));
         if (conc && i - 1 == max_shallow) CK(cudaStreamWaitEvent(s, p->ev[EV_SEEDS], 0));
         TB(NST_K_CONV_DGRAD);
-        CK(launch_conv_tc(p->dgrad[i], CONV_DGRAD, g_num_sms, s));
+        CK(launch_conv_tc(p->dgrad[i], CONV_DGRAD, g_conv_sms, s));
         ++nl;
         TM(NST_K_CONV_DGRAD, i);
       }
@@ -1282,7 +1289,7 @@ static int eval_enqueue(nst_plan* p, const float* x, float* grad, int* counter, 
             ConvParams d = img[m]->dgrad[0];
             d.out_pix = img_grad(m);
             for (int c = 0; c < 3; ++c) d.inv_std[c] = 1.f / p->pc.stdv[c];
-            CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_num_sms, s));
+            CK(launch_conv_tc(d, CONV_DGRAD_PIX, g_conv_sms, s));
           }
           nl += n_img - 1;
         }

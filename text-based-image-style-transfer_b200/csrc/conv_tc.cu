@@ -827,8 +827,21 @@ static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t s
   // live on L1 hits (34 KB less L1 cost conv1_2's data gradient 17 us inside the step)
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES - (TMA_OUT ? 0 : Cfg::EPI_BYTES);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  // NST_KERNEL_PRIO: the tensor-core launches get the highest launch priority, the optimizer's streaming passes the lowest
+  // (lbfgs.cu), whatever the priority of the stream: when work of two frames shares the GPU an SM that frees up goes to a
+  // waiting convolution CTA first
+  static const int prio = [] {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    return getenv("NST_KERNEL_PRIO") != nullptr ? greatest : 1000;
+  }();
+  if (prio != 1000) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = prio;
+    ++na;
+  }
   if (PAIR) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;

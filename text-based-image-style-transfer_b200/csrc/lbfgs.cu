@@ -469,11 +469,25 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  static const int prio = [] {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    return getenv("NST_KERNEL_PRIO") != nullptr ? least : 1000;
+  }();
+  if (prio != 1000) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = prio;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 cudaError_t launch_lbfgs_pass1(const LbfgsBuffers& b, cudaStream_t s) {
