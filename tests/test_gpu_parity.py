@@ -434,7 +434,9 @@ def test_config5_video_frames_match_single_image_runs(nst, rst, oracle):
 @pytest.mark.parametrize("env", [
     {"NST_DIRECT_STORES": "1", "NST_NO_SEED_FOLD": "1"},   # per-thread stores, Gram backward as separate 1x1 launches
     {"NST_NO_PDL": "1", "NST_NO_SIDE_STREAM": "1"},        # no programmatic dependent launch, single stream
-], ids=["direct-stores-unfolded", "no-pdl-single-stream"])
+    {"NST_PAIR": "0"},                                      # single-CTA convolutions (cta_group::1, two MMA issuers on one-slice layers)
+    {"NST_PAIR": "2", "NST_CONV_SMS": "100", "NST_KERNEL_PRIO": "1"},   # pairs for the data gradients only, fewer SMs, launch priorities
+], ids=["direct-stores-unfolded", "no-pdl-single-stream", "single-cta", "mixed-pairs-100-sms"])
 def test_optional_paths_stay_parity_green(env):
     """The schedule / epilogue variants that are switched by environment variables (read when the library or a plan is
     created, hence a fresh process) must give the same answers: __graft_entry__.smoke() checks step-0 losses and
