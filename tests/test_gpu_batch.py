@@ -5,6 +5,7 @@ gram_matrix's batch normalisation (style_transfer_losses.py:84-93) is why per-im
 
 Every image of a batch is held to the ORACLE's loop on that image alone, and to this library's own single-image plan."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -145,3 +146,61 @@ def test_frame_styler_batch_against_oracle_and_frame_by_frame(nst, oracle, vgg_w
                 mse = np.mean((got[k].astype(np.float64) - ref.astype(np.float64)) ** 2)
                 assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= PSNR_MIN, (k, mse)
             assert not np.array_equal(got[k], frames[k])
+
+
+def test_batch_of_two_goldens_with_different_styles(nst, rst, oracle):
+    """BASELINE configs[1] twice in ONE head: the natural and the synthetic 512 x 512 pair of tests/golden (written by the
+    UNMODIFIED reference, make_golden_large.py) as the two members of a batch - different content AND different style
+    targets per member - for the whole num_steps = 300 job (320 evaluations each, 16 graph launches): every member's loss
+    curve within 1e-2 of its golden and its final image at >= 40 dB, north_star's run-level tolerances."""
+    O = oracle
+    engine = importlib.import_module("text-based-image-style-transfer_b200.engine")
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    names = ["nat512", "syn512"]
+    gs = []
+    for n in names:
+        path = os.path.join(gdir, "large_%s.npz" % n)
+        if not os.path.exists(path):
+            pytest.skip("golden %s not generated" % path)
+        gs.append(np.load(path))
+    sessions, bp = [], None
+    try:
+        for g in gs:
+            sessions.append(rst.StyleTransferSession(O.VGG_MEAN, O.VGG_STD, (512, 512), [O.to_tensor_u8(g["style0_u8"]).cuda()],
+                                                     device="cuda", **O.APP_WEIGHTS))
+        s0 = sessions[0]
+        with torch.cuda.stream(s0.stream):
+            bp = engine.BatchPlan(s0.net, 512, 512, rst.STYLE_LAYERS, rst.CONTENT_LAYERS, 2, mean=s0.mean, std=s0.std)
+            bp.set_weights(*s0.weights)
+            for m, ses in zip(bp.members, sessions):
+                for name in m.style_layers:
+                    m.set_style_target(name, ses.style_targets[name])
+            cs = [O.to_tensor_u8(g["content_u8"]).cuda() for g in gs]
+            for m, c in zip(bp.members, cs):
+                prepare_member(m, c, 352)
+            calls = [0, 0]
+            for _ in range(40):
+                if all(c > 300 for c in calls):          # run_style_transfer.py:100 per member
+                    break
+                for k in range(2):
+                    if calls[k] > 300:
+                        bp.freeze(k)
+                bp.step()
+                calls = [m.lbfgs_status().closure_calls for m in bp.members]
+            got = [(m.lbfgs_status(), m.lbfgs_trace(352)[:, 0].double().numpy(), m.lbfgs_x().cpu()) for m in bp.members]
+        for k, g in enumerate(gs):
+            st, tr, x = got[k]
+            ref = g["loss_trace"]
+            assert st.closure_calls == int(g["n_evals"]) == len(ref) == len(tr)
+            dev = np.abs(tr - ref) / np.abs(ref)
+            p = psnr(x, torch.from_numpy(g["x_final"].astype(np.float32)))
+            print("\n[batch of two goldens, member %d = %s] %d evals, loss %.5f -> %.5f (reference %.5f -> %.5f); max loss-curve deviation "
+                  "%.2e (reference self-noise %.2e); final image %.1f dB (reference self-noise %.1f dB)"
+                  % (k, names[k], len(tr), tr[0], tr[-1], ref[0], ref[-1], dev.max(), float(g["self_loss_dev"]), p, float(g["self_psnr"])))
+            assert dev.max() <= CURVE_TOL, (names[k], float(dev.max()), int(dev.argmax()))
+            assert p >= PSNR_MIN, (names[k], p)
+    finally:
+        if bp is not None:
+            bp.close()
+        for ses in sessions:
+            ses.close()
