@@ -332,8 +332,11 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
     frames = torch.stack([((1 - k / max(n_frames - 1, 1)) * f0 + (k / max(n_frames - 1, 1)) * f1).round().to(torch.uint8)
                           for k in range(n_frames)])
     t_setup = time.perf_counter()
-    styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=steps, device=dev, **synth.APP_WEIGHTS)
-    styler.process_block(frames[:1])                       # warm-up: graph capture, allocator, pinned buffers
+    # two frames per launch (nst_batch_create: batch dimension inside the convolution / Gram kernels): +3 % at 720p, where one
+    # frame already fills the GPU (profiles/README.md); --video-row-batch 1 = one frame at a time
+    styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=steps, device=dev, batch=args.video_row_batch,
+                               **synth.APP_WEIGHTS)
+    styler.process_block(frames[:max(1, args.video_row_batch)])   # warm-up: graph capture, allocator, pinned buffers
     lo, hi = video.shard_range(n_frames, world, rank)
     video.gather_frames(frames[lo:hi].to(dev), n_frames, dev)    # ... and the communicator / buffers of the all-gather (same sizes)
     torch.cuda.synchronize()
@@ -366,6 +369,7 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
                 frames=n_frames, frames_per_rank=hi - lo, n_gpus=world, num_steps=steps, evals_per_frame=evals, seconds=dt,
                 slowest_rank_compute_s=compute, gather_s_rank0=gather, setup_s_untimed=setup_s, evals_per_s=n_frames * evals / dt,
                 scaling="strong", h2d_bytes_per_frame=3 * H * W, d2h_bytes_per_frame=3 * H * W, checksum=checksum,
+                frames_per_launch=args.video_row_batch,
                 what="%d synthetic %dx%d frames in total at every N (strong scaling), one shared 512x512 style, num_steps=%d (%d evaluations per "
                      "frame; the reference UI uses 240 frames x num_steps=400), contiguous frame blocks per rank, NCCL broadcast of the style Gram "
                      "targets (untimed setup) + all-gather of the finished frames (timed); wall clock, barrier on both sides, max over ranks"
@@ -844,6 +848,7 @@ def main():
     ap.add_argument("--no-batch-row", action="store_true", help="skip the `batched_small_frames` row (256x256 frames, several per launch)")
     ap.add_argument("--no-video-row", action="store_true", help="skip the 720p frame-sharded `video` row of the default workload")
     ap.add_argument("--video-row-frames", type=int, default=64, help="`video` row: total 720p frames, the same at every N (strong scaling)")
+    ap.add_argument("--video-row-batch", type=int, default=2, help="`video` row: frames per launch on every GPU (FrameStyler(batch=B)); 1 = one at a time")
     ap.add_argument("--video-row-steps", type=int, default=60, help="`video` row: num_steps per frame (60 -> 80 evaluations)")
     ap.add_argument("--kernel-table", default=None, help="write the per-launch timing table (CSV) here")
     ap.add_argument("--workload", default="pair512", choices=["pair512", "video"])
