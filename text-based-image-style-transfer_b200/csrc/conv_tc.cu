@@ -37,8 +37,17 @@ static constexpr int HALO_TX_BYTES = HALO_ROWS * BLOCK_K * 2;     // 23040
 static constexpr int HALO_STAGE_BYTES = 23 * 1024;                // keeps the next stage 1024-byte aligned
 static constexpr int FLAT_TX_BYTES = BLOCK_M * BLOCK_K * 2;       // 1x1 convolution: no halo
 static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
+#ifndef NST_HALO64
+#define NST_HALO64 3
+#endif
+#ifndef NST_HALO64_PAIR
+#define NST_HALO64_PAIR 3
+#endif
+#ifndef NST_HALO128_PAIR
+#define NST_HALO128_PAIR 4
+#endif
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 struct ConvCfg {
   // warps 0..3: TMA producer, MMA issuer, TMEM allocator, spare; then the epilogue warps.  Eight of them (two per TMEM
   // lane quarter, each taking half of the accumulator columns): the epilogue is a latency chain (tcgen05.ld -> math ->
@@ -47,13 +56,17 @@ struct ConvCfg {
   static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
   // Patches in flight: two.  Deeper rings (5 at N = 64, 8 at N = 16) were measured inside the captured step and made the
   // 64-channel data gradients slower (conv1_2: 39 -> 58 us), not faster: the operand stream is not what bounds them.
-  static constexpr int HALO_STAGES = 2;
+  // Round 2, inside the step on one box (bench.py, two repetitions each): 64-channel tiles with 2 / 3 / 4 patches in flight
+  // run the conv class in 426 / 419 / 421 us per evaluation - the data gradient of conv1_2 loads TWO operands per tile (patch
+  // and the tap tile of the folded Gram backward) and waited 10 of its 30 us for them with two stages.  As CTA pairs a weight
+  // stage is half as large, which pays for a third patch stage at N = 128 as well.
+  static constexpr int HALO_STAGES = (BLOCK_N == 64) ? (PAIR ? NST_HALO64_PAIR : NST_HALO64) : ((BLOCK_N == 128 && PAIR) ? NST_HALO128_PAIR : 2);
   // Filter taps per weight stage.  One pipeline iteration (barrier wait, fence, commit) costs a few hundred cycles of
   // the issuing thread and every tcgen05.mma about 45 (profiles/r01_mma_issue_rate.log); with one tap (4 MMAs) per
   // iteration the main loop was issue-bound at ~480 cycles per tap for every N <= 128.  Three taps per stage amortise it.
   static constexpr int TPS = BLOCK_N >= 256 ? 1 : (BLOCK_N >= 64 ? 3 : 9);
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // one tap
-  static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // one tap (both CTAs of a pair together)
+  static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES / (PAIR ? 2 : 1);   // a CTA of a pair stages half of the rows
   static constexpr int B_STAGES_FIT = (SMEM_BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
   static constexpr int B_STAGES = B_STAGES_FIT > 6 ? 6 : B_STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
@@ -84,8 +97,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // halves the per-MMA issue cost that bounds the N = 64 layers.  The leader (cluster rank 0) issues every MMA; both CTAs keep
 // their own producer and epilogue warps.
 template <int BLOCK_N, int MODE, bool TMA_OUT, bool PAIR>
-__global__ void __launch_bounds__(ConvCfg<BLOCK_N>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N, PAIR>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stages
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -816,7 +829,7 @@ int conv_grid_ctas(const ConvParams& p, int num_sms) {
 
 template <int BLOCK_N, int MODE, bool TMA_OUT, bool PAIR>
 static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, PAIR>;
   const int grid = conv_grid_ctas(p, num_sms);
   static const bool pdl = getenv("NST_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
@@ -887,10 +900,10 @@ static cudaError_t init_one() {
   if constexpr ((MODE == CONV_FWD || MODE == CONV_DGRAD) && (BLOCK_N == 64 || BLOCK_N == 128)) {
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<BLOCK_N>::SMEM_BYTES);
+                               ConvCfg<BLOCK_N, true>::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<BLOCK_N>::SMEM_BYTES);
+                               ConvCfg<BLOCK_N, true>::SMEM_BYTES);
   }
   return e;
 }
