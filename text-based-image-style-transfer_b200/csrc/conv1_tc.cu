@@ -31,7 +31,13 @@ static constexpr int C1_N = 64;
 static constexpr int C1_A1_BYTES = 128 * 128;              // 128 pixels x [xh(32) | xl(32)] fp16
 static constexpr int C1_A2_BYTES = 128 * 128;              // 128 pixels x [xh(32) | unused]
 static constexpr int C1_STAGE_BYTES = C1_A1_BYTES + C1_A2_BYTES;
-static constexpr int C1_STAGES = 3;
+// im2col stages in flight.  Measured inside the step on one box (bench.py, two repetitions): 2 / 3 / 4 stages -> 30.7 / 32.5 /
+// 35.3 us per launch: the builder warps read the image through L1, which shares its 256 KB with shared memory - every 32 KB
+// stage is 32 KB less cache for the 3x overlapping patch reads.
+#ifndef NST_C1_STAGES
+#define NST_C1_STAGES 2
+#endif
+static constexpr int C1_STAGES = NST_C1_STAGES;
 static constexpr int C1_B_BYTES = 2 * C1_N * 128;          // B1, B2: 64 rows x 128 B each
 static constexpr int C1_PATCH = 3 * (C1_TILE_H + 2) * (C1_TILE_W + 2);  // 540 normalised input values
 static constexpr int C1_PATCH_PER_THREAD = (C1_PATCH + 127) / 128;      // 5

@@ -43,6 +43,9 @@ static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 #ifndef NST_HALO64_PAIR
 #define NST_HALO64_PAIR 3
 #endif
+#ifndef NST_HALO16
+#define NST_HALO16 2
+#endif
 #ifndef NST_HALO128_PAIR
 #define NST_HALO128_PAIR 4
 #endif
@@ -54,13 +57,16 @@ struct ConvCfg {
   // scattered 16-byte stores) and one warp per scheduler cannot hide it.
   static constexpr int EPI_WARPS = BLOCK_N >= 64 ? 8 : 4;
   static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
-  // Patches in flight: two.  Deeper rings (5 at N = 64, 8 at N = 16) were measured inside the captured step and made the
-  // 64-channel data gradients slower (conv1_2: 39 -> 58 us), not faster: the operand stream is not what bounds them.
-  // Round 2, inside the step on one box (bench.py, two repetitions each): 64-channel tiles with 2 / 3 / 4 patches in flight
-  // run the conv class in 426 / 419 / 421 us per evaluation - the data gradient of conv1_2 loads TWO operands per tile (patch
-  // and the tap tile of the folded Gram backward) and waited 10 of its 30 us for them with two stages.  As CTA pairs a weight
-  // stage is half as large, which pays for a third patch stage at N = 128 as well.
-  static constexpr int HALO_STAGES = (BLOCK_N == 64) ? (PAIR ? NST_HALO64_PAIR : NST_HALO64) : ((BLOCK_N == 128 && PAIR) ? NST_HALO128_PAIR : 2);
+  // Patches in flight.  r01 (single CTAs, the Gram backward still a launch of its own): two; deeper rings (5 at N = 64, 8 at
+  // N = 16) made the 64-channel data gradients slower inside the captured step (conv1_2: 39 -> 58 us).  Round 2, as CTA pairs,
+  // every build on the same box inside the step (profiles/r03_patch_stage_sweep.log): a pair CTA stages half of the weight
+  // rows, so a weight stage is half as large and the ring holds five of them at N = 128 beside FOUR patches (conv class 412 ->
+  // 406 us per evaluation; six patches leave two weight stages and starve the weight stream: 459 us); at N = 64 three patches
+  // (426 -> 419 us: the data gradient of conv1_2 loads two operands per tile - the patch and the tap tile of the folded Gram
+  // backward - and waited 10 of its 30 us for them with two stages).  conv1_1's gradient (N = 16) keeps two: its two MMA
+  // issuers own one patch stage each.
+  static constexpr int HALO_STAGES = (BLOCK_N == 64) ? (PAIR ? NST_HALO64_PAIR : NST_HALO64)
+                                                     : ((BLOCK_N == 128 && PAIR) ? NST_HALO128_PAIR : (BLOCK_N == 16 ? NST_HALO16 : 2));
   // Filter taps per weight stage.  One pipeline iteration (barrier wait, fence, commit) costs a few hundred cycles of
   // the issuing thread and every tcgen05.mma about 45 (profiles/r01_mma_issue_rate.log); with one tap (4 MMAs) per
   // iteration the main loop was issue-bound at ~480 cycles per tap for every N <= 128.  Three taps per stage amortise it.
