@@ -43,6 +43,9 @@ static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 #ifndef NST_HALO64_PAIR
 #define NST_HALO64_PAIR 3
 #endif
+#ifndef NST_HALO128_PAIR_DGRAD
+#define NST_HALO128_PAIR_DGRAD NST_HALO128_PAIR
+#endif
 #ifndef NST_HALO16
 #define NST_HALO16 2
 #endif
@@ -50,8 +53,14 @@ static constexpr int SMEM_BUDGET = 196608;  // bytes of operand staging per CTA
 #define NST_HALO128_PAIR 4
 #endif
 
-template <int BLOCK_N, bool PAIR = false>
+#ifndef NST_DGRAD_BUDGET
+#define NST_DGRAD_BUDGET SMEM_BUDGET
+#endif
+template <int BLOCK_N, bool PAIR = false, int MODE = CONV_FWD>
 struct ConvCfg {
+  // operand staging of this instantiation: the data gradients' epilogues read their masks / routing bytes / seeds through L1,
+  // which is what shared memory leaves of the SM's 256 KB
+  static constexpr int BUDGET = (MODE == CONV_DGRAD && BLOCK_N >= 64) ? NST_DGRAD_BUDGET : SMEM_BUDGET;
   // warps 0..3: TMA producer, MMA issuer, TMEM allocator, spare; then the epilogue warps.  Eight of them (two per TMEM
   // lane quarter, each taking half of the accumulator columns): the epilogue is a latency chain (tcgen05.ld -> math ->
   // scattered 16-byte stores) and one warp per scheduler cannot hide it.
@@ -66,14 +75,14 @@ struct ConvCfg {
   // backward - and waited 10 of its 30 us for them with two stages).  conv1_1's gradient (N = 16) keeps two: its two MMA
   // issuers own one patch stage each.
   static constexpr int HALO_STAGES = (BLOCK_N == 64) ? (PAIR ? NST_HALO64_PAIR : NST_HALO64)
-                                                     : ((BLOCK_N == 128 && PAIR) ? NST_HALO128_PAIR : (BLOCK_N == 16 ? NST_HALO16 : 2));
+                                                     : ((BLOCK_N == 128 && PAIR) ? (MODE == CONV_DGRAD ? NST_HALO128_PAIR_DGRAD : NST_HALO128_PAIR) : (BLOCK_N == 16 ? NST_HALO16 : 2));
   // Filter taps per weight stage.  One pipeline iteration (barrier wait, fence, commit) costs a few hundred cycles of
   // the issuing thread and every tcgen05.mma about 45 (profiles/r01_mma_issue_rate.log); with one tap (4 MMAs) per
   // iteration the main loop was issue-bound at ~480 cycles per tap for every N <= 128.  Three taps per stage amortise it.
   static constexpr int TPS = BLOCK_N >= 256 ? 1 : (BLOCK_N >= 64 ? 3 : 9);
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // one tap (both CTAs of a pair together)
   static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES / (PAIR ? 2 : 1);   // a CTA of a pair stages half of the rows
-  static constexpr int B_STAGES_FIT = (SMEM_BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
+  static constexpr int B_STAGES_FIT = (BUDGET - HALO_STAGES * HALO_STAGE_BYTES) / B_STAGE_BYTES;
   static constexpr int B_STAGES = B_STAGES_FIT > 6 ? 6 : B_STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 32 / 128 / 256 / 512: powers of two >= 32
   // data gradient with a folded Gram backward: two more accumulator stages (columns 2N .. 4N)
@@ -103,8 +112,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // halves the per-MMA issue cost that bounds the N = 64 layers.  The leader (cluster rank 0) issues every MMA; both CTAs keep
 // their own producer and epilogue warps.
 template <int BLOCK_N, int MODE, bool TMA_OUT, bool PAIR>
-__global__ void __launch_bounds__(ConvCfg<BLOCK_N, PAIR>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N, PAIR>;
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N, PAIR, MODE>::NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N, PAIR, MODE>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stages
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -835,7 +844,7 @@ int conv_grid_ctas(const ConvParams& p, int num_sms) {
 
 template <int BLOCK_N, int MODE, bool TMA_OUT, bool PAIR>
 static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N, PAIR>;
+  using Cfg = ConvCfg<BLOCK_N, PAIR, MODE>;
   const int grid = conv_grid_ctas(p, num_sms);
   static const bool pdl = getenv("NST_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
@@ -897,19 +906,19 @@ static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t str
 template <int BLOCK_N, int MODE>
 static cudaError_t init_one() {
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ConvCfg<BLOCK_N>::SMEM_BYTES);
+                                       ConvCfg<BLOCK_N, false, MODE>::SMEM_BYTES);
   if constexpr (MODE != CONV_DGRAD_PIX) {
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<BLOCK_N>::SMEM_BYTES);
+                               ConvCfg<BLOCK_N, false, MODE>::SMEM_BYTES);
   }
   if constexpr ((MODE == CONV_FWD || MODE == CONV_DGRAD) && (BLOCK_N == 64 || BLOCK_N == 128)) {
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<BLOCK_N, true>::SMEM_BYTES);
+                               ConvCfg<BLOCK_N, true, MODE>::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<BLOCK_N, true>::SMEM_BYTES);
+                               ConvCfg<BLOCK_N, true, MODE>::SMEM_BYTES);
   }
   return e;
 }
