@@ -217,6 +217,10 @@ int nst_lbfgs_ctl_clocks(nst_plan* plan, long long* out8, void* stream);
  * does (content target at the plan's content taps, edge target), then runs the whole loop. */
 int nst_run_frame_host(nst_plan* plan, const uint8_t* content_u8, uint8_t* out_u8, int num_steps, int channel_attention,
                        const float* ca_w1, const float* ca_w2, void* stream);
+/* shared != 0: other plans step on the same GPU at the same time as this one (several host threads / streams).  Their CTA-pair
+ * convolution launches are then issued without programmatic dependent launch - two such chains side by side can hang the GPU -
+ * at ~5 % of a single chain's speed.  nst_run_frames_host sets it itself for count > 1; nst_batch_create needs none (one chain). */
+int nst_plan_set_shared_gpu(nst_plan* plan, int shared);
 /* the same for `count` (<= 16) independent frames at once: plans[k] / streams[k] (all distinct, same weights and targets as a
  * frame-by-frame run would use) process content_u8[k] -> out_u8[k]; every frame's optimizer.step() is enqueued before the host
  * waits for the first one, so small frames (bound by per-launch latency) overlap: the per-frame body of apply_video_process,

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "nst_lbfgs_step_timed_grouped": (C.c_int, [_P, C.POINTER(NstLaunchTime), C.c_int, _P]),
     "nst_run_frames_host": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.POINTER(_P),
                                       C.POINTER(C.c_int)]),
+    "nst_plan_set_shared_gpu": (C.c_int, [_P, C.c_int]),
     "nst_batch_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "nst_batch_size": (C.c_int, [_P]),
     "nst_batch_member": (_P, [_P, C.c_int]),

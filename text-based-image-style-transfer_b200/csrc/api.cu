@@ -232,6 +232,7 @@ struct nst_plan {
   // ordinary single-image plans whose pointers to those tensors are slices of the head's: image `index`.  Everything per
   // image - pixel-space losses, content loss, loss assembly, conv1_1 (fp32 planar image on either side), the optimizer and
   // its history - runs per member; a member is also usable on its own (targets from the content frame, status, trace).
+  bool shared_gpu = false;   // nst_plan_set_shared_gpu: other plans step on this GPU at the same time
   int batch = 1;
   nst_plan* head = nullptr;
   int index = 0;
@@ -748,6 +749,20 @@ extern "C" int nst_plan_set_norm(nst_plan* p, const float mean[3], const float s
   }
   drop_graph(p);
   for (nst_plan* m : p->members) CKI(nst_plan_set_norm(m, mean, std));
+  return NST_OK;
+}
+
+// Plans that step at the same time on one GPU (several frames in flight, the planes of the depth variant): their CTA-pair
+// launches must not be chained by programmatic dependent launch (conv_tc.cu, launch_one_t).  nst_run_frames_host sets this
+// itself; a caller that steps several plans from several host threads / streams sets it on each of them.
+extern "C" int nst_plan_set_shared_gpu(nst_plan* p, int shared) {
+  if (!p) return fail(NST_ERR_ARG, "nst_plan_set_shared_gpu: null plan");
+  const bool want = shared != 0;
+  if (p->shared_gpu == want) return NST_OK;
+  p->shared_gpu = want;
+  for (int i = 0; i < NST_MAX_CONV; ++i) p->fwd[i].no_pdl_pair = p->dgrad[i].no_pdl_pair = p->scale[i].no_pdl_pair = want ? 1 : 0;
+  drop_graph(p);   // the launch attributes are baked into the captured step
+  for (nst_plan* m : p->members) CKI(nst_plan_set_shared_gpu(m, shared));
   return NST_OK;
 }
 
@@ -2065,6 +2080,8 @@ extern "C" int nst_run_frames_host(nst_plan* const* plans, int count, const uint
   int guard[MAX_FRAMES];
   memset(st, 0, sizeof(st));
   memset(guard, 0, sizeof(guard));
+  if (count > 1)
+    for (int k = 0; k < count; ++k) CKI(nst_plan_set_shared_gpu(plans[k], 1));   // several chains of pair launches side by side
   for (int k = 0; k < count; ++k)
     CKI(frame_begin(plans[k], content_u8[k], num_steps, channel_attention, ca_w1, ca_w2, static_cast<cudaStream_t>(streams[k])));
   for (;;) {

@@ -516,6 +516,20 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, PAIR, MODE>::NUM_THREADS, 1) 
       }
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if constexpr (PAIR) {
+      // The peer's epilogue warps release the accumulator stages of the last tiles with REMOTE arrivals on this CTA's
+      // barriers, and nobody would wait for them: the teardown barrier below orders execution, not those writes.  If this CTA
+      // left first, an arrival still in flight could land in the shared memory of the NEXT CTA scheduled on this SM - on the
+      // freshly initialised barrier it keeps at the same offset (with several plans stepping on their own streams that next
+      // CTA starts right away: one run in five of four concurrent 256 x 256 frames hung).  So the leader collects them.
+      for (int s = 0; s < 2; ++s) {
+        mbar_wait(&tempty_bar[ts], tphase ^ 1u);
+        if (++ts == 2) {
+          ts = 0;
+          tphase ^= 1u;
+        }
+      }
+    }
     if (dbg) {
       NST_DBG_PTR(p)[8] = wacc0;
       NST_DBG_PTR(p)[9] = wacc1;
@@ -877,7 +891,13 @@ static cudaError_t launch_one_t(const ConvParams& p, int num_sms, cudaStream_t s
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl) {
+  // A pair launch of a plan that shares the GPU with other plans' launches carries no programmatic-launch attribute
+  // (ConvParams::no_pdl_pair, nst_plan_set_shared_gpu): two chains of cluster launches, each released early by its
+  // predecessor, running beside each other on different streams hung about one run in four (four 256 x 256 frames in flight);
+  // without the attribute on the pairs - or without pairs, or without any programmatic launch - no run did.  A single
+  // chain keeps it: it is worth 5 % of the step (conv class 409 -> 461 us without).
+  static const bool pdl_pairs = getenv("NST_NO_PDL_PAIR") == nullptr;
+  if (pdl && (!PAIR || (pdl_pairs && !p.no_pdl_pair))) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

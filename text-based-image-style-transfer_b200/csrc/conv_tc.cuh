@@ -69,6 +69,8 @@ struct ConvParams {
   int b_per_image;   // != 0: tmB (CONV_SCALE) / tmB2 (folded Gram backward) hold one [N][K] matrix per image in their third dimension
   int pair;        // != 0: the launch runs as CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): conv_use_pair; set BEFORE
                    // make_tmap_wgt (the weight box is half an N tile) and conv_finalize_params (instruction descriptor)
+  int no_pdl_pair; // != 0: a pair launch is issued without the programmatic-dependent-launch attribute (plans that step beside other
+                   // plans on the same GPU: nst_plan_set_shared_gpu)
   int dual_issue;  // != 0: one-slice layers with resident weights are issued by two threads (conv_tc.cu); NST_SINGLE_ISSUE clears it
   // ---- CONV_FWD
   const float* bias;   // [N]

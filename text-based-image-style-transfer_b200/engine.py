@@ -111,6 +111,11 @@ class Plan:
     def bytes(self) -> int:
         return int(self.lib.nst_plan_bytes(self.handle))
 
+    def set_shared_gpu(self, shared: bool = True):
+        """Mark a plan that steps at the same time as other plans on this GPU (own host thread / stream): its CTA-pair launches
+        are then not chained by programmatic dependent launch (nst_plan_set_shared_gpu).  nst_run_frames_host does it itself."""
+        check(self.lib.nst_plan_set_shared_gpu(self.handle, 1 if shared else 0))
+
     # -- forward
     def _img(self, x: torch.Tensor) -> torch.Tensor:
         x = _f32c(x, self.device)

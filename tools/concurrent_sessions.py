@@ -33,6 +33,8 @@ for size in args.sizes.split(","):
         for k in range(K):
             s = rst.StyleTransferSession(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], device=dev, style_targets=targets, **synth.APP_WEIGHTS)
             targets = s.style_targets
+            if K > 1:
+                s.plan.set_shared_gpu(True)   # several chains of pair launches side by side: no programmatic launch on them
             content = torch.from_numpy(synth.synth_image(H, W, 100 + k)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
             s.prepare(content, None, False, trace_capacity=0)
             sessions.append(s)
