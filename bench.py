@@ -376,7 +376,7 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
                      % (n_frames, W, H, steps, evals))
 
 
-def bench_batched_small_frames(dev, synth, size=256, n_frames=32, steps=60):
+def bench_batched_small_frames(dev, synth, size=256, n_frames=32, steps=60, with_concurrent=False):
     """SURVEY 8f row 2 in front of the driver: small frames (C1's 256 x 256), several per LAUNCH - the batch dimension inside the
     tcgen05 convolution / Gram kernels (FrameStyler(batch=B) -> nst_run_batch_host) - beside one frame at a time and
     several frames in flight on separate plans / streams (FrameStyler(concurrent=K)).  Every frame is a whole
@@ -388,7 +388,10 @@ def bench_batched_small_frames(dev, synth, size=256, n_frames=32, steps=60):
     style = torch.from_numpy(synth.synth_image(512, 512, 1)).permute(2, 0, 1).float().div(255).unsqueeze(0).to(dev)
     frames = torch.stack([torch.from_numpy(synth.synth_image(size, size, 200 + k)) for k in range(n_frames)])
     rows = {}
-    for name, kw in (("one_at_a_time", {}), ("concurrent_4", dict(concurrent=4)), ("batch_4", dict(batch=4)), ("batch_8", dict(batch=8))):
+    configs = [("one_at_a_time", {}), ("batch_4", dict(batch=4)), ("batch_8", dict(batch=8))]
+    if with_concurrent:   # four plans / streams / graphs in lock step (--batch-row-concurrent; profiles/r03_bench_default.json has the row)
+        configs.insert(1, ("concurrent_4", dict(concurrent=4)))
+    for name, kw in configs:
         styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (size, size), [style], num_steps=steps, device=dev, **kw, **synth.APP_WEIGHTS)
         try:
             styler.process_block(frames[:8])
@@ -410,7 +413,8 @@ def bench_batched_small_frames(dev, synth, size=256, n_frames=32, steps=60):
                 h2d_bytes_per_frame=3 * size * size, d2h_bytes_per_frame=3 * size * size,
                 what="%d synthetic %dx%d frames, one shared 512x512 style, num_steps=%d (%d evaluations per frame), host uint8 in / out; "
                      "`value` = 8 frames per launch (nst_batch_create: batch dimension inside conv_tc_kernel / gram_partial_kernel); rows: "
-                     "one frame at a time, 4 frames in flight on 4 plans / streams, 4 and 8 frames per launch; best of 2 repetitions"
+                     "one frame at a time, 4 and 8 frames per launch (--batch-row-concurrent adds 4 frames in flight on 4 plans / streams: "
+                     "5 187 evaluations/s in profiles/r03_bench_default.json); best of 2 repetitions"
                      % (n_frames, size, size, steps, evals))
 
 
@@ -700,7 +704,7 @@ def run_b200(args, rank, world, local_rank):
     mask_row = assemble_row = mip_row = batch_row = None
     if world == 1:
         if not args.no_batch_row:
-            batch_row = bench_batched_small_frames(dev, synth)
+            batch_row = bench_batched_small_frames(dev, synth, with_concurrent=args.batch_row_concurrent)
         mask_row = bench_mask_composite(dev, pk)
         assemble_row = bench_video_assemble(dev, pk)
         mip_row = bench_mip(dev, pk)
@@ -846,6 +850,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager-on-GPU timing of the reference algorithm")
     ap.add_argument("--no-batch-row", action="store_true", help="skip the `batched_small_frames` row (256x256 frames, several per launch)")
+    ap.add_argument("--batch-row-concurrent", action="store_true", help="`batched_small_frames` row: also time four frames in flight on four plans / streams")
     ap.add_argument("--no-video-row", action="store_true", help="skip the 720p frame-sharded `video` row of the default workload")
     ap.add_argument("--video-row-frames", type=int, default=64, help="`video` row: total 720p frames, the same at every N (strong scaling)")
     ap.add_argument("--video-row-batch", type=int, default=2, help="`video` row: frames per launch on every GPU (FrameStyler(batch=B)); 1 = one at a time")
