@@ -334,9 +334,10 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
     t_setup = time.perf_counter()
     # two frames per launch (nst_batch_create: batch dimension inside the convolution / Gram kernels): +3 % at 720p, where one
     # frame already fills the GPU (profiles/README.md); --video-row-batch 1 = one frame at a time
-    styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=steps, device=dev, batch=args.video_row_batch,
+    row_batch = args.video_row_batch if (H % 16 == 0 and W % 16 == 0 and args.video_row_batch > 1) else 1   # batches need sides that are multiples of 16
+    styler = video.FrameStyler(synth.VGG_MEAN, synth.VGG_STD, (H, W), [style], num_steps=steps, device=dev, batch=row_batch,
                                **synth.APP_WEIGHTS)
-    styler.process_block(frames[:max(1, args.video_row_batch)])   # warm-up: graph capture, allocator, pinned buffers
+    styler.process_block(frames[:max(1, row_batch)])   # warm-up: graph capture, allocator, pinned buffers
     lo, hi = video.shard_range(n_frames, world, rank)
     video.gather_frames(frames[lo:hi].to(dev), n_frames, dev)    # ... and the communicator / buffers of the all-gather (same sizes)
     torch.cuda.synchronize()
@@ -369,7 +370,7 @@ def video_strong_scaling(args, rank, world, dev, dist, hf, synth):
                 frames=n_frames, frames_per_rank=hi - lo, n_gpus=world, num_steps=steps, evals_per_frame=evals, seconds=dt,
                 slowest_rank_compute_s=compute, gather_s_rank0=gather, setup_s_untimed=setup_s, evals_per_s=n_frames * evals / dt,
                 scaling="strong", h2d_bytes_per_frame=3 * H * W, d2h_bytes_per_frame=3 * H * W, checksum=checksum,
-                frames_per_launch=args.video_row_batch,
+                frames_per_launch=row_batch,
                 what="%d synthetic %dx%d frames in total at every N (strong scaling), one shared 512x512 style, num_steps=%d (%d evaluations per "
                      "frame; the reference UI uses 240 frames x num_steps=400), contiguous frame blocks per rank, NCCL broadcast of the style Gram "
                      "targets (untimed setup) + all-gather of the finished frames (timed); wall clock, barrier on both sides, max over ranks"
