@@ -10,6 +10,7 @@ the style Gram targets and the per-resolution plan alive across calls (the refer
 per call, app.py:794-798).
 """
 import contextlib
+import threading
 from typing import List, Optional
 
 import numpy as np
@@ -201,6 +202,9 @@ class StyleTransferSession:
         self.plan.close()
 
 
+_RUN_LOCK = threading.RLock()
+
+
 def run_multi_style_transfer(vgg_mean, vgg_std, content_img, num_steps, random_init, w_style, w_content, w_tv,
                              w_edge, style_img1, style_img2=None, style_img_weight=0.5, print_iter=50,
                              channel_attention=False, device="cpu"):
@@ -221,20 +225,24 @@ def run_multi_style_transfer(vgg_mean, vgg_std, content_img, num_steps, random_i
         raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (3) at non-singleton "
                            "dimension 1" % content.shape[1])               # normalize() broadcast error of the reference
 
-    session = StyleTransferSession(vgg_mean, vgg_std, content.shape[2:], styles, w_style, w_content, w_tv, w_edge,
-                                   style_img_weight, dev)
-    try:
-        if random_init:
-            x0 = torch.randn(content.size(), device=dev)                   # :84
-        else:
-            x0 = None                                                      # :87 content.clone()
-        print("Channel attention enabled: " + str(channel_attention))      # :92
-        evals = 20 * (int(num_steps) // 20 + 1)
-        session.prepare(content, x0, channel_attention, trace_capacity=evals + 32)
-        session.run(int(num_steps), print_iter)
-        out = session.result()
-    finally:
-        session.close()
+    # One optimisation at a time per process: the reference is not re-entrant either (it reseeds the global generators, :52),
+    # and two chains of launches stepping side by side on one GPU need nst_plan_set_shared_gpu - callers
+    # that want several images at once use video.FrameStyler(batch= / concurrent=).
+    with _RUN_LOCK:
+        session = StyleTransferSession(vgg_mean, vgg_std, content.shape[2:], styles, w_style, w_content, w_tv, w_edge,
+                                       style_img_weight, dev)
+        try:
+            if random_init:
+                x0 = torch.randn(content.size(), device=dev)                   # :84
+            else:
+                x0 = None                                                      # :87 content.clone()
+            print("Channel attention enabled: " + str(channel_attention))      # :92
+            evals = 20 * (int(num_steps) // 20 + 1)
+            session.prepare(content, x0, channel_attention, trace_capacity=evals + 32)
+            session.run(int(num_steps), print_iter)
+            out = session.result()
+        finally:
+            session.close()
     return tensor_to_PIL(out[0])                                           # :157
 
 
