@@ -2080,8 +2080,10 @@ extern "C" int nst_run_frames_host(nst_plan* const* plans, int count, const uint
   int guard[MAX_FRAMES];
   memset(st, 0, sizeof(st));
   memset(guard, 0, sizeof(guard));
+#ifndef NST_EXP_NO_SHARED   // experiment builds only
   if (count > 1)
     for (int k = 0; k < count; ++k) CKI(nst_plan_set_shared_gpu(plans[k], 1));   // several chains of pair launches side by side
+#endif
   for (int k = 0; k < count; ++k)
     CKI(frame_begin(plans[k], content_u8[k], num_steps, channel_attention, ca_w1, ca_w2, static_cast<cudaStream_t>(streams[k])));
   for (;;) {

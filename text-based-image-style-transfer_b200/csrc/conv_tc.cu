@@ -333,7 +333,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, PAIR, MODE>::NUM_THREADS, 1) 
         // The peer never issues an MMA: it releases the dependent launch here, when its last load is on its way (the leader's
         // MMA thread, which comes later, decides).  Then both producers stay until every stage they filled has been released:
         // the leader's commits arrive at this CTA's barriers, which must still exist.
+#ifndef NST_EXP_LATE_TRIGGER   // experiment builds only (profiles/r03_concurrent_plans_hang.log): dependents released at CTA exit
         if (cta_rank != 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
         for (int s = 0; s < Cfg::HALO_STAGES; ++s) {
           mbar_wait(&aempty_bar[as], aphase ^ 1u);
           if (++as == Cfg::HALO_STAGES) {
@@ -515,6 +517,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, PAIR, MODE>::NUM_THREADS, 1) 
         tphase ^= 1u;
       }
     }
+#ifdef NST_EXP_LATE_TRIGGER
+    if constexpr (!PAIR)
+#endif
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if constexpr (PAIR) {
       // The peer's epilogue warps release the accumulator stages of the last tiles with REMOTE arrivals on this CTA's
