@@ -62,6 +62,9 @@ def test_library_contains_blackwell_tensor_core_code(built_libs):
     assert "UTCHMMA" in sass      # tcgen05.mma
     assert "UTMALDG" in sass      # TMA tensor loads
     assert "LDTM" in sass         # tcgen05.ld
+    assert "UTCHMMA.2CTA" in sass             # tcgen05.mma.cta_group::2: the convolutions run as CTA pairs
+    assert "UTCBAR.2CTA.MULTICAST" in sass    # tcgen05.commit to the barriers of both CTAs of a pair
+    assert "UTMALDG.4D.2CTA" in sass          # a pair CTA's patch load completing on the leader's barrier
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", built_libs[0]], stdout=subprocess.PIPE, text=True).stdout
 
 
