@@ -42,7 +42,7 @@ def env_int(name, default):
 
 
 def _ncu_summary_name():
-    for name in ("r02b_ncu_full_conv_tc_summary.csv", "r02_ncu_full_conv_tc_summary.csv", "r01d_ncu_full_conv_tc_summary.csv"):
+    for name in ("r03_ncu_full_conv_tc_summary.csv", "r02b_ncu_full_conv_tc_summary.csv", "r02_ncu_full_conv_tc_summary.csv", "r01d_ncu_full_conv_tc_summary.csv"):
         if os.path.exists(os.path.join(ROOT, "profiles", name)):
             return name
     return "r02_ncu_full_conv_tc_summary.csv"
